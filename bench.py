@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- secp256k1 verifies/sec of the go-ibft message-verification hot path on N B200s (one process per GPU).
+
+A "step" is one pass of the hot path over one batch: the 10k-validator COMMIT round of SURVEY.md §8(d) config 3
+(10,000 committed seals + 10,000 COMMIT sender signatures, 1 % adversarial, weighted voting power) replicated to
+ITEMS_PER_GPU = 2^20 packed tuples per GPU (128 MiB of tuples: larger than the 126 MB L2, so no flush is needed between
+iterations).  Every step runs: K1+K2 recover kernel over the rank's shard -> (N>1: one NCCL all-gather of the
+pass/fail bitmap words) -> K3 quorum kernels over the complete bitmap.
+
+  value   whole-job verifies/s with the tuples resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e     the same metric through the host-buffer C-ABI call (ibft_verify_batch): H2D of the tuples and D2H of the
+          bitmap + quorum results inside the timed region
+  roofline  integer-issue roofline: verifies/s x 5.0e5 IMAD-class instructions / measured IMAD peak
+  cpu_baseline / --impl reference   the C oracle (a port; the Go reference has no crypto and no toolchain here) on the
+          box's host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ITEMS_PER_GPU = 1 << 20
+ALGO_IMAD_PER_VERIFY = 5.0e5      # 2.5e5 MAC32 = 5.0e5 mad.lo+mad.hi class instructions
+ALGO_BYTES_PER_VERIFY = 128 + 133 / 2 + 1 / 8  # packed tuple + payload bytes (half the items hash a 133-byte payload) + 1 bit
+
+
+def load_workload():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "config3.npz"))
+    return d
+
+
+def tile_items(items: np.ndarray, n: int) -> np.ndarray:
+    reps = (n + len(items) - 1) // len(items)
+    return np.ascontiguousarray(np.tile(items, reps)[:n])
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(s[3 + k].lower().startswith("active") for s in self.samples)]
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.samples)}
+
+
+def cpu_baseline(d, items, n_threads: int, target_seconds: float = 12.0):
+    """Times the C oracle (oracle/liboracle.so, kind "port") on a bounded sample of the same workload."""
+    from oracle import coracle as co
+    co.lib()
+    arena = d["arena"].tobytes()
+    gt = [0] * len(d["groups"])
+    probe = items[: max(64, 8 * n_threads)]
+    t0 = time.perf_counter()
+    co.verify_batch(probe, arena, tables=[d["addrs"]], group_table=gt, n_threads=n_threads)
+    rate = len(probe) / (time.perf_counter() - t0)
+    n = int(min(len(items), max(len(probe), rate * target_seconds)))
+    sample = items[:n]
+    t0 = time.perf_counter()
+    bm = co.verify_batch(sample, arena, tables=[d["addrs"]], group_table=gt, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return n / dt, n, bm
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  go-ibft verifies serially and delegates the
+    arithmetic to the embedder (no crypto in the tree, no Go toolchain on the box), so this arm times the oracle port with
+    all host threads -- the "goroutine-parallel CPU verify" the north star asks for."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d = load_workload()
+    items = np.ascontiguousarray(d["items"]).view(_item_dtype()).reshape(-1)
+    cores = os.cpu_count() or 1
+    from oracle import coracle as co
+    arena = d["arena"].tobytes()
+    gt = [0] * len(d["groups"])
+    sample_n = min(len(items), max(256, cores * 40))
+    sample = items[:sample_n]
+    for _ in range(args.warmup):
+        co.verify_batch(sample[: max(64, cores)], arena, tables=[d["addrs"]], group_table=gt, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        co.verify_batch(sample, arena, tables=[d["addrs"]], group_table=gt, n_threads=cores)
+    dt = time.perf_counter() - t0
+    v = sample_n * args.steps / dt
+    line = {"impl": "reference", "metric": "secp256k1_verifies_per_sec", "value": v, "unit": "verifies/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 (256-bit modular integer)", "data": "synthetic",
+            "config": workload_config(args.gpus), "gpu_launches": 0,
+            "cpu_baseline": {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample_n} items of the config-3 batch per step (bounded sample), C oracle, {cores} threads"},
+            "e2e": {"value": v, "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def _item_dtype():
+    import ibft_b200 as ib
+    return ib.ITEM_DTYPE
+
+
+def workload_config(n_gpus):
+    return {"workload": "config3: 10k-validator COMMIT round (10,000 committed seals + 10,000 COMMIT sender signatures, weighted "
+                        "voting power, 1% adversarial) replicated to 2^20 packed tuples per GPU",
+            "items_per_gpu": ITEMS_PER_GPU, "global_items": ITEMS_PER_GPU * n_gpus, "validators": 10000,
+            "parallelism": f"shard{n_gpus}+bitmap-allgather" if n_gpus > 1 else "single",
+            "l2": "inputs (128 MiB of tuples per GPU) exceed the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ibft_b200 as ib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    d = load_workload()
+    base_items = np.ascontiguousarray(d["items"]).view(ib.ITEM_DTYPE).reshape(-1)
+    n_local = ITEMS_PER_GPU
+    n_global = n_local * n_gpus
+    lo, hi = rank * n_local, (rank + 1) * n_local
+
+    eng = ib.Engine(device=local_rank, max_items=n_local, max_payload_bytes=max(1 << 22, len(d["arena"])), max_groups=8,
+                    max_table_slots=2, max_validators=16384)
+    eng.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+    groups = np.zeros(len(d["groups"]), dtype=ib.GROUP_DTYPE)
+    eng.bind_groups(groups)
+
+    # ---- device-resident inputs (every rank holds the global tuple array: the quorum kernels read every signer)
+    host_global = tile_items(base_items, n_global)
+    t_items = torch.from_numpy(host_global.view(np.uint8).reshape(-1, 128)).cuda()
+    t_arena = torch.from_numpy(np.ascontiguousarray(d["arena"])).cuda()
+    words_local = n_local // 32
+    t_bitmap = torch.zeros(n_global // 32, dtype=torch.int32, device="cuda")
+    t_results = torch.zeros(len(groups) * ib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()  # a real (non-default) stream: the C ABI launches on exactly this one
+    torch.cuda.set_stream(stream)
+
+    def step():
+        eng.verify_device(t_items.data_ptr(), n_global, t_arena.data_ptr(), t_arena.numel(), lo, hi, t_bitmap.data_ptr(), 0,
+                          stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(t_bitmap, t_bitmap[rank * words_local:(rank + 1) * words_local])
+        eng.quorum_reduce_device(t_items.data_ptr(), n_global, t_bitmap.data_ptr(), len(groups), t_results.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    # correctness of the timed configuration: bitmap must equal the replicated golden bitmap
+    golden_bits = np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(base_items)]
+    got_bits = np.unpackbits(t_bitmap.cpu().numpy().view(np.uint8), bitorder="little")[: n_global]
+    reps = (n_global + len(base_items) - 1) // len(base_items)
+    if not np.array_equal(got_bits, np.tile(golden_bits, reps)[:n_global]):
+        raise SystemExit("bench: verdict bitmap differs from the golden bitmap -- refusing to report a number")
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_k = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record(stream)
+    for i in range(args.steps):
+        ev_k[i][0].record(stream)
+        eng.verify_device(t_items.data_ptr(), n_global, t_arena.data_ptr(), t_arena.numel(), lo, hi, t_bitmap.data_ptr(), 0, stream.cuda_stream)
+        ev_k[i][1].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(t_bitmap, t_bitmap[rank * words_local:(rank + 1) * words_local])
+        eng.quorum_reduce_device(t_items.data_ptr(), n_global, t_bitmap.data_ptr(), len(groups), t_results.data_ptr(), stream.cuda_stream)
+    ev1.record(stream)
+    barrier()
+    launches = eng.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    ms_kernel = sum(a.elapsed_time(b) for a, b in ev_k) / args.steps
+    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_kernel = float(t[0]), float(t[1])
+    if rank == 0:
+        time.sleep(0.2)
+        sampler.stop()
+    ms_per_step = ms_total / args.steps
+    value = n_global / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through ibft_verify_batch (H2D + kernels + D2H inside the timed region)
+    host_local = np.ascontiguousarray(host_global[lo:hi])
+    arena_host = np.ascontiguousarray(d["arena"])
+    e2e_steps = max(3, min(args.steps, 5))
+    eng.verify_batch(host_local, arena_host, groups)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        bm_local, res_local, _ = eng.verify_batch(host_local, arena_host, groups)
+        if world > 1:
+            tb = torch.from_numpy(bm_local.view(np.int32)).cuda()
+            full = torch.empty(n_global // 32, dtype=torch.int32, device="cuda")
+            dist.all_gather_into_tensor(full, tb)
+            full.cpu()
+    torch.cuda.synchronize()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = n_global * e2e_steps / float(e2e_dt[0])
+    h2d = host_local.nbytes + arena_host.nbytes + groups.nbytes
+    d2h = (n_local // 8) + len(groups) * ib.RESULT_DTYPE.itemsize
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- quorum latency of ONE 10k-validator COMMIT round (10,000 committed seals), host buffers in / bitmap + quorum out
+    seal_group = list(d["groups"]).index("COMMIT_SEAL")
+    seals = np.ascontiguousarray(base_items[base_items["group"] == seal_group])
+    lat = []
+    for i in range(args.latency_reps + 5):
+        t0 = time.perf_counter()
+        _, res, _ = eng.verify_batch(seals, b"", groups)
+        if i >= 5:
+            lat.append((time.perf_counter() - t0) * 1e6)
+    lat.sort()
+    # device-only (no H2D): same round, tuples resident
+    t_seals = torch.from_numpy(seals.view(np.uint8).reshape(-1, 128)).cuda()
+    nb = (len(seals) + 31) // 32
+    t_bm2 = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    lat_dev = []
+    for i in range(args.latency_reps + 5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        eng.verify_device(t_seals.data_ptr(), len(seals), 0, 0, 0, len(seals), t_bm2.data_ptr(), 0, stream.cuda_stream)
+        eng.quorum_reduce_device(t_seals.data_ptr(), len(seals), t_bm2.data_ptr(), len(groups), t_results.data_ptr(), stream.cuda_stream)
+        b.record(stream)
+        torch.cuda.synchronize()
+        if i >= 5:
+            lat_dev.append(a.elapsed_time(b) * 1e3)
+    lat_dev.sort()
+
+    imad_peak, wide_peak = eng.probe_int_peak()
+    info = eng.device_info()
+    kernel_rate = n_local / (ms_kernel * 1e-3)  # per GPU
+    achieved = kernel_rate * ALGO_IMAD_PER_VERIFY
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak_gbs, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        try:
+            pk = json.load(open(peaks_path))
+            hbm_peak_gbs, hbm_src = float(pk.get("hbm_gbs", hbm_peak_gbs)), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    hbm_gbs = kernel_rate * ALGO_BYTES_PER_VERIFY / 1e9
+    line = {
+        "metric": "secp256k1_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 (256-bit modular integer)", "data": "synthetic", "config": workload_config(n_gpus),
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "api": "ibft_verify_batch (host buffers -> pinned staging -> H2D -> kernels -> D2H bitmap + quorum)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "int32-imad-issue", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-class instr/s",
+                     "frac": achieved / imad_peak, "traffic": None,
+                     "kernel": "k_recover", "kernel_ms": ms_kernel, "kernel_verifies_per_s_per_gpu": kernel_rate,
+                     "algorithmic_instr_per_verify": ALGO_IMAD_PER_VERIFY,
+                     "peak_source": "dependent-free mad.lo.u32 probe on this GPU (ibft_probe_int_peak), measured live",
+                     "wide_mac_peak_per_s": wide_peak, "wide_mac_frac_at_2.5e5_mac_per_verify": kernel_rate * 2.5e5 / wide_peak,
+                     "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak_gbs, "frac": hbm_gbs / hbm_peak_gbs, "peak_source": hbm_src,
+                             "note": "reported only to show HBM is not the bound"},
+                     "kernel_regs": info["kernel_regs"], "kernel_smem_bytes": info["kernel_smem_bytes"]},
+        "quorum_latency_us": {"config": "10k-validator COMMIT round, 10,000 committed seals, host tuples -> bitmap+quorum on host",
+                              "reps": len(lat), "p50": lat[len(lat) // 2], "p95": lat[int(len(lat) * 0.95)],
+                              "device_only_p50": lat_dev[len(lat_dev) // 2], "device_only_p95": lat_dev[int(len(lat_dev) * 0.95)]},
+    }
+    if not args.no_cpu_baseline and n_gpus == 1:
+        cores = os.cpu_count() or 1
+        v, n_s, bm = cpu_baseline(d, base_items, cores)
+        v1, n1, _ = cpu_baseline(d, base_items, 1, target_seconds=3.0)
+        ok = np.array_equal(bm, d["bitmap"][: len(bm)]) if n_s == len(base_items) else True
+        line["cpu_baseline"] = {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port",
+                                "sample": f"first {n_s} items of the config-3 batch, C oracle (oracle/c/ibft_oracle.c), {cores} threads",
+                                "single_thread": v1, "matches_golden": bool(ok)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

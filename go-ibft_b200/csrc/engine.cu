@@ -1,0 +1,962 @@
+// engine.cu -- CUDA kernels (sm_100a) and the C ABI (include/ibft_verify.h) of the batched verification engine.
+//
+// Kernels (SURVEY.md §2.2 checklist):
+//   k_recover        K1+K2 fused: Keccak-256 of the payload / seal wrap, secp256k1 public-key recovery, address
+//                    derivation + compare with msg.From / seal.Signer, validator-set membership, warp-ballot of the
+//                    32 verdicts of a warp into one word of the pass/fail bitmap.
+//   k_quorum_mark /  K3: resolve every passing item's signer to its validator index and OR it into the group's voted
+//   k_quorum_reduce  set; then per group: distinct count, 320-bit weighted voting-power sum, >= quorum threshold
+//                    (reference core/validator_manager.go:77-96, :130-135).
+//   k_keccak_batch   hash-only batch for IsValidProposalHash (reference core/backend.go:50-51).
+// There is no CPU fallback anywhere in this file: without a CUDA device ibft_engine_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/ibft_verify.h"
+#include "verify_core.cuh"
+
+#include "secp_gtable.inc"
+
+using namespace ibft;
+
+static_assert(sizeof(ibft_sig_item) == 128, "packed item must be 128 bytes");
+static_assert(IBFT_GTABLE_WG == IBFT_WG, "regenerate secp_gtable.inc (tools/gen_tables.py) for this IBFT_WG");
+
+#define IBFT_BLOCK 128
+#define IBFT_ITEM_ROW_WORDS 33  // 128-byte item + 1 pad word: conflict-free per-thread reads from shared memory
+
+// ------------------------------------------------------------------------------------------------------------
+// device-side tables
+// ------------------------------------------------------------------------------------------------------------
+__device__ uint32_t g_gtable[24 * IBFT_GTAB_ENTRIES];  // filled from IBFT_GTABLE at engine creation
+
+struct slot_dev {
+  const uint32_t* keys;    // n x 6 words: address as 5 big-endian words (sorted ascending) + validator index
+  const uint64_t* powers;  // n x 4 little-endian limbs, validator-index order
+  uint64_t quorum[5];      // floor(2*total/3) + 1
+  uint32_t n;
+  uint32_t valid;
+};
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// binary search of a 20-byte address in a slot's sorted key table; returns validator index or -1
+__device__ int lookup_validator(const slot_dev& s, const uint8_t* addr) {
+  uint32_t a[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++)
+    a[i] = ((uint32_t)addr[4 * i] << 24) | ((uint32_t)addr[4 * i + 1] << 16) | ((uint32_t)addr[4 * i + 2] << 8) | addr[4 * i + 3];
+  int lo = 0, hi = (int)s.n - 1;
+  while (lo <= hi) {
+    int mid = (lo + hi) >> 1;
+    const uint32_t* k = s.keys + 6 * (size_t)mid;
+    int cmp = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      uint32_t kv = __ldg(k + i);
+      if (cmp == 0 && kv != a[i]) cmp = kv < a[i] ? -1 : 1;
+    }
+    if (cmp == 0) return (int)__ldg(k + 5);
+    if (cmp < 0) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1 + K2: recover kernel.  One thread per signature; a warp's 32 verdicts become one bitmap word.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IBFT_BLOCK)
+k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
+          uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
+          const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
+          uint8_t* __restrict__ recovered) {
+  __shared__ uint32_t s_gtab[24 * IBFT_GTAB_ENTRIES];
+  __shared__ uint32_t s_items[IBFT_BLOCK * IBFT_ITEM_ROW_WORDS];
+  const uint32_t tid = threadIdx.x;
+  // stage the generator window table (shared by every signature of the CTA)
+  for (uint32_t i = tid; i < 24 * IBFT_GTAB_ENTRIES; i += IBFT_BLOCK) s_gtab[i] = g_gtable[i];
+  // stage this CTA's 128 packed tuples with coalesced 16-byte loads
+  const uint32_t base = shard_lo + blockIdx.x * IBFT_BLOCK;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(items + base);
+    uint32_t avail = base < shard_hi ? min((uint32_t)IBFT_BLOCK, shard_hi - base) : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint32_t q = tid + k * IBFT_BLOCK;  // uint4 index within the CTA's 16 KB
+      uint32_t row = q >> 3, col = q & 7;
+      if (row < avail) {
+        uint4 v = __ldg(src + q);
+        uint32_t* d = s_items + row * IBFT_ITEM_ROW_WORDS + col * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t idx = base + tid;
+  bool ok = false;
+  if (idx < shard_hi) {
+    ibft_sig_item it;
+    {
+      uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+      const uint32_t* s = s_items + tid * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+      for (int i = 0; i < 32; i++) w[i] = s[i];
+    }
+    uint8_t z[32], addr[20];
+    bool have = item_digest(it, arena, arena_len, z);
+    gtab_view G{s_gtab};
+    bool rec = have && ecrecover_address(it.r, it.s, it.v, z, G, addr);
+    if (!rec) {
+#pragma unroll
+      for (int i = 0; i < 20; i++) addr[i] = 0;
+    }
+    ok = rec;
+#pragma unroll
+    for (int i = 0; i < 20; i++) ok = ok && (addr[i] == it.signer[i]);
+    // validator-set membership at the message's height (reference core/backend.go:44)
+    if (ok && groups != nullptr) {
+      if (it.group >= n_groups) {
+        ok = false;
+      } else {
+        uint32_t slot = groups[it.group].table_slot;
+        if (slot != IBFT_NO_TABLE) {
+          if (slot >= n_slots || !slots[slot].valid) ok = false;
+          else ok = lookup_validator(slots[slot], it.signer) >= 0;
+        }
+      }
+    }
+    if (recovered != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 20; i++) recovered[(size_t)idx * 20 + i] = addr[i];
+    }
+  }
+  // warp-ballot reduction of the 32 verdicts into one bitmap word (shard bounds are multiples of 32)
+  uint32_t word = __ballot_sync(0xFFFFFFFFu, ok);
+  if ((tid & 31) == 0 && idx < shard_hi) bitmap[idx >> 5] = word;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3: quorum
+// ------------------------------------------------------------------------------------------------------------
+struct group_dev {
+  uint32_t voted_off;  // word offset of the group's voted set
+  uint32_t n_words;
+};
+
+__global__ void k_quorum_mark(const ibft_sig_item* __restrict__ items, uint32_t n, const uint32_t* __restrict__ bitmap,
+                              const ibft_group_desc* __restrict__ groups, const group_dev* __restrict__ gdev,
+                              uint32_t n_groups, const slot_dev* __restrict__ slots, uint32_t n_slots,
+                              uint32_t* __restrict__ voted, uint32_t* __restrict__ n_valid) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!((bitmap[i >> 5] >> (i & 31)) & 1u)) return;
+  const ibft_sig_item* it = items + i;
+  uint32_t g = it->group;
+  if (g >= n_groups) return;
+  atomicAdd(&n_valid[g], 1u);
+  uint32_t slot = groups[g].table_slot;
+  if (slot == IBFT_NO_TABLE || slot >= n_slots || !slots[slot].valid) return;
+  uint8_t addr[20];
+#pragma unroll
+  for (int k = 0; k < 20; k++) addr[k] = it->signer[k];
+  int v = lookup_validator(slots[slot], addr);
+  if (v >= 0) atomicOr(&voted[gdev[g].voted_off + ((uint32_t)v >> 5)], 1u << (v & 31));
+}
+
+// one CTA per group: 320-bit sum of the voting power of the voted validators, compared with the threshold
+__global__ void __launch_bounds__(256)
+k_quorum_reduce(const ibft_group_desc* __restrict__ groups, const group_dev* __restrict__ gdev, uint32_t n_groups,
+                const slot_dev* __restrict__ slots, uint32_t n_slots, const uint32_t* __restrict__ voted,
+                const uint32_t* __restrict__ n_valid, ibft_group_result* __restrict__ results) {
+  __shared__ uint64_t s_sum[256][5];
+  __shared__ uint32_t s_cnt[256];
+  uint32_t g = blockIdx.x;
+  if (g >= n_groups) return;
+  uint32_t slot = groups[g].table_slot;
+  bool has_table = slot != IBFT_NO_TABLE && slot < n_slots && slots[slot].valid;
+  uint64_t acc[5] = {0, 0, 0, 0, 0};
+  uint32_t cnt = 0;
+  if (has_table) {
+    const slot_dev& s = slots[slot];
+    const uint32_t* vw = voted + gdev[g].voted_off;
+    for (uint32_t v = threadIdx.x; v < s.n; v += blockDim.x) {
+      if ((vw[v >> 5] >> (v & 31)) & 1u) {
+        cnt++;
+        const uint64_t* p = s.powers + 4 * (size_t)v;
+        unsigned long long c = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          unsigned long long add = k < 4 ? p[k] : 0ull;
+          unsigned long long t = acc[k] + add;
+          unsigned long long c1 = t < add;
+          unsigned long long t2 = t + c;
+          c1 += t2 < c;
+          acc[k] = t2;
+          c = c1;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; k++) s_sum[threadIdx.x][k] = acc[k];
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (uint32_t stride = blockDim.x >> 1; stride > 0; stride >>= 1) {
+    if (threadIdx.x < stride) {
+      unsigned long long c = 0;
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        unsigned long long a = s_sum[threadIdx.x][k], b = s_sum[threadIdx.x + stride][k];
+        unsigned long long t = a + b;
+        unsigned long long c1 = t < b;
+        unsigned long long t2 = t + c;
+        c1 += t2 < c;
+        s_sum[threadIdx.x][k] = t2;
+        c = c1;
+      }
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + stride];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    ibft_group_result r;
+#pragma unroll
+    for (int k = 0; k < 5; k++) r.power[k] = s_sum[0][k];
+    r.n_valid = n_valid[g];
+    r.n_distinct = s_cnt[0];
+    r.has_quorum = 0;
+    r.reserved = 0;
+    if (has_table) {
+      // power >= quorum ?
+      int cmp = 0;
+      for (int k = 4; k >= 0; k--) {
+        uint64_t q = slots[slot].quorum[k];
+        if (cmp == 0 && r.power[k] != q) cmp = r.power[k] < q ? -1 : 1;
+      }
+      r.has_quorum = cmp >= 0 ? 1u : 0u;
+    }
+    results[g] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// hash-only batch (IsValidProposalHash)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_keccak_batch(const uint8_t* __restrict__ arena, size_t arena_len, const uint32_t* __restrict__ offs,
+                               const uint32_t* __restrict__ lens, uint32_t n, uint8_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t h[32];
+  if ((size_t)offs[i] + lens[i] > arena_len) {
+#pragma unroll
+    for (int k = 0; k < 32; k++) h[k] = 0;
+  } else {
+    keccak256_bytes(arena + offs[i], lens[i], h);
+  }
+#pragma unroll
+  for (int k = 0; k < 32; k++) out[(size_t)i * 32 + k] = h[k];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// primitive parity hooks + integer-pipe probes
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_debug_op(int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint32_t n, uint8_t* out,
+                           uint32_t stride) {
+  __shared__ uint32_t s_gtab[24 * IBFT_GTAB_ENTRIES];
+  for (uint32_t i = threadIdx.x; i < 24 * IBFT_GTAB_ENTRIES; i += blockDim.x) s_gtab[i] = g_gtable[i];
+  __syncthreads();
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* pa = a + 32 * (size_t)i;
+  const uint8_t* pb = b ? b + 32 * (size_t)i : pa;
+  uint8_t* o = out + (size_t)stride * i;
+  switch (op) {
+    case IBFT_DBG_FE_MUL: fe_to_be(fe_normalize(fe_mul(fe_from_be(pa), fe_from_be(pb))), o); break;
+    case IBFT_DBG_FE_SQR: fe_to_be(fe_normalize(fe_sqr(fe_from_be(pa))), o); break;
+    case IBFT_DBG_FE_INV: fe_to_be(fe_normalize(IBFT_FE_INV(fe_from_be(pa))), o); break;
+    case IBFT_DBG_FE_SQRT: fe_to_be(fe_normalize(fe_sqrt_candidate(fe_from_be(pa))), o); break;
+    case IBFT_DBG_FE_ADD: fe_to_be(fe_normalize(fe_add(fe_from_be(pa), fe_from_be(pb))), o); break;
+    case IBFT_DBG_FE_SUB: fe_to_be(fe_normalize(fe_sub(fe_from_be(pa), fe_from_be(pb))), o); break;
+    case IBFT_DBG_SC_MUL: sc_to_be(sc_mul(sc_from_be(pa), sc_from_be(pb)), o); break;
+    case IBFT_DBG_SC_INV: sc_to_be(IBFT_SC_INV(sc_reduce_once(sc_from_be(pa))), o); break;
+    case IBFT_DBG_GLV: {
+      glv_half h1, h2;
+      glv_split(sc_reduce_once(sc_from_be(pa)), h1, h2);
+      for (int k = 0; k < 64; k++) o[k] = 0;
+      for (int k = 0; k < 5; k++)
+        for (int j = 0; j < 4; j++) {
+          o[4 * k + j] = (uint8_t)(h1.k[k] >> (8 * j));
+          o[24 + 4 * k + j] = (uint8_t)(h2.k[k] >> (8 * j));
+        }
+      o[20] = h1.neg;
+      o[44] = h2.neg;
+      break;
+    }
+    case IBFT_DBG_ECMULT: {
+      gtab_view G{s_gtab};
+      const uint8_t* pc = c + 64 * (size_t)i;
+      aff P;
+      P.x = fe_from_be(pc);
+      P.y = fe_from_be(pc + 32);
+      jac Q = ecmult_double(sc_reduce_once(sc_from_be(pa)), sc_reduce_once(sc_from_be(pb)), P, G);
+      for (int k = 0; k < 64; k++) o[k] = 0;
+      if (!(Q.inf || fe_is_zero(Q.z))) {
+        fe zi = IBFT_FE_INV(Q.z), zi2 = fe_sqr(zi);
+        fe_to_be(fe_normalize(fe_mul(Q.x, zi2)), o);
+        fe_to_be(fe_normalize(fe_mul(Q.y, fe_mul(zi2, zi))), o + 32);
+      }
+      break;
+    }
+    default: break;
+  }
+}
+
+#define PROBE_ITERS 2048
+#define PROBE_UNROLL 16
+__global__ void k_probe_imad(uint32_t* out, uint32_t a, uint32_t b) {
+  uint32_t x[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = threadIdx.x + k;
+  for (int i = 0; i < PROBE_ITERS; i++) {
+#pragma unroll
+    for (int u = 0; u < PROBE_UNROLL; u++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0,%0,%1,%2;" : "+r"(x[k]) : "r"(a), "r"(b));
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s ^= x[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_probe_wide(uint32_t* out, uint32_t a, uint32_t b) {
+  uint32_t x[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[k][j] = threadIdx.x + k + j;
+  for (int i = 0; i < PROBE_ITERS; i++) {
+#pragma unroll
+    for (int u = 0; u < PROBE_UNROLL / 4; u++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        asm volatile(
+            "mad.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1;"
+            "madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+            "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5;"
+            "madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.u32 %7,%8,%9,%7;"
+            : "+r"(x[k][0]), "+r"(x[k][1]), "+r"(x[k][2]), "+r"(x[k][3]), "+r"(x[k][4]), "+r"(x[k][5]), "+r"(x[k][6]),
+              "+r"(x[k][7])
+            : "r"(a), "r"(b));
+      }
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= x[k][j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side: engine object + C ABI
+// ------------------------------------------------------------------------------------------------------------
+static thread_local char tl_err[512] = "";
+static void set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_err, sizeof tl_err, fmt, ap);
+  va_end(ap);
+}
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t _e = (call);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__);              \
+      return IBFT_ERR_CUDA;                                                                             \
+    }                                                                                                   \
+  } while (0)
+
+struct slot_host {
+  bool valid = false;
+  uint64_t height = 0;
+  uint32_t n = 0;
+  uint32_t* d_keys = nullptr;
+  uint64_t* d_powers = nullptr;
+  uint64_t quorum[5] = {0, 0, 0, 0, 0};
+};
+
+struct pending_call {
+  bool active = false;
+  uint32_t n = 0, n_groups = 0;
+  uint32_t* bitmap_out = nullptr;
+  ibft_group_result* results_out = nullptr;
+  uint8_t* recovered_out = nullptr;
+};
+
+struct ibft_engine {
+  ibft_engine_params p;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done_ev = nullptr;
+  // device
+  ibft_sig_item* d_items = nullptr;
+  uint8_t* d_arena = nullptr;
+  uint32_t* d_bitmap = nullptr;
+  uint8_t* d_recovered = nullptr;
+  ibft_group_desc* d_groups = nullptr;
+  group_dev* d_gdev = nullptr;
+  ibft_group_result* d_results = nullptr;
+  uint32_t* d_voted = nullptr;
+  uint32_t* d_nvalid = nullptr;
+  slot_dev* d_slots = nullptr;
+  size_t voted_words_cap = 0;
+  // pinned host staging
+  ibft_sig_item* h_items = nullptr;
+  uint8_t* h_arena = nullptr;
+  uint32_t* h_bitmap = nullptr;
+  uint8_t* h_recovered = nullptr;
+  ibft_group_desc* h_groups = nullptr;
+  group_dev* h_gdev = nullptr;
+  ibft_group_result* h_results = nullptr;
+  std::vector<slot_host> slots;
+  std::vector<slot_dev> slots_shadow;
+  std::vector<group_dev> last_gdev;  // layout of the voted sets of the most recent reduce
+  std::vector<ibft_group_desc> last_groups;
+  pending_call pending;
+  uint64_t launches = 0;
+  cudaFuncAttributes recover_attr{};
+};
+
+extern "C" int ibft_abi_version(void) { return IBFT_ABI_VERSION; }
+extern "C" const char* ibft_last_error(void) { return tl_err; }
+
+static void engine_free(ibft_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->p.device);
+  for (auto& s : e->slots) {
+    if (s.d_keys) cudaFree(s.d_keys);
+    if (s.d_powers) cudaFree(s.d_powers);
+  }
+  cudaFree(e->d_items); cudaFree(e->d_arena); cudaFree(e->d_bitmap); cudaFree(e->d_recovered); cudaFree(e->d_groups);
+  cudaFree(e->d_gdev); cudaFree(e->d_results); cudaFree(e->d_voted); cudaFree(e->d_nvalid); cudaFree(e->d_slots);
+  cudaFreeHost(e->h_items); cudaFreeHost(e->h_arena); cudaFreeHost(e->h_bitmap); cudaFreeHost(e->h_recovered);
+  cudaFreeHost(e->h_groups); cudaFreeHost(e->h_gdev); cudaFreeHost(e->h_results);
+  if (e->done_ev) cudaEventDestroy(e->done_ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+static int engine_alloc(ibft_engine* e) {
+  const ibft_engine_params& p = e->p;
+  CU(cudaSetDevice(p.device));
+  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&e->done_ev, cudaEventDisableTiming));
+  size_t n = p.max_items, words = (n + 31) / 32;
+  CU(cudaMalloc(&e->d_items, n * sizeof(ibft_sig_item)));
+  CU(cudaMalloc(&e->d_arena, std::max<size_t>(p.max_payload_bytes, 16)));
+  CU(cudaMalloc(&e->d_bitmap, std::max<size_t>(words, 1) * 4));
+  CU(cudaMalloc(&e->d_recovered, n * 20));
+  CU(cudaMalloc(&e->d_groups, (size_t)p.max_groups * sizeof(ibft_group_desc)));
+  CU(cudaMalloc(&e->d_gdev, (size_t)p.max_groups * sizeof(group_dev)));
+  CU(cudaMalloc(&e->d_results, (size_t)p.max_groups * sizeof(ibft_group_result)));
+  e->voted_words_cap = (size_t)p.max_groups * ((p.max_validators + 31) / 32);
+  CU(cudaMalloc(&e->d_voted, std::max<size_t>(e->voted_words_cap, 1) * 4));
+  CU(cudaMalloc(&e->d_nvalid, (size_t)p.max_groups * 4));
+  CU(cudaMalloc(&e->d_slots, (size_t)p.max_table_slots * sizeof(slot_dev)));
+  CU(cudaMemset(e->d_slots, 0, (size_t)p.max_table_slots * sizeof(slot_dev)));
+  CU(cudaHostAlloc(&e->h_items, n * sizeof(ibft_sig_item), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&e->h_arena, std::max<size_t>(p.max_payload_bytes, 16), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&e->h_bitmap, std::max<size_t>(words, 1) * 4, cudaHostAllocDefault));
+  CU(cudaHostAlloc(&e->h_recovered, n * 20, cudaHostAllocDefault));
+  CU(cudaHostAlloc(&e->h_groups, (size_t)p.max_groups * sizeof(ibft_group_desc), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&e->h_gdev, (size_t)p.max_groups * sizeof(group_dev), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&e->h_results, (size_t)p.max_groups * sizeof(ibft_group_result), cudaHostAllocDefault));
+  e->slots.resize(p.max_table_slots);
+  e->slots_shadow.assign(p.max_table_slots, slot_dev{});
+  CU(cudaMemcpyToSymbol(g_gtable, IBFT_GTABLE, sizeof(uint32_t) * 24 * IBFT_GTAB_ENTRIES));
+  CU(cudaFuncGetAttributes(&e->recover_attr, k_recover));
+  CU(cudaDeviceSynchronize());
+  return IBFT_OK;
+}
+
+extern "C" int ibft_engine_create(const ibft_engine_params* params, ibft_engine** out) {
+  if (!params || !out) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count <= 0) {
+    set_err("no CUDA device available (%s): this engine has no CPU fallback", ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    return IBFT_ERR_NO_DEVICE;
+  }
+  if (params->device < 0 || params->device >= count || params->max_items == 0 || params->max_groups == 0 ||
+      params->max_groups > 65535 || params->max_table_slots == 0 || params->max_table_slots > 65535) {
+    set_err("invalid engine parameters");
+    return IBFT_ERR_INVALID_ARG;
+  }
+  ibft_engine* e = new ibft_engine();
+  e->p = *params;
+  e->p.max_items = (e->p.max_items + 31u) & ~31u;
+  int rc = engine_alloc(e);
+  if (rc != IBFT_OK) { engine_free(e); return rc; }
+  *out = e;
+  return IBFT_OK;
+}
+
+extern "C" void ibft_engine_destroy(ibft_engine* e) { engine_free(e); }
+
+extern "C" int ibft_engine_device_info(ibft_engine* e, ibft_device_info* out) {
+  if (!e || !out) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, e->p.device));
+  memset(out, 0, sizeof *out);
+  snprintf(out->name, sizeof out->name, "%s", prop.name);
+  out->sm_count = prop.multiProcessorCount;
+  out->cc_major = prop.major;
+  out->cc_minor = prop.minor;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->p.device);
+  out->clock_khz = khz;
+  out->total_mem = prop.totalGlobalMem;
+  out->abi_version = IBFT_ABI_VERSION;
+  out->kernel_regs = e->recover_attr.numRegs;
+  out->kernel_smem_bytes = (int32_t)e->recover_attr.sharedSizeBytes;
+  out->block_threads = IBFT_BLOCK;
+  return IBFT_OK;
+}
+
+// 256-bit big-endian -> 4 little-endian u64 limbs
+static void be32_to_limbs(const uint8_t* b, uint64_t l[4]) {
+  for (int i = 0; i < 4; i++) {
+    uint64_t w = 0;
+    for (int j = 0; j < 8; j++) w = (w << 8) | b[(3 - i) * 8 + j];
+    l[i] = w;
+  }
+}
+
+extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t height, const uint8_t* addrs,
+                                   const uint8_t* powers_be, uint32_t n) {
+  if (!e || (!addrs && n)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  if (table_slot >= e->p.max_table_slots) { set_err("table slot %u out of range", table_slot); return IBFT_ERR_INVALID_ARG; }
+  if (n > e->p.max_validators) { set_err("validator table of %u exceeds capacity %u", n, e->p.max_validators); return IBFT_ERR_CAPACITY; }
+  // total voting power and quorum = floor(2*total/3) + 1 in 320-bit arithmetic (validator_manager.go:130-135)
+  std::vector<uint64_t> powers((size_t)n * 4);
+  uint64_t total[5] = {0, 0, 0, 0, 0};
+  for (uint32_t i = 0; i < n; i++) {
+    uint64_t l[4] = {1, 0, 0, 0};
+    if (powers_be) be32_to_limbs(powers_be + 32 * (size_t)i, l);
+    memcpy(&powers[4 * (size_t)i], l, sizeof l);
+    unsigned __int128 c = 0;
+    for (int k = 0; k < 5; k++) {
+      c += (unsigned __int128)total[k] + (k < 4 ? l[k] : 0);
+      total[k] = (uint64_t)c;
+      c >>= 64;
+    }
+  }
+  if ((total[0] | total[1] | total[2] | total[3] | total[4]) == 0) {
+    set_err("total voting power is zero or less");
+    return IBFT_ERR_VOTING_POWER;
+  }
+  uint64_t twice[6] = {0, 0, 0, 0, 0, 0};
+  {
+    uint64_t c = 0;
+    for (int k = 0; k < 5; k++) { twice[k] = (total[k] << 1) | c; c = total[k] >> 63; }
+    twice[5] = c;
+  }
+  uint64_t q[6];
+  {
+    unsigned __int128 rem = 0;
+    for (int k = 5; k >= 0; k--) {
+      unsigned __int128 cur = (rem << 64) | twice[k];
+      q[k] = (uint64_t)(cur / 3);
+      rem = cur % 3;
+    }
+    unsigned __int128 c = 1;
+    for (int k = 0; k < 6; k++) { c += q[k]; q[k] = (uint64_t)c; c >>= 64; }
+  }
+  // sorted key table: 5 big-endian words + validator index
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    int c = memcmp(addrs + 20 * (size_t)a, addrs + 20 * (size_t)b, 20);
+    return c != 0 ? c < 0 : a < b;
+  });
+  std::vector<uint32_t> keys((size_t)n * 6);
+  for (uint32_t r = 0; r < n; r++) {
+    const uint8_t* a = addrs + 20 * (size_t)order[r];
+    for (int w = 0; w < 5; w++)
+      keys[6 * (size_t)r + w] = ((uint32_t)a[4 * w] << 24) | ((uint32_t)a[4 * w + 1] << 16) | ((uint32_t)a[4 * w + 2] << 8) | a[4 * w + 3];
+    keys[6 * (size_t)r + 5] = order[r];
+  }
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->p.device));
+  slot_host& s = e->slots[table_slot];
+  CU(cudaStreamSynchronize(e->stream));
+  if (s.d_keys) { cudaFree(s.d_keys); s.d_keys = nullptr; }
+  if (s.d_powers) { cudaFree(s.d_powers); s.d_powers = nullptr; }
+  s.valid = false;
+  CU(cudaMalloc(&s.d_keys, std::max<size_t>(keys.size(), 6) * 4));
+  CU(cudaMalloc(&s.d_powers, std::max<size_t>(powers.size(), 4) * 8));
+  if (n) {
+    CU(cudaMemcpy(s.d_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s.d_powers, powers.data(), powers.size() * 8, cudaMemcpyHostToDevice));
+  }
+  s.n = n;
+  s.height = height;
+  memcpy(s.quorum, q, sizeof s.quorum);
+  s.valid = true;
+  slot_dev sd{};
+  sd.keys = s.d_keys;
+  sd.powers = s.d_powers;
+  memcpy(sd.quorum, q, sizeof sd.quorum);
+  sd.n = n;
+  sd.valid = 1;
+  e->slots_shadow[table_slot] = sd;
+  CU(cudaMemcpy(e->d_slots + table_slot, &sd, sizeof sd, cudaMemcpyHostToDevice));
+  return IBFT_OK;
+}
+
+extern "C" int ibft_get_quorum(ibft_engine* e, uint32_t table_slot, uint64_t quorum_out[5], uint64_t* height_out,
+                               uint32_t* n_out) {
+  if (!e || table_slot >= e->p.max_table_slots) { set_err("bad slot"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  const slot_host& s = e->slots[table_slot];
+  if (!s.valid) { set_err("slot %u not set", table_slot); return IBFT_ERR_NO_TABLE; }
+  if (quorum_out) memcpy(quorum_out, s.quorum, sizeof s.quorum);
+  if (height_out) *height_out = s.height;
+  if (n_out) *n_out = s.n;
+  return IBFT_OK;
+}
+
+// lay out the voted sets of the call's groups; validates table slots
+static int plan_groups(ibft_engine* e, const ibft_group_desc* groups, uint32_t n_groups, group_dev* gdev, size_t* total_words) {
+  size_t off = 0;
+  for (uint32_t g = 0; g < n_groups; g++) {
+    uint32_t slot = groups[g].table_slot;
+    uint32_t nw = 0;
+    if (slot != IBFT_NO_TABLE) {
+      if (slot >= e->p.max_table_slots || !e->slots[slot].valid) {
+        set_err("group %u references validator-table slot %u which is not set", g, slot);
+        return IBFT_ERR_NO_TABLE;
+      }
+      nw = (e->slots[slot].n + 31) / 32;
+    }
+    gdev[g].voted_off = (uint32_t)off;
+    gdev[g].n_words = nw;
+    off += nw;
+  }
+  if (off > e->voted_words_cap) { set_err("voted sets of the call exceed capacity"); return IBFT_ERR_CAPACITY; }
+  *total_words = off;
+  return IBFT_OK;
+}
+
+static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len,
+                          uint32_t lo, uint32_t hi, const ibft_group_desc* d_groups, uint32_t n_groups, uint32_t* d_bitmap,
+                          uint8_t* d_recovered, cudaStream_t st) {
+  if (hi <= lo) return IBFT_OK;
+  uint32_t blocks = (hi - lo + IBFT_BLOCK - 1) / IBFT_BLOCK;
+  k_recover<<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+                                           e->p.max_table_slots, d_bitmap, d_recovered);
+  e->launches++;
+  CU(cudaGetLastError());
+  return IBFT_OK;
+}
+
+static int launch_quorum(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint32_t* d_bitmap,
+                         const ibft_group_desc* d_groups, const group_dev* d_gdev, uint32_t n_groups, size_t voted_words,
+                         ibft_group_result* d_results, cudaStream_t st) {
+  if (n_groups == 0) return IBFT_OK;
+  CU(cudaMemsetAsync(e->d_voted, 0, std::max<size_t>(voted_words, 1) * 4, st));
+  CU(cudaMemsetAsync(e->d_nvalid, 0, (size_t)n_groups * 4, st));
+  if (n) {
+    k_quorum_mark<<<(n + 255) / 256, 256, 0, st>>>(d_items, n, d_bitmap, d_groups, d_gdev, n_groups, e->d_slots,
+                                                    e->p.max_table_slots, e->d_voted, e->d_nvalid);
+    e->launches++;
+    CU(cudaGetLastError());
+  }
+  k_quorum_reduce<<<n_groups, 256, 0, st>>>(d_groups, d_gdev, n_groups, e->d_slots, e->p.max_table_slots, e->d_voted,
+                                            e->d_nvalid, d_results);
+  e->launches++;
+  CU(cudaGetLastError());
+  return IBFT_OK;
+}
+
+static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
+                         const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
+                         ibft_group_result* results_out, uint8_t* recovered_out) {
+  if (e->pending.active) { set_err("a submitted call is still pending; wait for it first"); return IBFT_ERR_INVALID_ARG; }
+  if ((n && !items) || (n && !bitmap_out) || (arena_len && !arena) || (n_groups && !groups)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  if (n > e->p.max_items || arena_len > e->p.max_payload_bytes || n_groups > e->p.max_groups) {
+    set_err("batch (%u items, %zu payload bytes, %u groups) exceeds engine capacity (%u, %u, %u)", n, arena_len, n_groups,
+            e->p.max_items, e->p.max_payload_bytes, e->p.max_groups);
+    return IBFT_ERR_CAPACITY;
+  }
+  CU(cudaSetDevice(e->p.device));
+  size_t voted_words = 0;
+  if (n_groups) {
+    int rc = plan_groups(e, groups, n_groups, e->h_gdev, &voted_words);
+    if (rc != IBFT_OK) return rc;
+    memcpy(e->h_groups, groups, (size_t)n_groups * sizeof(ibft_group_desc));
+    e->last_gdev.assign(e->h_gdev, e->h_gdev + n_groups);
+    e->last_groups.assign(groups, groups + n_groups);
+  } else {
+    e->last_gdev.clear();
+    e->last_groups.clear();
+  }
+  cudaStream_t st = e->stream;
+  if (n) {
+    memcpy(e->h_items, items, (size_t)n * sizeof(ibft_sig_item));
+    CU(cudaMemcpyAsync(e->d_items, e->h_items, (size_t)n * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, st));
+  }
+  if (arena_len) {
+    memcpy(e->h_arena, arena, arena_len);
+    CU(cudaMemcpyAsync(e->d_arena, e->h_arena, arena_len, cudaMemcpyHostToDevice, st));
+  }
+  if (n_groups) {
+    CU(cudaMemcpyAsync(e->d_groups, e->h_groups, (size_t)n_groups * sizeof(ibft_group_desc), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->d_gdev, e->h_gdev, (size_t)n_groups * sizeof(group_dev), cudaMemcpyHostToDevice, st));
+  }
+  uint32_t padded = (n + 31u) & ~31u;
+  (void)padded;
+  int rc = launch_recover(e, e->d_items, n, e->d_arena, arena_len, 0, n, n_groups ? e->d_groups : nullptr, n_groups,
+                          e->d_bitmap, recovered_out ? e->d_recovered : nullptr, st);
+  if (rc != IBFT_OK) return rc;
+  if (n_groups && results_out) {
+    rc = launch_quorum(e, e->d_items, n, e->d_bitmap, e->d_groups, e->d_gdev, n_groups, voted_words, e->d_results, st);
+    if (rc != IBFT_OK) return rc;
+    CU(cudaMemcpyAsync(e->h_results, e->d_results, (size_t)n_groups * sizeof(ibft_group_result), cudaMemcpyDeviceToHost, st));
+  }
+  if (n) {
+    CU(cudaMemcpyAsync(e->h_bitmap, e->d_bitmap, (size_t)((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+    if (recovered_out) CU(cudaMemcpyAsync(e->h_recovered, e->d_recovered, (size_t)n * 20, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaEventRecord(e->done_ev, st));
+  e->pending.active = true;
+  e->pending.n = n;
+  e->pending.n_groups = (n_groups && results_out) ? n_groups : 0;
+  e->pending.bitmap_out = bitmap_out;
+  e->pending.results_out = results_out;
+  e->pending.recovered_out = recovered_out;
+  return IBFT_OK;
+}
+
+static int wait_locked(ibft_engine* e) {
+  if (!e->pending.active) { set_err("no submitted call to wait for"); return IBFT_ERR_INVALID_ARG; }
+  CU(cudaSetDevice(e->p.device));
+  cudaError_t ce = cudaEventSynchronize(e->done_ev);
+  pending_call pc = e->pending;
+  e->pending.active = false;
+  if (ce != cudaSuccess) {
+    // launch/execution failure: NO verdict is produced (outputs untouched) -- never `true`
+    set_err("device execution failed: %s", cudaGetErrorString(ce));
+    return IBFT_ERR_CUDA;
+  }
+  if (pc.n) {
+    size_t words = (pc.n + 31) / 32;
+    memcpy(pc.bitmap_out, e->h_bitmap, words * 4);
+    if (pc.n & 31) pc.bitmap_out[words - 1] &= (1u << (pc.n & 31)) - 1u;
+    if (pc.recovered_out) memcpy(pc.recovered_out, e->h_recovered, (size_t)pc.n * 20);
+  }
+  if (pc.n_groups) memcpy(pc.results_out, e->h_results, (size_t)pc.n_groups * sizeof(ibft_group_result));
+  return IBFT_OK;
+}
+
+extern "C" int ibft_verify_batch(ibft_engine* e, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
+                                 const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
+                                 ibft_group_result* results_out, uint8_t* recovered_out) {
+  if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  int rc = submit_locked(e, items, n, arena, arena_len, groups, n_groups, bitmap_out, results_out, recovered_out);
+  if (rc != IBFT_OK) return rc;
+  return wait_locked(e);
+}
+
+extern "C" int ibft_verify_submit(ibft_engine* e, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
+                                  const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
+                                  ibft_group_result* results_out, uint8_t* recovered_out) {
+  if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  return submit_locked(e, items, n, arena, arena_len, groups, n_groups, bitmap_out, results_out, recovered_out);
+}
+
+extern "C" int ibft_verify_poll(ibft_engine* e, int* done) {
+  if (!e || !done) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->pending.active) { *done = 1; return IBFT_OK; }
+  CU(cudaSetDevice(e->p.device));
+  cudaError_t ce = cudaEventQuery(e->done_ev);
+  if (ce == cudaSuccess) { *done = 1; return IBFT_OK; }
+  if (ce == cudaErrorNotReady) { *done = 0; return IBFT_OK; }
+  set_err("device execution failed: %s", cudaGetErrorString(ce));
+  return IBFT_ERR_CUDA;
+}
+
+extern "C" int ibft_verify_wait(ibft_engine* e) {
+  if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  return wait_locked(e);
+}
+
+extern "C" int ibft_verify_batch_device(ibft_engine* e, const void* d_items, uint32_t n, const void* d_arena, size_t arena_len,
+                                        uint32_t shard_lo, uint32_t shard_hi, void* d_bitmap, void* d_recovered, void* stream) {
+  if (!e || (n && (!d_items || !d_bitmap))) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  if (shard_hi > n || shard_lo > shard_hi || (shard_lo & 31) || ((shard_hi & 31) && shard_hi != n)) {
+    set_err("shard [%u,%u) of %u must be 32-aligned", shard_lo, shard_hi, n);
+    return IBFT_ERR_INVALID_ARG;
+  }
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  // membership is applied by ibft_quorum_reduce_device / the host mirror in this mode when no groups are bound
+  return launch_recover(e, (const ibft_sig_item*)d_items, n, (const uint8_t*)d_arena, arena_len, shard_lo, shard_hi,
+                        e->last_groups.empty() ? nullptr : e->d_groups, (uint32_t)e->last_groups.size(), (uint32_t*)d_bitmap,
+                        (uint8_t*)d_recovered, st);
+}
+
+// binds the groups used by the device-resident entry points (copied to the engine's device buffers)
+extern "C" int ibft_bind_groups(ibft_engine* e, const ibft_group_desc* groups, uint32_t n_groups) {
+  if (!e || (n_groups && !groups)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  if (n_groups > e->p.max_groups) { set_err("too many groups"); return IBFT_ERR_CAPACITY; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->p.device));
+  size_t voted_words = 0;
+  if (n_groups) {
+    int rc = plan_groups(e, groups, n_groups, e->h_gdev, &voted_words);
+    if (rc != IBFT_OK) return rc;
+    memcpy(e->h_groups, groups, (size_t)n_groups * sizeof(ibft_group_desc));
+    CU(cudaMemcpy(e->d_groups, e->h_groups, (size_t)n_groups * sizeof(ibft_group_desc), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_gdev, e->h_gdev, (size_t)n_groups * sizeof(group_dev), cudaMemcpyHostToDevice));
+    e->last_gdev.assign(e->h_gdev, e->h_gdev + n_groups);
+    e->last_groups.assign(groups, groups + n_groups);
+  } else {
+    e->last_gdev.clear();
+    e->last_groups.clear();
+  }
+  return IBFT_OK;
+}
+
+extern "C" int ibft_quorum_reduce_device(ibft_engine* e, const void* d_items, uint32_t n, const void* d_bitmap,
+                                         const void* d_groups, uint32_t n_groups, void* d_results, void* stream) {
+  if (!e || !d_results || (n && (!d_items || !d_bitmap))) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (n_groups != e->last_groups.size()) { set_err("call ibft_bind_groups with the same groups first"); return IBFT_ERR_INVALID_ARG; }
+  (void)d_groups;  // the bound copy is authoritative (its voted-set layout was planned on the host)
+  CU(cudaSetDevice(e->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  size_t voted_words = 0;
+  for (auto& g : e->last_gdev) voted_words += g.n_words;
+  return launch_quorum(e, (const ibft_sig_item*)d_items, n, (const uint32_t*)d_bitmap, e->d_groups, e->d_gdev, n_groups,
+                       voted_words, (ibft_group_result*)d_results, st);
+}
+
+extern "C" int ibft_get_voted_bitmap(ibft_engine* e, uint32_t group, uint32_t* words_out, uint32_t n_words) {
+  if (!e || !words_out) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (group >= e->last_gdev.size()) { set_err("group %u not part of the last call", group); return IBFT_ERR_INVALID_ARG; }
+  const group_dev& g = e->last_gdev[group];
+  if (n_words < g.n_words) { set_err("need %u words", g.n_words); return IBFT_ERR_CAPACITY; }
+  CU(cudaSetDevice(e->p.device));
+  CU(cudaStreamSynchronize(e->stream));
+  if (g.n_words) CU(cudaMemcpy(words_out, e->d_voted + g.voted_off, (size_t)g.n_words * 4, cudaMemcpyDeviceToHost));
+  for (uint32_t i = g.n_words; i < n_words; i++) words_out[i] = 0;
+  return IBFT_OK;
+}
+
+extern "C" int ibft_keccak256_batch(ibft_engine* e, const uint8_t* arena, size_t arena_len, const uint32_t* offsets,
+                                    const uint32_t* lens, uint32_t n, uint8_t* out32) {
+  if (!e || (n && (!offsets || !lens || !out32)) || (arena_len && !arena)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  if (n == 0) return IBFT_OK;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->p.device));
+  uint8_t *d_a = nullptr, *d_o = nullptr;
+  uint32_t *d_off = nullptr, *d_len = nullptr;
+  int rc = IBFT_OK;
+  cudaError_t ce;
+#define CUK(call) if ((ce = (call)) != cudaSuccess) { set_err("%s failed: %s", #call, cudaGetErrorString(ce)); rc = IBFT_ERR_CUDA; goto done; }
+  CUK(cudaMalloc(&d_a, std::max<size_t>(arena_len, 16)));
+  CUK(cudaMalloc(&d_o, (size_t)n * 32));
+  CUK(cudaMalloc(&d_off, (size_t)n * 4));
+  CUK(cudaMalloc(&d_len, (size_t)n * 4));
+  if (arena_len) CUK(cudaMemcpyAsync(d_a, arena, arena_len, cudaMemcpyHostToDevice, e->stream));
+  CUK(cudaMemcpyAsync(d_off, offsets, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  CUK(cudaMemcpyAsync(d_len, lens, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+  k_keccak_batch<<<(n + 127) / 128, 128, 0, e->stream>>>(d_a, arena_len, d_off, d_len, n, d_o);
+  e->launches++;
+  CUK(cudaGetLastError());
+  CUK(cudaMemcpyAsync(out32, d_o, (size_t)n * 32, cudaMemcpyDeviceToHost, e->stream));
+  CUK(cudaStreamSynchronize(e->stream));
+done:
+#undef CUK
+  cudaFree(d_a); cudaFree(d_o); cudaFree(d_off); cudaFree(d_len);
+  return rc;
+}
+
+extern "C" uint64_t ibft_engine_launch_count(ibft_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int ibft_probe_int_peak(ibft_engine* e, double* imad_per_s, double* wide_mac_per_s) {
+  if (!e || !imad_per_s || !wide_mac_per_s) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->p.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, e->p.device));
+  int blocks = prop.multiProcessorCount * 8, threads = 256;
+  uint32_t* d_out = nullptr;
+  CU(cudaMalloc(&d_out, (size_t)blocks * threads * 4));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best[2] = {0, 0};
+  for (int which = 0; which < 2; which++) {
+    for (int rep = 0; rep < 4; rep++) {
+      CU(cudaEventRecord(e0, e->stream));
+      if (which == 0) k_probe_imad<<<blocks, threads, 0, e->stream>>>(d_out, 3, 5);
+      else k_probe_wide<<<blocks, threads, 0, e->stream>>>(d_out, 3, 5);
+      CU(cudaEventRecord(e1, e->stream));
+      CU(cudaEventSynchronize(e1));
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, e0, e1));
+      double instr = (double)PROBE_ITERS * PROBE_UNROLL * (which == 0 ? 8 : 4) * (double)blocks * threads;
+      double rate = instr / (ms * 1e-3);
+      if (rep > 0 && rate > best[which]) best[which] = rate;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *imad_per_s = best[0];
+  *wide_mac_per_s = best[1];
+  return IBFT_OK;
+}
+
+extern "C" int ibft_debug_op(ibft_engine* e, int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint32_t n,
+                             uint8_t* out, uint32_t out_stride) {
+  if (!e || !a || !out || n == 0) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->p.device));
+  uint8_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_o = nullptr;
+  int rc = IBFT_OK;
+  cudaError_t ce;
+#define CUK(call) if ((ce = (call)) != cudaSuccess) { set_err("%s failed: %s", #call, cudaGetErrorString(ce)); rc = IBFT_ERR_CUDA; goto done; }
+  CUK(cudaMalloc(&d_a, (size_t)n * 32));
+  CUK(cudaMemcpy(d_a, a, (size_t)n * 32, cudaMemcpyHostToDevice));
+  if (b) { CUK(cudaMalloc(&d_b, (size_t)n * 32)); CUK(cudaMemcpy(d_b, b, (size_t)n * 32, cudaMemcpyHostToDevice)); }
+  if (c) { CUK(cudaMalloc(&d_c, (size_t)n * 64)); CUK(cudaMemcpy(d_c, c, (size_t)n * 64, cudaMemcpyHostToDevice)); }
+  CUK(cudaMalloc(&d_o, (size_t)n * out_stride));
+  CUK(cudaMemset(d_o, 0, (size_t)n * out_stride));
+  k_debug_op<<<(n + 63) / 64, 64, 0, e->stream>>>(op, d_a, d_b, d_c, n, d_o, out_stride);
+  e->launches++;
+  CUK(cudaGetLastError());
+  CUK(cudaStreamSynchronize(e->stream));
+  CUK(cudaMemcpy(out, d_o, (size_t)n * out_stride, cudaMemcpyDeviceToHost));
+done:
+#undef CUK
+  cudaFree(d_a); cudaFree(d_b); cudaFree(d_c); cudaFree(d_o);
+  return rc;
+}

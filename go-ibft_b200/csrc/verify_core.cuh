@@ -1,0 +1,80 @@
+// verify_core.cuh -- one signature check: (r, s, v, z) -> recovered signer address.
+//
+// This is the arithmetic behind core.Verifier.IsValidValidator (reference core/backend.go:41-45; callers
+// core/ibft.go:735,1128,1213,1220) and core.Verifier.IsValidCommittedSeal (core/backend.go:53-55; caller
+// core/ibft.go:943).  Conventions are those of SURVEY.md §8(c) and oracle/secp256k1.py: SEC 1 v2 §4.1.6 recovery
+// with x = r only, 1 <= r,s < n, v in {0,1}, high-s accepted, address = Keccak-256(X||Y)[12:].
+#pragma once
+#include "../../include/ibft_verify.h"
+#include "keccak.cuh"
+#include "secp_ec.cuh"
+
+namespace ibft {
+
+#ifndef IBFT_FE_INV
+#define IBFT_FE_INV fe_inv_fermat
+#endif
+#ifndef IBFT_SC_INV
+#define IBFT_SC_INV sc_inv_fermat
+#endif
+
+// digest of one item (kinds of include/ibft_verify.h).  Returns false for an unknown kind / out-of-range payload.
+IBFT_HD bool item_digest(const ibft_sig_item& it, const uint8_t* arena, size_t arena_len, uint8_t* z) {
+  switch (it.kind) {
+    case IBFT_KIND_DIGEST:
+#pragma unroll
+      for (int i = 0; i < 32; i++) z[i] = it.digest[i];
+      return true;
+    case IBFT_KIND_PAYLOAD:
+      if ((size_t)it.payload_off + it.payload_len > arena_len) return false;
+      keccak256_bytes(arena + it.payload_off, it.payload_len, z);
+      return true;
+    case IBFT_KIND_SEAL: {
+      uint8_t buf[33];
+#pragma unroll
+      for (int i = 0; i < 32; i++) buf[i] = it.digest[i];
+      buf[32] = 0x02;  // proto.MessageType_COMMIT (reference messages/proto/messages.proto:10)
+      keccak256_bytes(buf, 33, z);
+      return true;
+    }
+    default:
+      return false;
+  }
+}
+
+// Recover the signer of (r, s, v) over digest z.  Returns false when the signature is invalid; addr20 then zero.
+IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t v, const uint8_t* z_be,
+                               const gtab_view& G, uint8_t* addr20) {
+#pragma unroll
+  for (int i = 0; i < 20; i++) addr20[i] = 0;
+  sc r = sc_from_be(r_be), s = sc_from_be(s_be);
+  if (v > 1) return false;
+  if (sc_is_zero(r) || sc_is_zero(s) || sc_ge_n(r) || sc_ge_n(s)) return false;
+  // R = lift_x(r, v)   (r < n < p: always a canonical field element)
+  fe x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x.v[i] = r.v[i];
+  fe y2 = fe_add(fe_mul(fe_sqr(x), x), fe_from_u32(7));
+  fe y = fe_sqrt_candidate(y2);
+  if (!fe_equal(fe_sqr(y), y2)) return false;  // x^3 + 7 is a non-residue: r is not an abscissa
+  y = fe_normalize(y);
+  if ((y.v[0] & 1u) != (uint32_t)v) y = fe_normalize(fe_neg(y));
+  aff R;
+  R.x = x;
+  R.y = y;
+  // u1 = -z/r, u2 = s/r  (mod n)
+  sc z = sc_reduce_once(sc_from_be(z_be));
+  sc rinv = IBFT_SC_INV(r);
+  sc u1 = sc_neg(sc_mul(z, rinv));
+  sc u2 = sc_mul(s, rinv);
+  jac Q = ecmult_double(u1, u2, R, G);
+  if (Q.inf || fe_is_zero(Q.z)) return false;
+  fe zi = IBFT_FE_INV(Q.z);
+  fe zi2 = fe_sqr(zi);
+  fe qx = fe_normalize(fe_mul(Q.x, zi2));
+  fe qy = fe_normalize(fe_mul(Q.y, fe_mul(zi2, zi)));
+  keccak256_xy_address(qx, qy, addr20);
+  return true;
+}
+
+}  // namespace ibft

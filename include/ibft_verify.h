@@ -145,6 +145,9 @@ int ibft_verify_submit(ibft_engine* e, const ibft_sig_item* items, uint32_t n, c
 int ibft_verify_poll(ibft_engine* e, int* done);
 int ibft_verify_wait(ibft_engine* e);
 
+/* Binds the groups (and plans their voted-set layout) used by the two device-resident entry points below. */
+int ibft_bind_groups(ibft_engine* e, const ibft_group_desc* groups, uint32_t n_groups);
+
 /* Device-resident variant: every pointer is a DEVICE pointer on the engine's device and `stream` is a
  * cudaStream_t passed as void* (NULL = engine stream).  Enqueues only; the caller synchronises the stream.
  * Sharding: only items [shard_lo, shard_hi) are verified and only their bitmap words are written (both must

@@ -1,0 +1,250 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and the committed golden fixtures."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import ibft_b200 as ib
+import workloads as wl
+from oracle import coracle as co
+from oracle import secp256k1 as ec
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_fixture(name):
+    d = np.load(os.path.join(HERE, "golden", name))
+    items = np.ascontiguousarray(d["items"]).view(ib.ITEM_DTYPE).reshape(-1)
+    return d, items
+
+
+def groups_for(n_groups, slot=0):
+    g = np.zeros(n_groups, dtype=ib.GROUP_DTYPE)
+    g["table_slot"] = slot
+    return g
+
+
+def expected_groups(items, bitmap, addrs, powers):
+    """Python big-int restatement of HasQuorum over the verdict bitmap (core/validator_manager.go:77-96, :130-135)."""
+    index = {bytes(a): i for i, a in enumerate(addrs)}
+    pw = [int.from_bytes(bytes(p), "big") for p in powers]
+    quorum = 2 * sum(pw) // 3 + 1
+    out = {}
+    for i in range(len(items)):
+        if (int(bitmap[i >> 5]) >> (i & 31)) & 1:
+            g = int(items[i]["group"])
+            s = out.setdefault(g, [0, set()])
+            s[0] += 1
+            s[1].add(index[bytes(items[i]["signer"])])
+    return {g: (nv, len(vs), sum(pw[v] for v in vs), sum(pw[v] for v in vs) >= quorum) for g, (nv, vs) in out.items()}, quorum
+
+
+@pytest.mark.parametrize("name", ["config2.npz", "config3.npz"])
+def test_fixture_bitmap_and_quorum_bit_exact(engine, name):
+    d, items = load_fixture(name)
+    engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+    ng = len(d["groups"])
+    bitmap, results, recovered = engine.verify_batch(items, d["arena"], groups_for(ng), want_recovered=True)
+    assert np.array_equal(bitmap, d["bitmap"]), "verdict bitmap differs from the oracle's golden bitmap"
+    # recompute the oracle live as well (guards against a stale fixture)
+    gt = [0] * ng
+    assert np.array_equal(bitmap, co.verify_batch(items, d["arena"].tobytes(), tables=[d["addrs"]], group_table=gt, n_threads=8))
+    exp, quorum = expected_groups(items, bitmap, d["addrs"], d["powers"])
+    q, h, n = engine.get_quorum(0)
+    assert (q, h, n) == (quorum, int(d["meta"][2]), len(d["addrs"]))
+    for g in range(ng):
+        nv, nd, power, hq = exp.get(g, (0, 0, 0, False))
+        r = results[g]
+        assert (int(r["n_valid"]), int(r["n_distinct"]), bool(r["has_quorum"])) == (nv, nd, hq)
+        assert sum(int(r["power"][k]) << (64 * k) for k in range(5)) == power
+        voted = engine.voted_bitmap(g, len(d["addrs"]))
+        assert sum(bin(int(w)).count("1") for w in voted) == nd
+    # recovered addresses: equal to the expected signer exactly where the signature itself verifies
+    for i in random.Random(1).sample(range(len(items)), 300):
+        it = items[i]
+        z = (d["arena"][int(it["payload_off"]):int(it["payload_off"]) + int(it["payload_len"])].tobytes() if it["kind"] == 1 else None)
+        dig = co.keccak256(z) if z is not None else wl.seal_digest(bytes(it["digest"])) if it["kind"] == 2 else bytes(it["digest"])
+        want = co.ecrecover_address(dig, bytes(it["r"]) + bytes(it["s"]) + bytes([int(it["v"])]))
+        assert bytes(recovered[i]) == (want or bytes(20))
+
+
+def test_quorum_threshold_edge(engine):
+    """Exactly quorum-1 / quorum valid seals of a 100-validator set; duplicates do not add power."""
+    vs = wl.ValidatorSet(7, 100, weighted=True)
+    ph = os.urandom(32)
+    sd = wl.seal_digest(ph)
+    total = sum(vs.powers)
+    quorum = 2 * total // 3 + 1
+    engine.set_validators(1, 5, vs.addr_array(), vs.power_array())
+    order = list(range(100))
+    acc, k = 0, 0
+    while acc < quorum:
+        acc += vs.powers[order[k]]
+        k += 1
+    for take, want in ((k - 1, False), (k, True)):
+        its = [wl.make_item(wl.sign(vs.keys[i], sd), vs.addrs[i], 2, ph, 0) for i in order[:take]]
+        its += [its[0].copy(), its[0].copy()]  # duplicate sender: counted once (HasQuorum works on an address set)
+        bitmap, results, _ = engine.verify_batch(np.concatenate(its), b"", groups_for(1, slot=1))
+        assert int(results[0]["n_valid"]) == take + 2 and int(results[0]["n_distinct"]) == take
+        assert bool(results[0]["has_quorum"]) == want
+        assert sum(int(results[0]["power"][j]) << (64 * j) for j in range(5)) == sum(vs.powers[i] for i in order[:take])
+
+
+def test_huge_voting_powers(engine):
+    """Arbitrary-precision powers (the reference uses big.Int): 2^200-scale values, exact threshold."""
+    vs = wl.ValidatorSet(8, 4)
+    powers = [2**200 + 5, 2**200, 2**199, 1]
+    pw = np.frombuffer(b"".join(p.to_bytes(32, "big") for p in powers), np.uint8).reshape(4, 32)
+    engine.set_validators(2, 9, vs.addr_array(), pw)
+    q, _, _ = engine.get_quorum(2)
+    assert q == 2 * sum(powers) // 3 + 1
+    ph = os.urandom(32)
+    sd = wl.seal_digest(ph)
+    for subset in ([0, 1], [0, 2, 3], [0, 1, 2], [1, 2, 3]):
+        its = np.concatenate([wl.make_item(wl.sign(vs.keys[i], sd), vs.addrs[i], 2, ph, 0) for i in subset])
+        _, results, _ = engine.verify_batch(its, b"", groups_for(1, slot=2))
+        s = sum(powers[i] for i in subset)
+        assert sum(int(results[0]["power"][j]) << (64 * j) for j in range(5)) == s
+        assert bool(results[0]["has_quorum"]) == (s >= q)
+
+
+def test_zero_total_power_rejected(engine):
+    vs = wl.ValidatorSet(9, 3)
+    with pytest.raises(ib.EngineError) as ei:
+        engine.set_validators(3, 1, vs.addr_array(), np.zeros((3, 32), np.uint8))
+    assert ei.value.code == 5  # errVotingPowerNotCorrect, core/validator_manager.go:66-68
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 127, 128, 129, 1000])
+def test_ragged_sizes(engine, n):
+    d, items = load_fixture("config2.npz")
+    engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+    sub = items[2000 - n // 2: 2000 - n // 2 + n].copy()  # straddles COMMIT sender sigs / seals
+    bitmap, _, _ = engine.verify_batch(sub, d["arena"], groups_for(len(d["groups"])))
+    want = co.verify_batch(sub, d["arena"].tobytes(), tables=[d["addrs"]], group_table=[0] * len(d["groups"]), n_threads=4)
+    assert np.array_equal(bitmap, want)
+
+
+def test_malformed_items_are_false_never_crash(engine):
+    vs = wl.ValidatorSet(10, 4)
+    engine.set_validators(4, 1, vs.addr_array(), None)
+    dig = os.urandom(32)
+    good = wl.make_item(wl.sign(vs.keys[0], dig), vs.addrs[0], 0, dig, 0)
+    bad_kind = good.copy(); bad_kind["kind"] = 77
+    invalid = good.copy(); invalid["kind"] = 255                      # host-flagged: nil seal / wrong signature length
+    oob = good.copy(); oob["kind"] = 1; oob["payload_off"] = 2**31; oob["payload_len"] = 100
+    bad_group = good.copy(); bad_group["group"] = 9
+    short_sig = wl.make_item(b"\x01" * 64, vs.addrs[0], 0, dig, 0)     # len != 65 -> KIND_INVALID
+    its = np.concatenate([good, bad_kind, invalid, oob, bad_group, short_sig, good])
+    bitmap, results, _ = engine.verify_batch(its, b"\x00" * 16, groups_for(1, slot=4))
+    assert int(bitmap[0]) == 0b1000001
+    assert int(results[0]["n_valid"]) == 2 and int(results[0]["n_distinct"]) == 1
+    # a group that references an unset table slot is an error, not a verdict
+    g = groups_for(1, slot=15)
+    with pytest.raises(ib.EngineError) as ei:
+        engine.verify_batch(its, b"", g)
+    assert ei.value.code == 6
+    # no table: membership skipped, pure recover+compare
+    g = groups_for(1, slot=ib.NO_TABLE)
+    outsider = wl.privkey(999, 0)
+    it2 = wl.make_item(wl.sign(outsider, dig), wl.address_of(outsider), 0, dig, 0)
+    bitmap, results, _ = engine.verify_batch(it2, b"", g)
+    assert int(bitmap[0]) == 1 and int(results[0]["has_quorum"]) == 0
+    # same item against a table it is not a member of
+    bitmap, _, _ = engine.verify_batch(it2, b"", groups_for(1, slot=4))
+    assert int(bitmap[0]) == 0
+
+
+def test_multiblock_payloads_and_keccak_batch(engine):
+    """PREPREPARE / ROUND_CHANGE payloads span many 136-byte blocks (up to 909 KB)."""
+    rnd = random.Random(3)
+    vs = wl.ValidatorSet(11, 3)
+    engine.set_validators(5, 1, vs.addr_array(), None)
+    sizes = [0, 1, 135, 136, 137, 271, 272, 273, 1095, 5000, 70000]
+    arena = bytearray()
+    its = []
+    msgs = []
+    for k, sz in enumerate(sizes):
+        payload = bytes(rnd.getrandbits(8) for _ in range(sz))
+        msgs.append(payload)
+        key = vs.keys[k % 3]
+        its.append(wl.make_item(wl.sign(key, co.keccak256(payload)), vs.addrs[k % 3], 1, b"", 0, len(arena), sz))
+        arena.extend(payload)
+    its = np.concatenate(its)
+    bitmap, _, _ = engine.verify_batch(its, bytes(arena), groups_for(1, slot=5))
+    assert int(bitmap[0]) == (1 << len(sizes)) - 1
+    assert engine.keccak256_batch(msgs) == [co.keccak256(m) for m in msgs]
+    assert engine.keccak256_batch([]) == []
+
+
+def test_async_submit_poll_wait(engine):
+    d, items = load_fixture("config2.npz")
+    engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+    groups = groups_for(len(d["groups"]))
+    bitmap = np.zeros((len(items) + 31) // 32, np.uint32)
+    results = np.zeros(len(groups), ib.RESULT_DTYPE)
+    arena = np.ascontiguousarray(d["arena"])
+    engine.verify_submit(items, arena, groups, bitmap, results)
+    with pytest.raises(ib.EngineError):
+        engine.verify_submit(items, arena, groups, bitmap, results)  # one call in flight per engine
+    while not engine.poll():
+        pass
+    engine.wait()
+    assert np.array_equal(bitmap, d["bitmap"])
+    assert engine.poll()
+
+
+def test_device_resident_and_sharded_path(engine):
+    """Device-pointer ABI with torch-owned memory: two 'ranks' verify disjoint 32-aligned shards, the bitmap words are
+    concatenated (what the NCCL all-gather does) and the quorum reduce runs on the complete bitmap."""
+    import torch
+    d, items = load_fixture("config2.npz")
+    engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+    n = len(items)
+    groups = groups_for(len(d["groups"]))
+    engine.bind_groups(groups)
+    t_items = torch.from_numpy(items.view(np.uint8).reshape(-1, 128).copy()).cuda()
+    t_arena = torch.from_numpy(np.ascontiguousarray(d["arena"]).copy()).cuda()
+    words = (n + 31) // 32
+    t_bitmap = torch.zeros(words, dtype=torch.int32, device="cuda")
+    t_results = torch.zeros(len(groups) * ib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    mid = (n // 2) & ~31
+    before = engine.launch_count()
+    engine.verify_device(t_items.data_ptr(), n, t_arena.data_ptr(), t_arena.numel(), 0, mid, t_bitmap.data_ptr(), 0, st)
+    engine.verify_device(t_items.data_ptr(), n, t_arena.data_ptr(), t_arena.numel(), mid, n, t_bitmap.data_ptr(), 0, st)
+    engine.quorum_reduce_device(t_items.data_ptr(), n, t_bitmap.data_ptr(), len(groups), t_results.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert engine.launch_count() - before == 4
+    got = t_bitmap.cpu().numpy().view(np.uint32)
+    if n & 31:
+        got[-1] &= (1 << (n & 31)) - 1
+    assert np.array_equal(got, d["bitmap"])
+    res = t_results.cpu().numpy().view(ib.RESULT_DTYPE)
+    exp, _ = expected_groups(items, got, d["addrs"], d["powers"])
+    for g in range(len(groups)):
+        assert int(res[g]["n_distinct"]) == exp[g][1] and bool(res[g]["has_quorum"]) == exp[g][3]
+    with pytest.raises(ib.EngineError):
+        engine.verify_device(t_items.data_ptr(), n, 0, 0, 5, n, t_bitmap.data_ptr())  # unaligned shard
+    engine.bind_groups(None)
+
+
+def test_replicated_large_batch_properties(engine):
+    """BASELINE-size property check (oracle too slow to replay 2^16 items every run): a replicated batch must give the
+    replicated bitmap, and permuting items permutes verdict bits."""
+    d, items = load_fixture("config3.npz")
+    engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+    reps = 3
+    big = np.tile(items, reps)
+    perm = np.random.default_rng(0).permutation(len(big))
+    groups = groups_for(len(d["groups"]))
+    bm, results, _ = engine.verify_batch(big[perm], d["arena"], groups)
+    bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[: len(big)]
+    want_bits = np.tile(np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(items)], reps)[perm]
+    assert np.array_equal(bits, want_bits)
+    # replication adds no voting power: distinct senders, not messages, are counted
+    exp, _ = expected_groups(items, d["bitmap"], d["addrs"], d["powers"])
+    for g in range(len(groups)):
+        assert int(results[g]["n_distinct"]) == exp[g][1] and int(results[g]["n_valid"]) == reps * exp[g][0]

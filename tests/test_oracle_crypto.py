@@ -1,0 +1,106 @@
+"""The oracle is pinned (as far as the reference allows -- it ships no crypto, see oracle/__init__.py) against
+independent known-answer vectors and against OpenSSL through the `cryptography` package."""
+import os
+import random
+
+import pytest
+
+from oracle import coracle as co
+from oracle import secp256k1 as ec
+from oracle.keccak import keccak256
+
+KATS = {
+    b"": "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470",
+    b"abc": "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45",
+    b"testing": "5f16f4c7f149ac4f9510d9cf8cf384038ad348b3bcdc01915f95de12df9d1b02",
+}
+
+
+@pytest.mark.parametrize("impl", [keccak256, co.keccak256])
+def test_keccak_kats(impl):
+    for msg, digest in KATS.items():
+        assert impl(msg).hex() == digest
+    # 0x01 padding, not SHA-3's 0x06
+    import hashlib
+    assert impl(b"abc") != hashlib.sha3_256(b"abc").digest()
+
+
+def test_keccak_c_vs_python_all_block_boundaries():
+    rnd = random.Random(5)
+    for n in list(range(0, 140)) + [271, 272, 273, 408, 1000, 4096]:
+        data = bytes(rnd.getrandbits(8) for _ in range(n))
+        assert co.keccak256(data) == keccak256(data)
+
+
+def test_privkey_one_is_generator_and_known_address():
+    assert ec.privkey_to_pubkey(1) == (ec.GX, ec.GY)
+    assert ec.privkey_to_address(1).hex() == "7e5f4552091a69125d5dfcb7b8c2659029395bdf"
+    assert co.keccak256(co.pubkey_from_scalar(1))[12:].hex() == "7e5f4552091a69125d5dfcb7b8c2659029395bdf"
+    # well known: privkey 2
+    assert ec.privkey_to_address(2).hex() == "2b5ad5c4795c026514f8317c7a215e218dccd6cf"
+
+
+def test_against_openssl_via_cryptography():
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import ec as cec
+    from cryptography.hazmat.primitives.asymmetric import utils
+    rnd = random.Random(11)
+    for _ in range(12):
+        d = rnd.getrandbits(256) % (ec.N - 1) + 1
+        dig = keccak256(rnd.getrandbits(400).to_bytes(50, "big"))
+        key = cec.derive_private_key(d, cec.SECP256K1())
+        nums = key.public_key().public_numbers()
+        assert (nums.x, nums.y) == ec.privkey_to_pubkey(d)
+        assert co.pubkey_from_scalar(d) == nums.x.to_bytes(32, "big") + nums.y.to_bytes(32, "big")
+        sig = ec.sign(d, dig)
+        r, s = int.from_bytes(sig[:32], "big"), int.from_bytes(sig[32:64], "big")
+        key.public_key().verify(utils.encode_dss_signature(r, s), dig, cec.ECDSA(utils.Prehashed(hashes.SHA256())))
+        # RFC 6979 nonce agrees with OpenSSL's deterministic signing
+        r2, s2 = utils.decode_dss_signature(key.sign(dig, cec.ECDSA(utils.Prehashed(hashes.SHA256()), deterministic_signing=True)))
+        assert r2 == r and s2 in (s, ec.N - s)
+        # an OpenSSL-made signature is recovered by both oracles (try both v)
+        sig_os = r2.to_bytes(32, "big") + s2.to_bytes(32, "big")
+        want = ec.pubkey_to_address((nums.x, nums.y))
+        got = {ec.ecrecover_address(dig, sig_os + bytes([v])) for v in (0, 1)}
+        assert want in got
+        assert {co.ecrecover_address(dig, sig_os + bytes([v])) for v in (0, 1)} == got
+
+
+def test_c_oracle_matches_python_oracle_on_valid_and_adversarial():
+    rnd = random.Random(2)
+    for i in range(40):
+        d = rnd.getrandbits(256) % (ec.N - 1) + 1
+        dig = keccak256(bytes([i]) * 7)
+        sig = co.sign_with_k(d, dig, ec.rfc6979_k(d, dig), low_s=bool(i & 1))
+        assert sig == ec.sign(d, dig, low_s=bool(i & 1))
+        addr = ec.privkey_to_address(d)
+        assert co.ecrecover_address(dig, sig) == addr == ec.ecrecover_address(dig, sig)
+        r, s, v = sig[:32], sig[32:64], sig[64]
+        s_int = int.from_bytes(s, "big")
+        variants = [
+            r + (ec.N - s_int).to_bytes(32, "big") + bytes([v ^ 1]),   # high-s twin: accepted, same signer
+            r + s + bytes([v ^ 1]),                                    # wrong parity: different signer
+            r + s + bytes([v + 2]), r + s + bytes([27 + v]),           # bad v
+            bytes(32) + s + bytes([v]), r + bytes(32) + bytes([v]),    # r = 0, s = 0
+            ec.N.to_bytes(32, "big") + s + bytes([v]), r + ec.N.to_bytes(32, "big") + bytes([v]),  # >= n
+            (ec.N - 1).to_bytes(32, "big") + s + bytes([v]),
+            b"\xff" * 32 + s + bytes([v]),
+            (5).to_bytes(32, "big") + s + bytes([v]),                  # x = 5: x^3+7 = 132 is a non-residue?
+        ]
+        assert co.ecrecover_address(dig, variants[0]) == addr
+        for var in variants:
+            assert co.ecrecover_address(dig, var) == ec.ecrecover_address(dig, var)
+    assert co.ecrecover_address(b"\x00" * 31, b"\x00" * 65) is None
+
+
+def test_recover_infinity_and_zero_digest():
+    # z = 0 (u1 = 0) is fine; Q = infinity must be rejected: choose R = G (r = Gx), s = r*k... construct via u1*G + u2*G = 0
+    r = ec.GX % ec.N
+    # pick s, z with  z = s (mod n)  =>  u1 = -s/r, u2 = s/r  => Q = (u2 - ... ) -> u1*G + u2*R = (-s/r + s/r) G = infinity when R = G
+    s = 12345
+    gy_par = ec.GY & 1
+    sig = r.to_bytes(32, "big") + s.to_bytes(32, "big") + bytes([gy_par])
+    dig = s.to_bytes(32, "big")
+    assert ec.ecrecover_address(dig, sig) is None
+    assert co.ecrecover_address(dig, sig) is None
+    assert co.ecrecover_address(bytes(32), sig) == ec.ecrecover_address(bytes(32), sig) is not None
