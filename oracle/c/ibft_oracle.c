@@ -161,22 +161,41 @@ static u256 fp_mul(const u256* a, const u256* b) {
   return r;
 }
 static u256 fp_sqr(const u256* a) { return fp_mul(a, a); }
-static u256 fp_pow(const u256* a, const u256* e) {
-  u256 r = {{1, 0, 0, 0}};
-  for (int i = 255; i >= 0; i--) {
-    r = fp_sqr(&r);
-    if ((e->l[i / 64] >> (i % 64)) & 1) r = fp_mul(&r, a);
-  }
-  return r;
+static u256 fp_sqrn(u256 a, int n) {
+  for (int i = 0; i < n; i++) a = fp_sqr(&a);
+  return a;
 }
-static u256 fp_inv(const u256* a) {
-  u256 e = FP; e.l[0] -= 2;
-  return fp_pow(a, &e);
+/* x^(2^223 - 1) and the two helpers the tails need (standard secp256k1 addition chain: x2,x3,x6,x9,x11,x22,x44,x88,x176,x220,x223) */
+static void fp_chain223(const u256* a, u256* x2, u256* x22, u256* x223) {
+  u256 t = fp_sqr(a); *x2 = fp_mul(&t, a);
+  t = fp_sqr(x2); u256 x3 = fp_mul(&t, a);
+  t = fp_sqrn(x3, 3); u256 x6 = fp_mul(&t, &x3);
+  t = fp_sqrn(x6, 3); u256 x9 = fp_mul(&t, &x3);
+  t = fp_sqrn(x9, 2); u256 x11 = fp_mul(&t, x2);
+  t = fp_sqrn(x11, 11); *x22 = fp_mul(&t, &x11);
+  t = fp_sqrn(*x22, 22); u256 x44 = fp_mul(&t, x22);
+  t = fp_sqrn(x44, 44); u256 x88 = fp_mul(&t, &x44);
+  t = fp_sqrn(x88, 88); u256 x176 = fp_mul(&t, &x88);
+  t = fp_sqrn(x176, 44); u256 x220 = fp_mul(&t, &x44);
+  t = fp_sqrn(x220, 3); *x223 = fp_mul(&t, &x3);
 }
-static int fp_sqrt(u256* r, const u256* a) { /* p = 3 mod 4 */
-  u256 e = {{0xFFFFFFFFBFFFFF0CULL, 0xFFFFFFFFFFFFFFFFULL, 0xFFFFFFFFFFFFFFFFULL, 0x3FFFFFFFFFFFFFFFULL}}; /* (p+1)/4 */
-  u256 y = fp_pow(a, &e), y2 = fp_sqr(&y);
-  *r = y;
+static u256 fp_inv(const u256* a) { /* a^(p-2), p-2 = [223 ones][0][22 ones][0000][1][0][11][0][1] */
+  u256 x2, x22, x223;
+  fp_chain223(a, &x2, &x22, &x223);
+  u256 t = fp_sqrn(x223, 23); t = fp_mul(&t, &x22);
+  t = fp_sqrn(t, 5); t = fp_mul(&t, a);
+  t = fp_sqrn(t, 3); t = fp_mul(&t, &x2);
+  t = fp_sqrn(t, 2); t = fp_mul(&t, a);
+  return t;
+}
+static int fp_sqrt(u256* r, const u256* a) { /* a^((p+1)/4), (p+1)/4 = [223 ones][0][22 ones][0000][11][00]; p = 3 mod 4 */
+  u256 x2, x22, x223;
+  fp_chain223(a, &x2, &x22, &x223);
+  u256 t = fp_sqrn(x223, 23); t = fp_mul(&t, &x22);
+  t = fp_sqrn(t, 6); t = fp_mul(&t, &x2);
+  t = fp_sqrn(t, 2);
+  u256 y2 = fp_sqr(&t);
+  *r = t;
   return cmp256(&y2, a) == 0;
 }
 
@@ -218,12 +237,17 @@ static u256 fn_neg(const u256* a) {
   sub256(&r, &FN, a);
   return r;
 }
-static u256 fn_inv(const u256* a) {
+static u256 fn_inv(const u256* a) { /* a^(n-2), fixed 4-bit window */
   u256 e = FN; e.l[0] -= 2;
-  u256 r = {{1, 0, 0, 0}};
-  for (int i = 255; i >= 0; i--) {
-    r = fn_mul(&r, &r);
-    if ((e.l[i / 64] >> (i % 64)) & 1) r = fn_mul(&r, a);
+  u256 tab[16];
+  tab[0] = (u256){{1, 0, 0, 0}};
+  tab[1] = *a;
+  for (int i = 2; i < 16; i++) tab[i] = fn_mul(&tab[i - 1], a);
+  u256 r = tab[(e.l[3] >> 60) & 15];
+  for (int nib = 62; nib >= 0; nib--) {
+    for (int k = 0; k < 4; k++) r = fn_mul(&r, &r);
+    unsigned d = (unsigned)(e.l[nib / 16] >> (4 * (nib % 16))) & 15;
+    if (d) r = fn_mul(&r, &tab[d]);
   }
   return r;
 }
@@ -438,7 +462,10 @@ void oracle_fn_inv(const uint8_t a[32], uint8_t out[32]) {
  *     Keccak-256(PayloadNoSig) equals msg.From, and From is in the validator set of the height;
  *   IsValidCommittedSeal (core/backend.go:53-55): signer recovered from seal.Signature over
  *     Keccak-256(proposalHash || 0x02) equals seal.Signer, and Signer is in the validator set. */
-static int addr_in_table(const uint8_t* table, uint32_t n, const uint8_t addr[20]) {
+static int cmp_addr(const void* a, const void* b) { return memcmp(a, b, 20); }
+/* `sorted` != 0: the table is sorted (oracle_verify_batch sorts private copies once per call) */
+static int addr_in_table(const uint8_t* table, uint32_t n, const uint8_t addr[20], int sorted) {
+  if (sorted) return bsearch(addr, table, n, 20, cmp_addr) != NULL ? 0 : -1;
   for (uint32_t i = 0; i < n; i++)
     if (memcmp(table + 20 * (size_t)i, addr, 20) == 0) return (int)i;
   return -1;
@@ -462,16 +489,20 @@ int oracle_item_digest(const ibft_sig_item* it, const uint8_t* arena, size_t are
   }
 }
 
-int oracle_verify_item(const ibft_sig_item* it, const uint8_t* arena, size_t arena_len, const uint8_t* table,
-                       uint32_t table_n, uint8_t recovered[20]) {
+static int verify_item(const ibft_sig_item* it, const uint8_t* arena, size_t arena_len, const uint8_t* table,
+                       uint32_t table_n, int sorted, uint8_t recovered[20]) {
   uint8_t z[32], addr[20];
   if (recovered) memset(recovered, 0, 20);
   if (!oracle_item_digest(it, arena, arena_len, z)) return 0;
   if (!oracle_ecrecover_address(z, it->r, it->s, it->v, addr)) return 0;
   if (recovered) memcpy(recovered, addr, 20);
   if (memcmp(addr, it->signer, 20) != 0) return 0;
-  if (table && addr_in_table(table, table_n, addr) < 0) return 0;
+  if (table && addr_in_table(table, table_n, addr, sorted) < 0) return 0;
   return 1;
+}
+int oracle_verify_item(const ibft_sig_item* it, const uint8_t* arena, size_t arena_len, const uint8_t* table,
+                       uint32_t table_n, uint8_t recovered[20]) {
+  return verify_item(it, arena, arena_len, table, table_n, 0, recovered);
 }
 
 typedef struct {
@@ -490,7 +521,7 @@ static void* worker(void* arg) {
       tab = j->tables[j->group_table[it->group]];
       tn = j->table_n[j->group_table[it->group]];
     }
-    j->verdict[i] = (uint8_t)oracle_verify_item(it, j->arena, j->arena_len, tab, tn, NULL);
+    j->verdict[i] = (uint8_t)verify_item(it, j->arena, j->arena_len, tab, tn, 1, NULL);
   }
   return NULL;
 }
@@ -505,6 +536,17 @@ int oracle_verify_batch(const ibft_sig_item* items, uint32_t n, const uint8_t* a
   pthread_once(&g_once, init_g_table);
   uint8_t* verdict = (uint8_t*)calloc(n ? n : 1, 1);
   if (!verdict) return -1;
+  /* sorted private copies of the validator tables (set membership by binary search) */
+  uint32_t n_tables = 0;
+  for (uint32_t g = 0; group_table && g < n_groups; g++)
+    if (group_table[g] != 0xFFFF && group_table[g] + 1u > n_tables) n_tables = group_table[g] + 1u;
+  uint8_t** sorted_tabs = (uint8_t**)calloc(n_tables ? n_tables : 1, sizeof(uint8_t*));
+  for (uint32_t t = 0; t < n_tables; t++) {
+    sorted_tabs[t] = (uint8_t*)malloc((size_t)table_n[t] * 20 + 1);
+    memcpy(sorted_tabs[t], tables[t], (size_t)table_n[t] * 20);
+    qsort(sorted_tabs[t], table_n[t], 20, cmp_addr);
+  }
+  tables = (const uint8_t* const*)sorted_tabs;
   pthread_t th[256];
   job_t jobs[256];
   uint32_t per = (n + (uint32_t)n_threads - 1) / (uint32_t)n_threads;
@@ -523,5 +565,7 @@ int oracle_verify_batch(const ibft_sig_item* items, uint32_t n, const uint8_t* a
   for (uint32_t i = 0; i < n; i++)
     if (verdict[i]) bitmap[i / 32] |= 1u << (i % 32);
   free(verdict);
+  for (uint32_t t = 0; t < n_tables; t++) free(sorted_tabs[t]);
+  free(sorted_tabs);
   return 0;
 }
