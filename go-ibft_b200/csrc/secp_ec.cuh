@@ -56,6 +56,14 @@ IBFT_HD jac jac_double(const jac& p) {
   return r;
 }
 
+// Rarely-taken exceptional path of the adders (P + P): one shared out-of-line copy keeps the hot loop small.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void jac_double_slow(jac* r, const jac* p) { *r = jac_double(*p); }
+
 // p + (qx, qy) with q affine (never infinity): 8M + 3S
 IBFT_HD jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
   jac r;
@@ -72,7 +80,10 @@ IBFT_HD jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
   fe h = fe_sub(u2, p.x);
   fe rr = fe_sub(s2, p.y);
   if (fe_is_zero(h)) {
-    if (fe_is_zero(rr)) return jac_double(p);  // P + P
+    if (fe_is_zero(rr)) {  // P + P
+      jac_double_slow(&r, &p);
+      return r;
+    }
     r = p;
     r.inf = true;  // P + (-P)
     return r;
@@ -106,7 +117,10 @@ IBFT_HD jac jac_add(const jac& p, const fe& qx, const fe& qy, const fe& qz) {
   fe h = fe_sub(u2, u1);
   fe rr = fe_sub(s2, s1);
   if (fe_is_zero(h)) {
-    if (fe_is_zero(rr)) return jac_double(p);
+    if (fe_is_zero(rr)) {
+      jac_double_slow(&r, &p);
+      return r;
+    }
     r = p;
     r.inf = true;
     return r;
@@ -149,89 +163,88 @@ struct rtab_entry {
   fe x, y, z, bx;
 };
 
-// Returns u1*G + u2*R (R affine, on the curve) as a Jacobian point.  u1, u2 in [0, n).
-IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_view& G) {
-  glv_half g1, g2, r1, r2;
-  glv_split(u1, g1, g2);
-  glv_split(u2, r1, r2);
-  uint32_t kg1[6], kg2[6], kr1[6], kr2[6];
-#pragma unroll
-  for (int i = 0; i < 5; i++) { kg1[i] = g1.k[i]; kg2[i] = g2.k[i]; kr1[i] = r1.k[i]; kr2[i] = r2.k[i]; }
-  kg1[5] = kg2[5] = kr1[5] = kr2[5] = 0;
+#if defined(__CUDA_ARCH__)
+#define IBFT_ROLLED _Pragma("unroll 1")
+#else
+#define IBFT_ROLLED
+#endif
 
-  // {1..8} * R
+// Returns u1*G + u2*R (R affine, on the curve) as a Jacobian point.  u1, u2 in [0, n).
+// Every loop below is deliberately ROLLED and each group-law routine appears exactly once in the instruction stream:
+// the kernel is instruction-cache bound otherwise (see secp_fe.cuh, IBFT_FN).
+IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_view& G) {
+  // digit streams: 0 = u2 half 1 (R), 1 = u2 half 2 (lambda R), 2 = u1 half 1 (G), 3 = u1 half 2 (lambda G)
+  uint32_t ks[4][6];
+  bool kneg[4];
+  {
+    glv_half h1, h2;
+    glv_split(u2, h1, h2);
+#pragma unroll
+    for (int i = 0; i < 5; i++) { ks[0][i] = h1.k[i]; ks[1][i] = h2.k[i]; }
+    kneg[0] = h1.neg; kneg[1] = h2.neg;
+    glv_split(u1, h1, h2);
+#pragma unroll
+    for (int i = 0; i < 5; i++) { ks[2][i] = h1.k[i]; ks[3][i] = h2.k[i]; }
+    kneg[2] = h1.neg; kneg[3] = h2.neg;
+    ks[0][5] = ks[1][5] = ks[2][5] = ks[3][5] = 0;
+  }
+
+  // {1..8} * R: entry m holds (m+1)R; even multiples by doubling, odd ones by adding R
   rtab_entry tab[8];
   {
-    fe beta = fe_beta();
-    jac p1;
-    p1.x = R.x; p1.y = R.y; p1.z = fe_from_u32(1); p1.inf = false;
-    jac p2 = jac_double(p1);
-    jac p3 = jac_add_affine(p2, R.x, R.y);
-    jac p4 = jac_double(p2);
-    jac p5 = jac_add_affine(p4, R.x, R.y);
-    jac p6 = jac_double(p3);
-    jac p7 = jac_add_affine(p6, R.x, R.y);
-    jac p8 = jac_double(p4);
-#define IBFT_SETTAB(i, p)                                 \
-  tab[i].x = (p).x; tab[i].y = (p).y; tab[i].z = (p).z;   \
-  tab[i].bx = fe_mul((p).x, beta);
-    IBFT_SETTAB(0, p1) IBFT_SETTAB(1, p2) IBFT_SETTAB(2, p3) IBFT_SETTAB(3, p4)
-    IBFT_SETTAB(4, p5) IBFT_SETTAB(5, p6) IBFT_SETTAB(6, p7) IBFT_SETTAB(7, p8)
-#undef IBFT_SETTAB
+    const fe beta = fe_beta();
+    tab[0].x = R.x; tab[0].y = R.y; tab[0].z = fe_from_u32(1);
+    tab[0].bx = fe_mul(R.x, beta);
+    IBFT_ROLLED
+    for (int m = 1; m < 8; m++) {
+      jac t;
+      if (m & 1) {
+        int src = ((m + 1) >> 1) - 1;
+        jac p;
+        p.x = tab[src].x; p.y = tab[src].y; p.z = tab[src].z; p.inf = false;
+        t = jac_double(p);
+      } else {
+        jac p;
+        p.x = tab[m - 1].x; p.y = tab[m - 1].y; p.z = tab[m - 1].z; p.inf = false;
+        t = jac_add_affine(p, R.x, R.y);
+      }
+      tab[m].x = t.x; tab[m].y = t.y; tab[m].z = t.z;
+      tab[m].bx = fe_mul(t.x, beta);
+    }
   }
 
   jac acc;
   acc.x = fe_zero(); acc.y = fe_zero(); acc.z = fe_zero();
   acc.inf = true;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
+  IBFT_ROLLED
   for (int j = IBFT_NWIN_R - 1; j >= 0; j--) {
     if (!acc.inf) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
+      IBFT_ROLLED
       for (int t = 0; t < IBFT_WR; t++) acc = jac_double(acc);
     }
     // R streams (every window)
-    {
-      int d = booth_digit<IBFT_WR>(kr1, j);
+    IBFT_ROLLED
+    for (int s = 0; s < 2; s++) {
+      int d = booth_digit<IBFT_WR>(ks[s], j);
       if (d != 0) {
         int idx = (d < 0 ? -d : d) - 1;
-        bool neg = (d < 0) != r1.neg;
+        bool neg = (d < 0) != kneg[s];
+        fe x = s ? tab[idx].bx : tab[idx].x;
         fe y = tab[idx].y;
         if (neg) y = fe_neg(y);
-        acc = jac_add(acc, tab[idx].x, y, tab[idx].z);
-      }
-    }
-    {
-      int d = booth_digit<IBFT_WR>(kr2, j);
-      if (d != 0) {
-        int idx = (d < 0 ? -d : d) - 1;
-        bool neg = (d < 0) != r2.neg;
-        fe y = tab[idx].y;
-        if (neg) y = fe_neg(y);
-        acc = jac_add(acc, tab[idx].bx, y, tab[idx].z);
+        acc = jac_add(acc, x, y, tab[idx].z);
       }
     }
     // G streams (every WG/WR-th window)
     if (j % (IBFT_WG / IBFT_WR) == 0) {
       int jg = j / (IBFT_WG / IBFT_WR);
-      {
-        int d = booth_digit<IBFT_WG>(kg1, jg);
+      IBFT_ROLLED
+      for (int s = 0; s < 2; s++) {
+        int d = booth_digit<IBFT_WG>(ks[2 + s], jg);
         if (d != 0) {
           fe x, y;
-          G.load((d < 0 ? -d : d) - 1, false, x, y);
-          if ((d < 0) != g1.neg) y = fe_neg(y);
-          acc = jac_add_affine(acc, x, y);
-        }
-      }
-      {
-        int d = booth_digit<IBFT_WG>(kg2, jg);
-        if (d != 0) {
-          fe x, y;
-          G.load((d < 0 ? -d : d) - 1, true, x, y);
-          if ((d < 0) != g2.neg) y = fe_neg(y);
+          G.load((d < 0 ? -d : d) - 1, s != 0, x, y);
+          if ((d < 0) != kneg[2 + s]) y = fe_neg(y);
           acc = jac_add_affine(acc, x, y);
         }
       }

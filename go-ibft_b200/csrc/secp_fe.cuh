@@ -22,6 +22,20 @@
 #define IBFT_HD inline
 #endif
 
+// Code-size control.  The recover kernel is I-cache bound when everything is inlined (ncu r01_v1: 45% of the
+// stall samples are no_instruction on 735 KB of SASS), so the multiplier / squarer -- and optionally the adders --
+// are real device functions, passed BY VALUE so that the ABI keeps every operand in registers (no stack traffic).
+#if defined(__CUDACC__) && !defined(IBFT_INLINE_FE)
+#define IBFT_FN __host__ __device__ __noinline__
+#else
+#define IBFT_FN IBFT_HD
+#endif
+#if defined(__CUDACC__) && defined(IBFT_NOINLINE_ADD)
+#define IBFT_FN_ADD __host__ __device__ __noinline__
+#else
+#define IBFT_FN_ADD IBFT_HD
+#endif
+
 #if defined(__CUDA_ARCH__) && !defined(IBFT_PORTABLE_FE)
 #define IBFT_PTX 1
 #else
@@ -73,7 +87,7 @@ IBFT_HD void fe_to_be(const fe& a, uint8_t* b) {
 // ------------------------------------------------------------------------------------------------
 // add / sub
 // ------------------------------------------------------------------------------------------------
-IBFT_HD fe fe_add(const fe& a, const fe& b) {
+IBFT_FN_ADD fe fe_add(fe a, fe b) {
   fe r;
 #if IBFT_PTX
   uint32_t c;
@@ -128,7 +142,7 @@ IBFT_HD fe fe_add(const fe& a, const fe& b) {
   return r;
 }
 
-IBFT_HD fe fe_sub(const fe& a, const fe& b) {
+IBFT_FN_ADD fe fe_sub(fe a, fe b) {
   fe r;
 #if IBFT_PTX
   uint32_t c;
@@ -390,7 +404,7 @@ IBFT_HD fe fe_reduce512(const uint32_t* R) {
   return r;
 }
 
-IBFT_HD fe fe_mul(const fe& a, const fe& b) {
+IBFT_FN fe fe_mul(fe a, fe b) {
   uint32_t R[16];
   mul_wide_8x8(R, a.v, b.v);
   return fe_reduce512(R);
@@ -510,7 +524,7 @@ IBFT_HD void sqr_wide_8(uint32_t* R, const uint32_t* a) {
 #endif
 }
 
-IBFT_HD fe fe_sqr(const fe& a) {
+IBFT_FN fe fe_sqr(fe a) {
   uint32_t R[16];
   sqr_wide_8(R, a.v);
   return fe_reduce512(R);

@@ -8,14 +8,17 @@
 #include "../../include/ibft_verify.h"
 #include "keccak.cuh"
 #include "secp_ec.cuh"
+#include "secp_modinv.cuh"
 
 namespace ibft {
 
-#ifndef IBFT_FE_INV
+// modular inversions: safegcd divsteps by default, the Fermat ladders with -DIBFT_FERMAT (kept as a cross-check)
+#if defined(IBFT_FERMAT)
 #define IBFT_FE_INV fe_inv_fermat
-#endif
-#ifndef IBFT_SC_INV
 #define IBFT_SC_INV sc_inv_fermat
+#else
+#define IBFT_FE_INV fe_inv_safegcd
+#define IBFT_SC_INV sc_inv_safegcd
 #endif
 
 // digest of one item (kinds of include/ibft_verify.h).  Returns false for an unknown kind / out-of-range payload.

@@ -60,7 +60,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    so = path or _build.build()
+    so = path or os.environ.get("IBFT_LIB") or _build.build()  # IBFT_LIB: kernel-variant experiments (tools/quick_bench.py)
     lib = ctypes.CDLL(so)
     lib.ibft_last_error.restype = c_char_p
     lib.ibft_engine_launch_count.restype = c_uint64
