@@ -76,11 +76,17 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
           uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
           const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
           uint8_t* __restrict__ recovered) {
+#if IBFT_WG <= 8
   __shared__ uint32_t s_gtab[24 * IBFT_GTAB_ENTRIES];
+#else
+  const uint32_t* s_gtab = g_gtable;  // wide windows: the table (>= 48 KB) stays in global memory / L2
+#endif
   __shared__ uint32_t s_items[IBFT_BLOCK * IBFT_ITEM_ROW_WORDS];
   const uint32_t tid = threadIdx.x;
+#if IBFT_WG <= 8
   // stage the generator window table (shared by every signature of the CTA)
   for (uint32_t i = tid; i < 24 * IBFT_GTAB_ENTRIES; i += IBFT_BLOCK) s_gtab[i] = g_gtable[i];
+#endif
   // stage this CTA's 128 packed tuples with coalesced 16-byte loads
   const uint32_t base = shard_lo + blockIdx.x * IBFT_BLOCK;
   {
@@ -268,9 +274,13 @@ __global__ void k_keccak_batch(const uint8_t* __restrict__ arena, size_t arena_l
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_debug_op(int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint32_t n, uint8_t* out,
                            uint32_t stride) {
+#if IBFT_WG <= 8
   __shared__ uint32_t s_gtab[24 * IBFT_GTAB_ENTRIES];
   for (uint32_t i = threadIdx.x; i < 24 * IBFT_GTAB_ENTRIES; i += blockDim.x) s_gtab[i] = g_gtable[i];
   __syncthreads();
+#else
+  const uint32_t* s_gtab = g_gtable;
+#endif
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint8_t* pa = a + 32 * (size_t)i;

@@ -98,43 +98,6 @@ IBFT_HD jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
   return r;
 }
 
-// p + q, both Jacobian (q never infinity): 12M + 4S
-IBFT_HD jac jac_add(const jac& p, const fe& qx, const fe& qy, const fe& qz) {
-  jac r;
-  if (p.inf) {
-    r.x = qx;
-    r.y = qy;
-    r.z = qz;
-    r.inf = false;
-    return r;
-  }
-  fe z1z1 = fe_sqr(p.z);
-  fe z2z2 = fe_sqr(qz);
-  fe u1 = fe_mul(p.x, z2z2);
-  fe u2 = fe_mul(qx, z1z1);
-  fe s1 = fe_mul(fe_mul(p.y, qz), z2z2);
-  fe s2 = fe_mul(fe_mul(qy, p.z), z1z1);
-  fe h = fe_sub(u2, u1);
-  fe rr = fe_sub(s2, s1);
-  if (fe_is_zero(h)) {
-    if (fe_is_zero(rr)) {
-      jac_double_slow(&r, &p);
-      return r;
-    }
-    r = p;
-    r.inf = true;
-    return r;
-  }
-  fe hh = fe_sqr(h);
-  fe hhh = fe_mul(h, hh);
-  fe v = fe_mul(u1, hh);
-  r.x = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
-  r.y = fe_sub(fe_mul(rr, fe_sub(v, r.x)), fe_mul(s1, hhh));
-  r.z = fe_mul(fe_mul(p.z, qz), h);
-  r.inf = false;
-  return r;
-}
-
 // ------------------------------------------------------------------------------------------------
 // u1*G + u2*R
 // ------------------------------------------------------------------------------------------------
@@ -160,8 +123,11 @@ struct gtab_view {
 };
 
 struct rtab_entry {
-  fe x, y, z, bx;
+  fe x, y, bx;  // affine multiple of R and beta*x (the lambda-image shares y)
 };
+
+// inversion used for the per-signature table; defined by the including translation unit (verify_core.cuh)
+IBFT_HD fe fe_inv_for_table(const fe& a);
 
 #if defined(__CUDA_ARCH__)
 #define IBFT_ROLLED _Pragma("unroll 1")
@@ -189,28 +155,39 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
     ks[0][5] = ks[1][5] = ks[2][5] = ks[3][5] = 0;
   }
 
-  // {1..8} * R: entry m holds (m+1)R; even multiples by doubling, odd ones by adding R
+  // {1..8} * R: entry m holds (m+1)R; even multiples by doubling, odd ones by adding R.  The table is then made
+  // AFFINE with one shared inversion (Montgomery's trick over the seven Z's), so that every addition of the main loop
+  // is a mixed addition (8M+3S instead of 12M+4S) and the loop holds a single adder.
   rtab_entry tab[8];
   {
     const fe beta = fe_beta();
-    tab[0].x = R.x; tab[0].y = R.y; tab[0].z = fe_from_u32(1);
-    tab[0].bx = fe_mul(R.x, beta);
+    fe zs[8];  // Z of entry m
+    tab[0].x = R.x; tab[0].y = R.y; zs[0] = fe_from_u32(1);
     IBFT_ROLLED
     for (int m = 1; m < 8; m++) {
-      jac t;
-      if (m & 1) {
-        int src = ((m + 1) >> 1) - 1;
-        jac p;
-        p.x = tab[src].x; p.y = tab[src].y; p.z = tab[src].z; p.inf = false;
-        t = jac_double(p);
-      } else {
-        jac p;
-        p.x = tab[m - 1].x; p.y = tab[m - 1].y; p.z = tab[m - 1].z; p.inf = false;
-        t = jac_add_affine(p, R.x, R.y);
-      }
-      tab[m].x = t.x; tab[m].y = t.y; tab[m].z = t.z;
-      tab[m].bx = fe_mul(t.x, beta);
+      jac p, t;
+      int src = (m & 1) ? ((m + 1) >> 1) - 1 : m - 1;
+      p.x = tab[src].x; p.y = tab[src].y; p.z = zs[src]; p.inf = false;
+      if (m & 1) t = jac_double(p);
+      else t = jac_add_affine(p, R.x, R.y);
+      tab[m].x = t.x; tab[m].y = t.y; zs[m] = t.z;
     }
+    // prefix products pre[m] = Z_1 * ... * Z_m (Z_0 = 1), one inversion, then peel the inverses off backwards
+    fe pre[8];
+    pre[1] = zs[1];
+    IBFT_ROLLED
+    for (int m = 2; m < 8; m++) pre[m] = fe_mul(pre[m - 1], zs[m]);
+    fe acc_inv = fe_inv_for_table(pre[7]);
+    IBFT_ROLLED
+    for (int m = 7; m >= 1; m--) {
+      fe zi = m > 1 ? fe_mul(acc_inv, pre[m - 1]) : acc_inv;  // 1 / Z_m
+      if (m > 1) acc_inv = fe_mul(acc_inv, zs[m]);
+      fe zi2 = fe_sqr(zi);
+      tab[m].x = fe_mul(tab[m].x, zi2);
+      tab[m].y = fe_mul(tab[m].y, fe_mul(zi2, zi));
+    }
+    IBFT_ROLLED
+    for (int m = 0; m < 8; m++) tab[m].bx = fe_mul(tab[m].x, beta);
   }
 
   jac acc;
@@ -222,31 +199,22 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
       IBFT_ROLLED
       for (int t = 0; t < IBFT_WR; t++) acc = jac_double(acc);
     }
-    // R streams (every window)
+    // streams 0,1: R and lambda*R every window; streams 2,3: G and lambda*G every (WG/WR)-th window
+    const int ns = (j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2;
     IBFT_ROLLED
-    for (int s = 0; s < 2; s++) {
-      int d = booth_digit<IBFT_WR>(ks[s], j);
+    for (int s = 0; s < ns; s++) {
+      int d = s < 2 ? booth_digit<IBFT_WR>(ks[s], j) : booth_digit<IBFT_WG>(ks[s], j / (IBFT_WG / IBFT_WR));
       if (d != 0) {
         int idx = (d < 0 ? -d : d) - 1;
-        bool neg = (d < 0) != kneg[s];
-        fe x = s ? tab[idx].bx : tab[idx].x;
-        fe y = tab[idx].y;
-        if (neg) y = fe_neg(y);
-        acc = jac_add(acc, x, y, tab[idx].z);
-      }
-    }
-    // G streams (every WG/WR-th window)
-    if (j % (IBFT_WG / IBFT_WR) == 0) {
-      int jg = j / (IBFT_WG / IBFT_WR);
-      IBFT_ROLLED
-      for (int s = 0; s < 2; s++) {
-        int d = booth_digit<IBFT_WG>(ks[2 + s], jg);
-        if (d != 0) {
-          fe x, y;
-          G.load((d < 0 ? -d : d) - 1, s != 0, x, y);
-          if ((d < 0) != kneg[2 + s]) y = fe_neg(y);
-          acc = jac_add_affine(acc, x, y);
+        fe x, y;
+        if (s < 2) {
+          x = (s & 1) ? tab[idx].bx : tab[idx].x;
+          y = tab[idx].y;
+        } else {
+          G.load(idx, (s & 1) != 0, x, y);
         }
+        if ((d < 0) != kneg[s]) y = fe_neg(y);
+        acc = jac_add_affine(acc, x, y);
       }
     }
   }

@@ -21,6 +21,8 @@ namespace ibft {
 #define IBFT_SC_INV sc_inv_safegcd
 #endif
 
+IBFT_HD fe fe_inv_for_table(const fe& a) { return IBFT_FE_INV(a); }
+
 // digest of one item (kinds of include/ibft_verify.h).  Returns false for an unknown kind / out-of-range payload.
 IBFT_HD bool item_digest(const ibft_sig_item& it, const uint8_t* arena, size_t arena_len, uint8_t* z) {
   switch (it.kind) {
