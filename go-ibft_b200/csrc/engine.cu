@@ -71,7 +71,10 @@ __device__ int lookup_validator(const slot_dev& s, const uint8_t* addr) {
 // ------------------------------------------------------------------------------------------------------------
 // K1 + K2: recover kernel.  One thread per signature; a warp's 32 verdicts become one bitmap word.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(IBFT_BLOCK)
+#ifndef IBFT_MIN_BLOCKS
+#define IBFT_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(IBFT_BLOCK, IBFT_MIN_BLOCKS)
 k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
           uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
           const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,

@@ -34,38 +34,42 @@ IBFT_HD fe fe_beta() {
   return b;
 }
 
+// IBFT_POINT_INLINE: the two hot group-law routines become out-of-line functions (operands by reference) with the
+// field multiplier INLINED inside them -- one call per point operation instead of one per field operation.
+#if defined(IBFT_POINT_INLINE) && defined(__CUDACC__)
+#define IBFT_PT __host__ __device__ __noinline__
+#define PMUL fe_mul_i
+#define PSQR fe_sqr_i
+#else
+#define IBFT_PT IBFT_HD
+#define PMUL fe_mul
+#define PSQR fe_sqr
+#endif
+
 // dbl-2009-l: 2M + 5S
-IBFT_HD jac jac_double(const jac& p) {
+IBFT_PT jac jac_double(const jac& p) {
   jac r;
   // Y = 0 never happens on secp256k1 (no points of order 2), so no exceptional case besides infinity.
-  fe a = fe_sqr(p.x);
-  fe b = fe_sqr(p.y);
-  fe c = fe_sqr(b);
+  fe a = PSQR(p.x);
+  fe b = PSQR(p.y);
+  fe c = PSQR(b);
   fe t = fe_add(p.x, b);
-  t = fe_sqr(t);
+  t = PSQR(t);
   t = fe_sub(t, a);
   t = fe_sub(t, c);
   fe d = fe_dbl(t);
   fe e = fe_add(fe_dbl(a), a);
-  fe f = fe_sqr(e);
+  fe f = PSQR(e);
   r.x = fe_sub(f, fe_dbl(d));
   fe c8 = fe_dbl(fe_dbl(fe_dbl(c)));
-  r.y = fe_sub(fe_mul(e, fe_sub(d, r.x)), c8);
-  r.z = fe_dbl(fe_mul(p.y, p.z));
+  r.y = fe_sub(PMUL(e, fe_sub(d, r.x)), c8);
+  r.z = fe_dbl(PMUL(p.y, p.z));
   r.inf = p.inf;
   return r;
 }
 
-// Rarely-taken exceptional path of the adders (P + P): one shared out-of-line copy keeps the hot loop small.
-#if defined(__CUDACC__)
-__host__ __device__ __noinline__
-#else
-inline
-#endif
-void jac_double_slow(jac* r, const jac* p) { *r = jac_double(*p); }
-
 // p + (qx, qy) with q affine (never infinity): 8M + 3S
-IBFT_HD jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
+IBFT_PT jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
   jac r;
   if (p.inf) {
     r.x = qx;
@@ -74,26 +78,23 @@ IBFT_HD jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
     r.inf = false;
     return r;
   }
-  fe z1z1 = fe_sqr(p.z);
-  fe u2 = fe_mul(qx, z1z1);
-  fe s2 = fe_mul(fe_mul(qy, p.z), z1z1);
+  fe z1z1 = PSQR(p.z);
+  fe u2 = PMUL(qx, z1z1);
+  fe s2 = PMUL(PMUL(qy, p.z), z1z1);
   fe h = fe_sub(u2, p.x);
   fe rr = fe_sub(s2, p.y);
   if (fe_is_zero(h)) {
-    if (fe_is_zero(rr)) {  // P + P
-      jac_double_slow(&r, &p);
-      return r;
-    }
+    if (fe_is_zero(rr)) return jac_double(p);  // P + P (rare; kept inline so that `p` never has its address taken)
     r = p;
     r.inf = true;  // P + (-P)
     return r;
   }
-  fe hh = fe_sqr(h);
-  fe hhh = fe_mul(h, hh);
-  fe v = fe_mul(p.x, hh);
-  r.x = fe_sub(fe_sub(fe_sqr(rr), hhh), fe_dbl(v));
-  r.y = fe_sub(fe_mul(rr, fe_sub(v, r.x)), fe_mul(p.y, hhh));
-  r.z = fe_mul(p.z, h);
+  fe hh = PSQR(h);
+  fe hhh = PMUL(h, hh);
+  fe v = PMUL(p.x, hh);
+  r.x = fe_sub(fe_sub(PSQR(rr), hhh), fe_dbl(v));
+  r.y = fe_sub(PMUL(rr, fe_sub(v, r.x)), PMUL(p.y, hhh));
+  r.z = PMUL(p.z, h);
   r.inf = false;
   return r;
 }

@@ -267,9 +267,97 @@ __device__ __forceinline__ void mulw(uint32_t& lo, uint32_t& hi, uint32_t x, uin
 }
 #endif
 
+#if IBFT_PTX
+// ---- 4x4-limb product with the even/odd carry-chain layout; "fresh" accumulator halves use literal-zero addends
+__device__ __forceinline__ void mul4x4(uint32_t* R, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1, uint32_t b2, uint32_t b3) {
+  uint32_t E0, E1, E2, E3, E4, E5, E6, E7, O0, O1, O2, O3, O4, O5, O6;
+  // row 0
+  mulw(E0, E1, a0, b0); mulw(E2, E3, a2, b0);
+  mulw(O0, O1, a1, b0); mulw(O2, O3, a3, b0);
+  // row 1: O idx 0,2 (x = a0,a2) carry -> O4 ; E idx 2,4 (x = a1,a3), (E4,E5) fresh
+  asm("mad.lo.cc.u32 %0,%5,%7,%0;\n\tmadc.hi.cc.u32 %1,%5,%7,%1;\n\tmadc.lo.cc.u32 %2,%6,%7,%2;\n\tmadc.hi.cc.u32 %3,%6,%7,%3;\n\t"
+      "addc.u32 %4,0,0;"
+      : "+r"(O0), "+r"(O1), "+r"(O2), "+r"(O3), "=r"(O4) : "r"(a0), "r"(a2), "r"(b1));
+  asm("mad.lo.cc.u32 %0,%4,%6,%0;\n\tmadc.hi.cc.u32 %1,%4,%6,%1;\n\tmadc.lo.cc.u32 %2,%5,%6,0;\n\tmadc.hi.u32 %3,%5,%6,0;"
+      : "+r"(E2), "+r"(E3), "=r"(E4), "=r"(E5) : "r"(a1), "r"(a3), "r"(b1));
+  // row 2: E idx 2,4 (x = a0,a2) carry -> E6 ; O idx 2,4 (x = a1,a3), (O4,O5) = (carry, fresh)
+  asm("mad.lo.cc.u32 %0,%5,%7,%0;\n\tmadc.hi.cc.u32 %1,%5,%7,%1;\n\tmadc.lo.cc.u32 %2,%6,%7,%2;\n\tmadc.hi.cc.u32 %3,%6,%7,%3;\n\t"
+      "addc.u32 %4,0,0;"
+      : "+r"(E2), "+r"(E3), "+r"(E4), "+r"(E5), "=r"(E6) : "r"(a0), "r"(a2), "r"(b2));
+  asm("mad.lo.cc.u32 %0,%4,%6,%0;\n\tmadc.hi.cc.u32 %1,%4,%6,%1;\n\tmadc.lo.cc.u32 %2,%5,%6,%2;\n\tmadc.hi.u32 %3,%5,%6,0;"
+      : "+r"(O2), "+r"(O3), "+r"(O4), "=r"(O5) : "r"(a1), "r"(a3), "r"(b2));
+  // row 3: O idx 2,4 (x = a0,a2) carry -> O6 ; E idx 4,6 (x = a1,a3), (E6,E7) = (carry, fresh)
+  asm("mad.lo.cc.u32 %0,%5,%7,%0;\n\tmadc.hi.cc.u32 %1,%5,%7,%1;\n\tmadc.lo.cc.u32 %2,%6,%7,%2;\n\tmadc.hi.cc.u32 %3,%6,%7,%3;\n\t"
+      "addc.u32 %4,0,0;"
+      : "+r"(O2), "+r"(O3), "+r"(O4), "+r"(O5), "=r"(O6) : "r"(a0), "r"(a2), "r"(b3));
+  asm("mad.lo.cc.u32 %0,%4,%6,%0;\n\tmadc.hi.cc.u32 %1,%4,%6,%1;\n\tmadc.lo.cc.u32 %2,%5,%6,%2;\n\tmadc.hi.u32 %3,%5,%6,0;"
+      : "+r"(E4), "+r"(E5), "+r"(E6), "=r"(E7) : "r"(a1), "r"(a3), "r"(b3));
+  // R = E + (O << 32)
+  R[0] = E0;
+  asm("add.cc.u32 %0,%7,%14;\n\taddc.cc.u32 %1,%8,%15;\n\taddc.cc.u32 %2,%9,%16;\n\taddc.cc.u32 %3,%10,%17;\n\t"
+      "addc.cc.u32 %4,%11,%18;\n\taddc.cc.u32 %5,%12,%19;\n\taddc.u32 %6,%13,%20;"
+      : "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7])
+      : "r"(E1), "r"(E2), "r"(E3), "r"(E4), "r"(E5), "r"(E6), "r"(E7), "r"(O0), "r"(O1), "r"(O2), "r"(O3), "r"(O4), "r"(O5), "r"(O6));
+}
+
+// |x - y| for 4-limb operands; returns the sign mask (0xFFFFFFFF when x < y)
+__device__ __forceinline__ uint32_t absdiff4(uint32_t* d, const uint32_t* x, const uint32_t* y) {
+  uint32_t m;
+  asm("sub.cc.u32 %0,%5,%9;\n\tsubc.cc.u32 %1,%6,%10;\n\tsubc.cc.u32 %2,%7,%11;\n\tsubc.cc.u32 %3,%8,%12;\n\tsubc.u32 %4,0,0;"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(m)
+      : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+  // conditional two's-complement negation: (d ^ m) - m
+  uint32_t t0 = d[0] ^ m, t1 = d[1] ^ m, t2 = d[2] ^ m, t3 = d[3] ^ m;
+  asm("sub.cc.u32 %0,%4,%8;\n\tsubc.cc.u32 %1,%5,%8;\n\tsubc.cc.u32 %2,%6,%8;\n\tsubc.u32 %3,%7,%8;"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(t0), "r"(t1), "r"(t2), "r"(t3), "r"(m));
+  return m;
+}
+#endif
+
 // R[0..15] = a * b
 IBFT_HD void mul_wide_8x8(uint32_t* R, const uint32_t* a, const uint32_t* b) {
-#if IBFT_PTX
+#if IBFT_PTX && defined(IBFT_KARATSUBA)
+  // OPT-IN (measured slower): one level of (subtractive) Karatsuba, 48 wide MACs instead of 64.  The IMAD.WIDE pipe is the bottleneck of the whole
+  // kernel (4 issue cycles per warp-instruction) while the ALU pipe that takes the ~70 extra add/xor instructions is
+  // less than half used (ncu r01_v2), so trading 16 MACs for carry-chain adds is a net win on sm_100a.
+  //   a*b = z0 + (z0 + z2 + (a0-a1)(b1-b0)) 2^128 + z2 2^256
+  uint32_t z0[8], z2[8], m[8], da[4], db[4];
+  mul4x4(z0, a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]);
+  mul4x4(z2, a[4], a[5], a[6], a[7], b[4], b[5], b[6], b[7]);
+  uint32_t sa = absdiff4(da, a, a + 4);      // a0 - a1
+  uint32_t sb = absdiff4(db, b + 4, b);      // b1 - b0
+  mul4x4(m, da[0], da[1], da[2], da[3], db[0], db[1], db[2], db[3]);
+  uint32_t s = sa ^ sb;                      // all-ones: the cross term is negative
+  // z1 = z0 + z2 (9 limbs)
+  uint32_t z1[9];
+  asm("add.cc.u32 %0,%9,%17;\n\taddc.cc.u32 %1,%10,%18;\n\taddc.cc.u32 %2,%11,%19;\n\taddc.cc.u32 %3,%12,%20;\n\t"
+      "addc.cc.u32 %4,%13,%21;\n\taddc.cc.u32 %5,%14,%22;\n\taddc.cc.u32 %6,%15,%23;\n\taddc.cc.u32 %7,%16,%24;\n\t"
+      "addc.u32 %8,0,0;"
+      : "=r"(z1[0]), "=r"(z1[1]), "=r"(z1[2]), "=r"(z1[3]), "=r"(z1[4]), "=r"(z1[5]), "=r"(z1[6]), "=r"(z1[7]), "=r"(z1[8])
+      : "r"(z0[0]), "r"(z0[1]), "r"(z0[2]), "r"(z0[3]), "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]), "r"(z2[1]),
+        "r"(z2[2]), "r"(z2[3]), "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
+  // z1 += (-1)^s m :  z1 + (m ^ s) + (s & 1), and the 2^256 that the complement adds is taken back from the top limb
+  uint32_t x0 = m[0] ^ s, x1 = m[1] ^ s, x2 = m[2] ^ s, x3 = m[3] ^ s, x4 = m[4] ^ s, x5 = m[5] ^ s, x6 = m[6] ^ s, x7 = m[7] ^ s;
+  uint32_t scr;
+  asm("add.cc.u32 %9,%18,0xFFFFFFFF;\n\t"  // carry flag <- (s != 0)
+      "addc.cc.u32 %0,%0,%10;\n\taddc.cc.u32 %1,%1,%11;\n\taddc.cc.u32 %2,%2,%12;\n\taddc.cc.u32 %3,%3,%13;\n\t"
+      "addc.cc.u32 %4,%4,%14;\n\taddc.cc.u32 %5,%5,%15;\n\taddc.cc.u32 %6,%6,%16;\n\taddc.cc.u32 %7,%7,%17;\n\t"
+      "addc.u32 %8,%8,%18;"  // top limb: + carry, and - 1 (adding 0xFFFFFFFF) when the term was subtracted
+      : "+r"(z1[0]), "+r"(z1[1]), "+r"(z1[2]), "+r"(z1[3]), "+r"(z1[4]), "+r"(z1[5]), "+r"(z1[6]), "+r"(z1[7]), "+r"(z1[8]),
+        "=&r"(scr)
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(x4), "r"(x5), "r"(x6), "r"(x7), "r"(s));
+  // R = z0 + z1 2^128 + z2 2^256
+  R[0] = z0[0]; R[1] = z0[1]; R[2] = z0[2]; R[3] = z0[3];
+  asm("add.cc.u32 %0,%12,%24;\n\taddc.cc.u32 %1,%13,%25;\n\taddc.cc.u32 %2,%14,%26;\n\taddc.cc.u32 %3,%15,%27;\n\t"
+      "addc.cc.u32 %4,%16,%28;\n\taddc.cc.u32 %5,%17,%29;\n\taddc.cc.u32 %6,%18,%30;\n\taddc.cc.u32 %7,%19,%31;\n\t"
+      "addc.cc.u32 %8,%20,%32;\n\taddc.cc.u32 %9,%21,0;\n\taddc.cc.u32 %10,%22,0;\n\taddc.u32 %11,%23,0;"
+      : "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]), "=r"(R[9]), "=r"(R[10]), "=r"(R[11]), "=r"(R[12]),
+        "=r"(R[13]), "=r"(R[14]), "=r"(R[15])
+      : "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(z2[4]), "r"(z2[5]),
+        "r"(z2[6]), "r"(z2[7]), "r"(z1[0]), "r"(z1[1]), "r"(z1[2]), "r"(z1[3]), "r"(z1[4]), "r"(z1[5]), "r"(z1[6]), "r"(z1[7]),
+        "r"(z1[8]));
+#elif IBFT_PTX
   // E[k] sits at limb position k, O[k] at position k+1 (see DESIGN.md "field multiplier").
   uint32_t E[16], O[16];
 #pragma unroll
@@ -404,11 +492,13 @@ IBFT_HD fe fe_reduce512(const uint32_t* R) {
   return r;
 }
 
-IBFT_FN fe fe_mul(fe a, fe b) {
+// always-inline body (used inside the out-of-line point routines) and the out-of-line entry point (everything else)
+IBFT_HD fe fe_mul_i(const fe& a, const fe& b) {
   uint32_t R[16];
   mul_wide_8x8(R, a.v, b.v);
   return fe_reduce512(R);
 }
+IBFT_FN fe fe_mul(fe a, fe b) { return fe_mul_i(a, b); }
 
 #if IBFT_PTX
 // shorter carry chains for the squaring triangle
@@ -524,18 +614,19 @@ IBFT_HD void sqr_wide_8(uint32_t* R, const uint32_t* a) {
 #endif
 }
 
-IBFT_FN fe fe_sqr(fe a) {
+IBFT_HD fe fe_sqr_i(const fe& a) {
   uint32_t R[16];
   sqr_wide_8(R, a.v);
   return fe_reduce512(R);
 }
+IBFT_FN fe fe_sqr(fe a) { return fe_sqr_i(a); }
 
-// a^(2^n)
-IBFT_HD fe fe_sqrn(fe a, int n) {
+// a^(2^n): out of line, with the squarer inlined in the loop (no per-iteration call marshalling)
+IBFT_FN fe fe_sqrn(fe a, int n) {
 #if IBFT_PTX
 #pragma unroll 1
 #endif
-  for (int i = 0; i < n; i++) a = fe_sqr(a);
+  for (int i = 0; i < n; i++) a = fe_sqr_i(a);
   return a;
 }
 
