@@ -74,7 +74,10 @@ __device__ int lookup_validator(const slot_dev& s, const uint8_t* addr) {
 #ifndef IBFT_MIN_BLOCKS
 #define IBFT_MIN_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(IBFT_BLOCK, IBFT_MIN_BLOCKS)
+// BLOCK = 128 for throughput (12 resident warps/SM at 166 registers); BLOCK = 32 for latency-critical small batches (a
+// 10k-validator COMMIT round is only 313 warps: one-warp CTAs spread them over all 148 SMs instead of 79).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (IBFT_MIN_BLOCKS * IBFT_BLOCK) / BLOCK)
 k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
           uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
           const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
@@ -84,20 +87,20 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
 #else
   const uint32_t* s_gtab = g_gtable;  // wide windows: the table (>= 48 KB) stays in global memory / L2
 #endif
-  __shared__ uint32_t s_items[IBFT_BLOCK * IBFT_ITEM_ROW_WORDS];
+  __shared__ uint32_t s_items[BLOCK * IBFT_ITEM_ROW_WORDS];
   const uint32_t tid = threadIdx.x;
 #if IBFT_WG <= 8
   // stage the generator window table (shared by every signature of the CTA)
-  for (uint32_t i = tid; i < 24 * IBFT_GTAB_ENTRIES; i += IBFT_BLOCK) s_gtab[i] = g_gtable[i];
+  for (uint32_t i = tid; i < 24 * IBFT_GTAB_ENTRIES; i += BLOCK) s_gtab[i] = g_gtable[i];
 #endif
   // stage this CTA's 128 packed tuples with coalesced 16-byte loads
-  const uint32_t base = shard_lo + blockIdx.x * IBFT_BLOCK;
+  const uint32_t base = shard_lo + blockIdx.x * BLOCK;
   {
     const uint4* src = reinterpret_cast<const uint4*>(items + base);
-    uint32_t avail = base < shard_hi ? min((uint32_t)IBFT_BLOCK, shard_hi - base) : 0u;
+    uint32_t avail = base < shard_hi ? min((uint32_t)BLOCK, shard_hi - base) : 0u;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      uint32_t q = tid + k * IBFT_BLOCK;  // uint4 index within the CTA's 16 KB
+      uint32_t q = tid + k * BLOCK;  // uint4 index within the CTA's tuple block
       uint32_t row = q >> 3, col = q & 7;
       if (row < avail) {
         uint4 v = __ldg(src + q);
@@ -445,6 +448,7 @@ struct ibft_engine {
   std::vector<ibft_group_desc> last_groups;
   pending_call pending;
   uint64_t launches = 0;
+  int sm_count = 148;
   cudaFuncAttributes recover_attr{};
 };
 
@@ -495,7 +499,12 @@ static int engine_alloc(ibft_engine* e) {
   e->slots.resize(p.max_table_slots);
   e->slots_shadow.assign(p.max_table_slots, slot_dev{});
   CU(cudaMemcpyToSymbol(g_gtable, IBFT_GTABLE, sizeof(uint32_t) * 24 * IBFT_GTAB_ENTRIES));
-  CU(cudaFuncGetAttributes(&e->recover_attr, k_recover));
+  CU(cudaFuncGetAttributes(&e->recover_attr, k_recover<IBFT_BLOCK>));
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, p.device));
+    e->sm_count = prop.multiProcessorCount;
+  }
   CU(cudaDeviceSynchronize());
   return IBFT_OK;
 }
@@ -674,9 +683,15 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
                           uint32_t lo, uint32_t hi, const ibft_group_desc* d_groups, uint32_t n_groups, uint32_t* d_bitmap,
                           uint8_t* d_recovered, cudaStream_t st) {
   if (hi <= lo) return IBFT_OK;
-  uint32_t blocks = (hi - lo + IBFT_BLOCK - 1) / IBFT_BLOCK;
-  k_recover<<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                           e->p.max_table_slots, d_bitmap, d_recovered);
+  if (hi - lo <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs (latency path)
+    uint32_t blocks = (hi - lo + 31) / 32;
+    k_recover<32><<<blocks, 32, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+                                         e->p.max_table_slots, d_bitmap, d_recovered);
+  } else {
+    uint32_t blocks = (hi - lo + IBFT_BLOCK - 1) / IBFT_BLOCK;
+    k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+                                                         e->p.max_table_slots, d_bitmap, d_recovered);
+  }
   e->launches++;
   CU(cudaGetLastError());
   return IBFT_OK;

@@ -125,7 +125,7 @@ def are_valid_pc_messages(msgs: List[ip.IbftMessage], height: int, round_limit: 
         if m.view.round != rnd or m.view.round >= round_limit:
             return False
         extracted, ok = _extract_pc_message_hash(m)
-        if h is None:
+        if not h:  # Go: `if hash == nil` -- a wire-decoded empty hash is a nil slice, so it never becomes the reference hash
             h = extracted
         if not ok or not _bytes_equal(h, extracted):
             return False

@@ -259,3 +259,12 @@ def test_handle_prepare_and_commit_transitions():
     for k in (0, 1, 2, 3):
         i2.messages.add_message(ip.IbftMessage(v, b"node %d" % k, b"", ip.PREPARE, ip.PrepareMessage(HASH)))
     assert i2.handle_prepare(v) is False
+
+
+def test_are_valid_pc_messages_nil_hash_quirk():
+    """helpers.go:190-198: `if hash == nil { hash = extractedHash }` -- an empty (nil) hash never becomes the reference, so
+    [empty, "h"] passes while ["h", empty] fails."""
+    a, b = gen_unique(2, ip.PREPARE)
+    b.payload.proposal_hash = b"h"
+    assert L.are_valid_pc_messages([a, b], 0, 1) is True
+    assert L.are_valid_pc_messages([b, a], 0, 1) is False
