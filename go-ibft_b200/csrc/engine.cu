@@ -421,6 +421,8 @@ struct ibft_engine {
   ibft_engine_params p;
   std::mutex mu;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;       // H2D of chunk k+1 overlaps the recover kernel of chunk k
+  std::vector<cudaEvent_t> chunk_ev;
   cudaEvent_t done_ev = nullptr;
   // device
   ibft_sig_item* d_items = nullptr;
@@ -467,6 +469,8 @@ static void engine_free(ibft_engine* e) {
   cudaFreeHost(e->h_items); cudaFreeHost(e->h_arena); cudaFreeHost(e->h_bitmap); cudaFreeHost(e->h_recovered);
   cudaFreeHost(e->h_groups); cudaFreeHost(e->h_gdev); cudaFreeHost(e->h_results);
   if (e->done_ev) cudaEventDestroy(e->done_ev);
+  for (auto ev : e->chunk_ev) cudaEventDestroy(ev);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -475,6 +479,7 @@ static int engine_alloc(ibft_engine* e) {
   const ibft_engine_params& p = e->p;
   CU(cudaSetDevice(p.device));
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&e->done_ev, cudaEventDisableTiming));
   size_t n = p.max_items, words = (n + 31) / 32;
   CU(cudaMalloc(&e->d_items, n * sizeof(ibft_sig_item)));
@@ -739,10 +744,6 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
     e->last_groups.clear();
   }
   cudaStream_t st = e->stream;
-  if (n) {
-    memcpy(e->h_items, items, (size_t)n * sizeof(ibft_sig_item));
-    CU(cudaMemcpyAsync(e->d_items, e->h_items, (size_t)n * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, st));
-  }
   if (arena_len) {
     memcpy(e->h_arena, arena, arena_len);
     CU(cudaMemcpyAsync(e->d_arena, e->h_arena, arena_len, cudaMemcpyHostToDevice, st));
@@ -751,11 +752,33 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
     CU(cudaMemcpyAsync(e->d_groups, e->h_groups, (size_t)n_groups * sizeof(ibft_group_desc), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(e->d_gdev, e->h_gdev, (size_t)n_groups * sizeof(group_dev), cudaMemcpyHostToDevice, st));
   }
-  uint32_t padded = (n + 31u) & ~31u;
-  (void)padded;
-  int rc = launch_recover(e, e->d_items, n, e->d_arena, arena_len, 0, n, n_groups ? e->d_groups : nullptr, n_groups,
-                          e->d_bitmap, recovered_out ? e->d_recovered : nullptr, st);
-  if (rc != IBFT_OK) return rc;
+  // Tuples go up in chunks: while the recover kernel works on chunk k, the host stages chunk k+1 into pinned memory and the
+  // copy engine moves it (two streams + events).  Small batches are a single chunk.
+  const uint32_t CHUNK = 1u << 17;
+  uint32_t n_chunks = n ? (n + CHUNK - 1) / CHUNK : 0;
+  while (e->chunk_ev.size() < n_chunks + 1) {
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->chunk_ev.push_back(ev);
+  }
+  if (n_chunks > 1) {  // the copy stream must see the arena / groups uploads of this call
+    CU(cudaEventRecord(e->chunk_ev[n_chunks], st));
+    CU(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[n_chunks], 0));
+  }
+  int rc = IBFT_OK;
+  for (uint32_t c = 0; c < n_chunks; c++) {
+    uint32_t lo = c * CHUNK, hi = std::min(n, lo + CHUNK);
+    memcpy(e->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
+    cudaStream_t cs = n_chunks > 1 ? e->copy_stream : st;
+    CU(cudaMemcpyAsync(e->d_items + lo, e->h_items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, cs));
+    if (n_chunks > 1) {
+      CU(cudaEventRecord(e->chunk_ev[c], cs));
+      CU(cudaStreamWaitEvent(st, e->chunk_ev[c], 0));
+    }
+    rc = launch_recover(e, e->d_items, n, e->d_arena, arena_len, lo, hi, n_groups ? e->d_groups : nullptr, n_groups, e->d_bitmap,
+                        recovered_out ? e->d_recovered : nullptr, st);
+    if (rc != IBFT_OK) return rc;
+  }
   if (n_groups && results_out) {
     rc = launch_quorum(e, e->d_items, n, e->d_bitmap, e->d_groups, e->d_gdev, n_groups, voted_words, e->d_results, st);
     if (rc != IBFT_OK) return rc;
