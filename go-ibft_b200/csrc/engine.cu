@@ -29,12 +29,15 @@ static_assert(sizeof(ibft_sig_item) == 128, "packed item must be 128 bytes");
 static_assert(IBFT_GTABLE_WG == IBFT_WG, "regenerate secp_gtable.inc (tools/gen_tables.py) for this IBFT_WG");
 
 #define IBFT_BLOCK 128
+#ifndef IBFT_GTAB_SMEM
+#define IBFT_GTAB_SMEM (IBFT_WG <= 8)
+#endif
 #define IBFT_ITEM_ROW_WORDS 33  // 128-byte item + 1 pad word: conflict-free per-thread reads from shared memory
 
 // ------------------------------------------------------------------------------------------------------------
 // device-side tables
 // ------------------------------------------------------------------------------------------------------------
-__device__ uint32_t g_gtable[24 * IBFT_GTAB_ENTRIES];  // filled from IBFT_GTABLE at engine creation
+__device__ uint32_t g_gtable[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];  // filled from IBFT_GTABLE at engine creation
 
 struct slot_dev {
   const uint32_t* keys;    // n x 6 words: address as 5 big-endian words (sorted ascending) + validator index
@@ -82,16 +85,19 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
           uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
           const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
           uint8_t* __restrict__ recovered) {
-#if IBFT_WG <= 8
-  __shared__ uint32_t s_gtab[24 * IBFT_GTAB_ENTRIES];
+#if IBFT_GTAB_SMEM
+  __shared__ uint32_t s_gtab[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];
 #else
-  const uint32_t* s_gtab = g_gtable;  // wide windows: the table (>= 48 KB) stays in global memory / L2
+  const uint32_t* s_gtab = g_gtable;  // the table stays in global memory (L1/L2 resident)
 #endif
-  __shared__ uint32_t s_items[BLOCK * IBFT_ITEM_ROW_WORDS];
+  // Dynamic shared memory, BLOCK x 128 words, used twice: first as the staging area of the CTA's packed tuples (33-word
+  // rows), then -- once every thread holds its tuple in registers -- as the per-signature tables {1..8}*R (thread-interleaved).
+  extern __shared__ uint32_t s_rtab[];
+  uint32_t* s_items = s_rtab;
   const uint32_t tid = threadIdx.x;
-#if IBFT_WG <= 8
+#if IBFT_GTAB_SMEM
   // stage the generator window table (shared by every signature of the CTA)
-  for (uint32_t i = tid; i < 24 * IBFT_GTAB_ENTRIES; i += BLOCK) s_gtab[i] = g_gtable[i];
+  for (uint32_t i = tid; i < IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES; i += BLOCK) s_gtab[i] = g_gtable[i];
 #endif
   // stage this CTA's 128 packed tuples with coalesced 16-byte loads
   const uint32_t base = shard_lo + blockIdx.x * BLOCK;
@@ -112,18 +118,20 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
   __syncthreads();
   const uint32_t idx = base + tid;
   bool ok = false;
-  if (idx < shard_hi) {
-    ibft_sig_item it;
-    {
-      uint32_t* w = reinterpret_cast<uint32_t*>(&it);
-      const uint32_t* s = s_items + tid * IBFT_ITEM_ROW_WORDS;
+  ibft_sig_item it;
+  {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+    const uint32_t* s = s_items + tid * IBFT_ITEM_ROW_WORDS;
 #pragma unroll
-      for (int i = 0; i < 32; i++) w[i] = s[i];
-    }
+    for (int i = 0; i < 32; i++) w[i] = s[i];
+  }
+  __syncthreads();  // the staging area becomes the R tables from here on
+  if (idx < shard_hi) {
     uint8_t z[32], addr[20];
     bool have = item_digest(it, arena, arena_len, z);
     gtab_view G{s_gtab};
-    bool rec = have && ecrecover_address(it.r, it.s, it.v, z, G, addr);
+    rtab_view T{s_rtab + tid, (uint32_t)BLOCK};
+    bool rec = have && ecrecover_address(it.r, it.s, it.v, z, G, T, addr);
     if (!rec) {
 #pragma unroll
       for (int i = 0; i < 20; i++) addr[i] = 0;
@@ -280,9 +288,9 @@ __global__ void k_keccak_batch(const uint8_t* __restrict__ arena, size_t arena_l
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_debug_op(int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint32_t n, uint8_t* out,
                            uint32_t stride) {
-#if IBFT_WG <= 8
-  __shared__ uint32_t s_gtab[24 * IBFT_GTAB_ENTRIES];
-  for (uint32_t i = threadIdx.x; i < 24 * IBFT_GTAB_ENTRIES; i += blockDim.x) s_gtab[i] = g_gtable[i];
+#if IBFT_GTAB_SMEM
+  __shared__ uint32_t s_gtab[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];
+  for (uint32_t i = threadIdx.x; i < IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES; i += blockDim.x) s_gtab[i] = g_gtable[i];
   __syncthreads();
 #else
   const uint32_t* s_gtab = g_gtable;
@@ -320,7 +328,9 @@ __global__ void k_debug_op(int op, const uint8_t* a, const uint8_t* b, const uin
       aff P;
       P.x = fe_from_be(pc);
       P.y = fe_from_be(pc + 32);
-      jac Q = ecmult_double(sc_reduce_once(sc_from_be(pa)), sc_reduce_once(sc_from_be(pb)), P, G);
+      uint32_t rtab[IBFT_RTAB_WORDS];
+      rtab_view T{rtab, 1};
+      jac Q = ecmult_double(sc_reduce_once(sc_from_be(pa)), sc_reduce_once(sc_from_be(pb)), P, G, T);
       for (int k = 0; k < 64; k++) o[k] = 0;
       if (!(Q.inf || fe_is_zero(Q.z))) {
         fe zi = IBFT_FE_INV(Q.z), zi2 = fe_sqr(zi);
@@ -503,7 +513,9 @@ static int engine_alloc(ibft_engine* e) {
   CU(cudaHostAlloc(&e->h_results, (size_t)p.max_groups * sizeof(ibft_group_result), cudaHostAllocDefault));
   e->slots.resize(p.max_table_slots);
   e->slots_shadow.assign(p.max_table_slots, slot_dev{});
-  CU(cudaMemcpyToSymbol(g_gtable, IBFT_GTABLE, sizeof(uint32_t) * 24 * IBFT_GTAB_ENTRIES));
+  CU(cudaMemcpyToSymbol(g_gtable, IBFT_GTABLE, sizeof(uint32_t) * IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES));
+  CU(cudaFuncSetAttribute(k_recover<IBFT_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, IBFT_BLOCK * IBFT_RTAB_WORDS * 4));
+  CU(cudaFuncSetAttribute(k_recover<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * IBFT_RTAB_WORDS * 4));
   CU(cudaFuncGetAttributes(&e->recover_attr, k_recover<IBFT_BLOCK>));
   {
     cudaDeviceProp prop;
@@ -554,7 +566,7 @@ extern "C" int ibft_engine_device_info(ibft_engine* e, ibft_device_info* out) {
   out->total_mem = prop.totalGlobalMem;
   out->abi_version = IBFT_ABI_VERSION;
   out->kernel_regs = e->recover_attr.numRegs;
-  out->kernel_smem_bytes = (int32_t)e->recover_attr.sharedSizeBytes;
+  out->kernel_smem_bytes = (int32_t)e->recover_attr.sharedSizeBytes + IBFT_BLOCK * IBFT_RTAB_WORDS * 4;
   out->block_threads = IBFT_BLOCK;
   return IBFT_OK;
 }
@@ -690,11 +702,11 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
   if (hi <= lo) return IBFT_OK;
   if (hi - lo <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs (latency path)
     uint32_t blocks = (hi - lo + 31) / 32;
-    k_recover<32><<<blocks, 32, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+    k_recover<32><<<blocks, 32, 32 * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                          e->p.max_table_slots, d_bitmap, d_recovered);
   } else {
     uint32_t blocks = (hi - lo + IBFT_BLOCK - 1) / IBFT_BLOCK;
-    k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+    k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                                          e->p.max_table_slots, d_bitmap, d_recovered);
   }
   e->launches++;

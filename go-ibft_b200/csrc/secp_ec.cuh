@@ -103,29 +103,51 @@ IBFT_PT jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
 // u1*G + u2*R
 // ------------------------------------------------------------------------------------------------
 #ifndef IBFT_WG
-#define IBFT_WG 8  // generator window: 2^(WG-1) table entries of (x, y, beta*x)
+#define IBFT_WG 8  // generator window: 2^(WG-1) table entries of (x, y)
 #endif
 #define IBFT_WR 4  // per-signature window: table {1..8} * R
 #define IBFT_GTAB_ENTRIES (1 << (IBFT_WG - 1))
 #define IBFT_NWIN_R 33  // ceil(130 / 4)
 static_assert(IBFT_WG % IBFT_WR == 0, "generator window must be a multiple of the R window");
 
-// Generator table accessor: entry i (0-based) = (i+1)*G as 24 words x[8] y[8] bx[8].
+// Generator table accessor: entry i (0-based) = (i+1)*G as 16 words x[8] y[8] (shared memory on the device).
+#define IBFT_GTAB_ENTRY_WORDS 16
 struct gtab_view {
-  const uint32_t* base;  // shared or global memory
-  IBFT_HD void load(int idx, bool lambda, fe& x, fe& y) const {
-    const uint32_t* e = base + 24 * idx;
+  const uint32_t* base;
+  IBFT_HD void load(int idx, fe& x, fe& y) const {
+    const uint32_t* e = base + IBFT_GTAB_ENTRY_WORDS * idx;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      x.v[i] = lambda ? e[16 + i] : e[i];
+      x.v[i] = e[i];
       y.v[i] = e[8 + i];
     }
   }
 };
 
-struct rtab_entry {
-  fe x, y, bx;  // affine multiple of R and beta*x (the lambda-image shares y)
+// Per-signature table {1..8}*R (affine x, y; 16 words per entry).  On the device it lives in SHARED memory, interleaved
+// across the CTA's threads -- word (entry*16 + limb) of thread t sits at base[(entry*16 + limb) * stride + t] -- so that
+// every lane always hits its own bank whatever entry it selects (conflict-free), and none of it ever reaches HBM.  (Kept
+// in thread-local memory, the tables were written back through L2: 0.86 GB of DRAM writes per 2^20-signature launch in ncu
+// r01_v4, 5x the algorithmic traffic.)  The host emulation passes a plain array with stride 1.
+struct rtab_view {
+  uint32_t* base;
+  uint32_t stride;
+  IBFT_HD void store(int entry, const fe& x, const fe& y) const {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      base[(uint32_t)(entry * 16 + i) * stride] = x.v[i];
+      base[(uint32_t)(entry * 16 + 8 + i) * stride] = y.v[i];
+    }
+  }
+  IBFT_HD void load(int entry, fe& x, fe& y) const {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      x.v[i] = base[(uint32_t)(entry * 16 + i) * stride];
+      y.v[i] = base[(uint32_t)(entry * 16 + 8 + i) * stride];
+    }
+  }
 };
+#define IBFT_RTAB_WORDS 128  // 8 entries x 16 words per signature
 
 // inversion used for the per-signature table; defined by the including translation unit (verify_core.cuh)
 IBFT_HD fe fe_inv_for_table(const fe& a);
@@ -139,7 +161,7 @@ IBFT_HD fe fe_inv_for_table(const fe& a);
 // Returns u1*G + u2*R (R affine, on the curve) as a Jacobian point.  u1, u2 in [0, n).
 // Every loop below is deliberately ROLLED and each group-law routine appears exactly once in the instruction stream:
 // the kernel is instruction-cache bound otherwise (see secp_fe.cuh, IBFT_FN).
-IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_view& G) {
+IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_view& G, const rtab_view& T) {
   // digit streams: 0 = u2 half 1 (R), 1 = u2 half 2 (lambda R), 2 = u1 half 1 (G), 3 = u1 half 2 (lambda G)
   uint32_t ks[4][6];
   bool kneg[4];
@@ -159,19 +181,21 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
   // {1..8} * R: entry m holds (m+1)R; even multiples by doubling, odd ones by adding R.  The table is then made
   // AFFINE with one shared inversion (Montgomery's trick over the seven Z's), so that every addition of the main loop
   // is a mixed addition (8M+3S instead of 12M+4S) and the loop holds a single adder.
-  rtab_entry tab[8];
+  const fe beta = fe_beta();
   {
-    const fe beta = fe_beta();
     fe zs[8];  // Z of entry m
-    tab[0].x = R.x; tab[0].y = R.y; zs[0] = fe_from_u32(1);
+    T.store(0, R.x, R.y);
+    zs[0] = fe_from_u32(1);
     IBFT_ROLLED
     for (int m = 1; m < 8; m++) {
       jac p, t;
       int src = (m & 1) ? ((m + 1) >> 1) - 1 : m - 1;
-      p.x = tab[src].x; p.y = tab[src].y; p.z = zs[src]; p.inf = false;
+      T.load(src, p.x, p.y);
+      p.z = zs[src]; p.inf = false;
       if (m & 1) t = jac_double(p);
       else t = jac_add_affine(p, R.x, R.y);
-      tab[m].x = t.x; tab[m].y = t.y; zs[m] = t.z;
+      T.store(m, t.x, t.y);
+      zs[m] = t.z;
     }
     // prefix products pre[m] = Z_1 * ... * Z_m (Z_0 = 1), one inversion, then peel the inverses off backwards
     fe pre[8];
@@ -184,11 +208,10 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
       fe zi = m > 1 ? fe_mul(acc_inv, pre[m - 1]) : acc_inv;  // 1 / Z_m
       if (m > 1) acc_inv = fe_mul(acc_inv, zs[m]);
       fe zi2 = fe_sqr(zi);
-      tab[m].x = fe_mul(tab[m].x, zi2);
-      tab[m].y = fe_mul(tab[m].y, fe_mul(zi2, zi));
+      fe x, y;
+      T.load(m, x, y);
+      T.store(m, fe_mul(x, zi2), fe_mul(y, fe_mul(zi2, zi)));
     }
-    IBFT_ROLLED
-    for (int m = 0; m < 8; m++) tab[m].bx = fe_mul(tab[m].x, beta);
   }
 
   jac acc;
@@ -208,12 +231,9 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
       if (d != 0) {
         int idx = (d < 0 ? -d : d) - 1;
         fe x, y;
-        if (s < 2) {
-          x = (s & 1) ? tab[idx].bx : tab[idx].x;
-          y = tab[idx].y;
-        } else {
-          G.load(idx, (s & 1) != 0, x, y);
-        }
+        if (s < 2) T.load(idx, x, y);
+        else G.load(idx, x, y);
+        if (s & 1) x = fe_mul(x, beta);  // lambda * (x, y) = (beta x, y)
         if ((d < 0) != kneg[s]) y = fe_neg(y);
         acc = jac_add_affine(acc, x, y);
       }

@@ -49,7 +49,7 @@ IBFT_HD bool item_digest(const ibft_sig_item& it, const uint8_t* arena, size_t a
 
 // Recover the signer of (r, s, v) over digest z.  Returns false when the signature is invalid; addr20 then zero.
 IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t v, const uint8_t* z_be,
-                               const gtab_view& G, uint8_t* addr20) {
+                               const gtab_view& G, const rtab_view& T, uint8_t* addr20) {
 #pragma unroll
   for (int i = 0; i < 20; i++) addr20[i] = 0;
   sc r = sc_from_be(r_be), s = sc_from_be(s_be);
@@ -72,7 +72,7 @@ IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t
   sc rinv = IBFT_SC_INV(r);
   sc u1 = sc_neg(sc_mul(z, rinv));
   sc u2 = sc_mul(s, rinv);
-  jac Q = ecmult_double(u1, u2, R, G);
+  jac Q = ecmult_double(u1, u2, R, G, T);
   if (Q.inf || fe_is_zero(Q.z)) return false;
   fe zi = IBFT_FE_INV(Q.z);
   fe zi2 = fe_sqr(zi);

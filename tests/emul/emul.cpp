@@ -19,7 +19,9 @@ int emul_verify_item(const ibft_sig_item* it, const uint8_t* arena, size_t arena
   memset(recovered20, 0, 20);
   if (!item_digest(*it, arena, arena_len, z)) return 0;
   gtab_view G{IBFT_GTABLE};
-  if (!ecrecover_address(it->r, it->s, it->v, z, G, addr)) return 0;
+  uint32_t rtab[IBFT_RTAB_WORDS];
+  rtab_view T{rtab, 1};
+  if (!ecrecover_address(it->r, it->s, it->v, z, G, T, addr)) return 0;
   memcpy(recovered20, addr, 20);
   return memcmp(addr, it->signer, 20) == 0;
 }
@@ -55,7 +57,9 @@ int emul_debug_op(int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, 
       aff P;
       P.x = fe_from_be(c);
       P.y = fe_from_be(c + 32);
-      jac Q = ecmult_double(sc_reduce_once(sc_from_be(a)), sc_reduce_once(sc_from_be(b)), P, G);
+      uint32_t rtab[IBFT_RTAB_WORDS];
+      rtab_view T{rtab, 1};
+      jac Q = ecmult_double(sc_reduce_once(sc_from_be(a)), sc_reduce_once(sc_from_be(b)), P, G, T);
       memset(out, 0, 64);
       if (Q.inf || fe_is_zero(Q.z)) return 1;
       fe zi = IBFT_FE_INV(Q.z), zi2 = fe_sqr(zi);
