@@ -284,6 +284,43 @@ __global__ void k_keccak_batch(const uint8_t* __restrict__ arena, size_t arena_l
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// batched signing (MessageConstructor side)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+k_sign(const uint8_t* __restrict__ privkeys, const uint8_t* __restrict__ digests, const uint8_t* __restrict__ nonces, uint32_t n,
+       uint8_t* __restrict__ sigs) {
+  __shared__ uint32_t s_gtab[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];
+  __shared__ uint32_t s_rtab[64 * IBFT_RTAB_WORDS];
+  for (uint32_t i = threadIdx.x; i < IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES; i += 64) s_gtab[i] = g_gtable[i];
+  __syncthreads();
+  uint32_t i = blockIdx.x * 64 + threadIdx.x;
+  if (i >= n) return;
+  uint8_t d[32], z[32], k[32], sig[65];
+#pragma unroll
+  for (int j = 0; j < 32; j++) { d[j] = privkeys[32 * (size_t)i + j]; z[j] = digests[32 * (size_t)i + j]; }
+  gtab_view G{s_gtab};
+  rtab_view T{s_rtab + threadIdx.x, 64u};
+  bool ok = false;
+  if (nonces != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) k[j] = nonces[32 * (size_t)i + j];
+    ok = ecdsa_sign(d, z, k, G, T, sig);
+  } else {
+    // derived nonce: k = Keccak-256(d || z || ctr), ctr = 0, 1, ... until usable (deterministic, unique per (key, digest))
+    for (uint32_t ctr = 0; ctr < 4 && !ok; ctr++) {
+      uint8_t buf[65];
+#pragma unroll
+      for (int j = 0; j < 32; j++) { buf[j] = d[j]; buf[32 + j] = z[j]; }
+      buf[64] = (uint8_t)ctr;
+      keccak256_bytes(buf, 65, k);
+      ok = ecdsa_sign(d, z, k, G, T, sig);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 65; j++) sigs[65 * (size_t)i + j] = ok ? sig[j] : (uint8_t)0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // primitive parity hooks + integer-pipe probes
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_debug_op(int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint32_t n, uint8_t* out,
@@ -958,6 +995,40 @@ extern "C" int ibft_keccak256_batch(ibft_engine* e, const uint8_t* arena, size_t
 done:
 #undef CUK
   cudaFree(d_a); cudaFree(d_o); cudaFree(d_off); cudaFree(d_len);
+  return rc;
+}
+
+extern "C" int ibft_sign_batch(ibft_engine* e, const uint8_t* privkeys, const uint8_t* digests, const uint8_t* nonces, uint32_t n,
+                               uint8_t* sigs65_out) {
+  if (!e || (n && (!privkeys || !digests || !sigs65_out))) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  if (n == 0) return IBFT_OK;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->p.device));
+  uint8_t *d_d = nullptr, *d_z = nullptr, *d_k = nullptr, *d_s = nullptr;
+  int rc = IBFT_OK;
+  cudaError_t ce;
+#define CUK(call) if ((ce = (call)) != cudaSuccess) { set_err("%s failed: %s", #call, cudaGetErrorString(ce)); rc = IBFT_ERR_CUDA; goto done; }
+  CUK(cudaMalloc(&d_d, (size_t)n * 32));
+  CUK(cudaMalloc(&d_z, (size_t)n * 32));
+  CUK(cudaMalloc(&d_s, (size_t)n * 65));
+  CUK(cudaMemcpyAsync(d_d, privkeys, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+  CUK(cudaMemcpyAsync(d_z, digests, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+  if (nonces) {
+    CUK(cudaMalloc(&d_k, (size_t)n * 32));
+    CUK(cudaMemcpyAsync(d_k, nonces, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+  }
+  k_sign<<<(n + 63) / 64, 64, 0, e->stream>>>(d_d, d_z, d_k, n, d_s);
+  e->launches++;
+  CUK(cudaGetLastError());
+  CUK(cudaMemcpyAsync(sigs65_out, d_s, (size_t)n * 65, cudaMemcpyDeviceToHost, e->stream));
+  CUK(cudaStreamSynchronize(e->stream));
+  // private keys do not stay on the device
+  cudaMemsetAsync(d_d, 0, (size_t)n * 32, e->stream);
+  if (d_k) cudaMemsetAsync(d_k, 0, (size_t)n * 32, e->stream);
+  cudaStreamSynchronize(e->stream);
+done:
+#undef CUK
+  cudaFree(d_d); cudaFree(d_z); cudaFree(d_k); cudaFree(d_s);
   return rc;
 }
 

@@ -87,6 +87,39 @@ IBFT_HD sc sc_neg(const sc& a) {
   return r;
 }
 
+// a + b mod n, a, b in [0, n)
+IBFT_HD sc sc_add(const sc& a, const sc& b) {
+  sc t;
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.v[i] + b.v[i];
+    t.v[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  // a + b < 2n < 2^257: subtract n when the sum overflowed 2^256 or is >= n
+  sc u;
+  uint64_t d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    d += (uint64_t)t.v[i] + (i < 5 ? sc_nc_limb(i) : 0u);
+    u.v[i] = (uint32_t)d;
+    d >>= 32;
+  }
+  bool ge = (c != 0) || (d != 0);  // (sum + 2^256 - n) carried  <=>  sum >= n
+  sc r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = ge ? u.v[i] : t.v[i];
+  return r;
+}
+// a > (n-1)/2 ?  (the "high-s" half)
+IBFT_HD bool sc_is_high(const sc& a) {
+  const uint32_t h[8] = {0x681B20A0u, 0xDFE92F46u, 0x57A4501Du, 0x5D576E73u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x7FFFFFFFu};  // (n-1)/2
+  for (int i = 7; i >= 0; i--)
+    if (a.v[i] != h[i]) return a.v[i] > h[i];
+  return false;
+}
+
 // 512-bit R -> R mod n.  2^256 = NC (mod n), NC = 2^256 - n is 129 bits: three folds.
 IBFT_HD sc sc_reduce512(const uint32_t* R) {
   // fold 1: acc1 = L + H * NC                      (< 2^386: 13 limbs + carry)

@@ -82,4 +82,43 @@ IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t
   return true;
 }
 
+// ECDSA signing with a given nonce (the MessageConstructor side: reference core/backend.go:12-34 requires every built
+// message to be signed and BuildCommitMessage to create a committed seal).  sig65 = R||S||V, s normalised to the low half.
+// Returns false when the nonce is unusable (k = 0 mod n, R.x >= n, r = 0 or s = 0) -- same rule as oracle_sign_with_k.
+IBFT_HD bool ecdsa_sign(const uint8_t* d_be, const uint8_t* z_be, const uint8_t* k_be, const gtab_view& G, const rtab_view& T,
+                        uint8_t* sig65) {
+#pragma unroll
+  for (int i = 0; i < 65; i++) sig65[i] = 0;
+  sc k = sc_from_be(k_be);
+  if (sc_is_zero(k) || sc_ge_n(k)) return false;
+  sc d = sc_reduce_once(sc_from_be(d_be));
+  sc z = sc_reduce_once(sc_from_be(z_be));
+  aff g1;
+  G.load(0, g1.x, g1.y);  // 1*G; its digit streams are all zero (u2 = 0), only the generator streams add
+  sc zero;
+#pragma unroll
+  for (int i = 0; i < 8; i++) zero.v[i] = 0;
+  jac Rj = ecmult_double(k, zero, g1, G, T);
+  if (Rj.inf || fe_is_zero(Rj.z)) return false;
+  fe zi = IBFT_FE_INV(Rj.z);
+  fe zi2 = fe_sqr(zi);
+  fe rx = fe_normalize(fe_mul(Rj.x, zi2));
+  fe ry = fe_normalize(fe_mul(Rj.y, fe_mul(zi2, zi)));
+  sc r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = rx.v[i];
+  if (sc_ge_n(r) || sc_is_zero(r)) return false;
+  sc s = sc_mul(IBFT_SC_INV(k), sc_add(z, sc_mul(r, d)));
+  if (sc_is_zero(s)) return false;
+  uint8_t v = (uint8_t)(ry.v[0] & 1u);
+  if (sc_is_high(s)) {
+    s = sc_neg(s);
+    v ^= 1;
+  }
+  sc_to_be(r, sig65);
+  sc_to_be(s, sig65 + 32);
+  sig65[64] = v;
+  return true;
+}
+
 }  // namespace ibft

@@ -31,7 +31,7 @@ EXPORTS = [
     "ibft_abi_version", "ibft_last_error", "ibft_engine_create", "ibft_engine_destroy", "ibft_engine_device_info",
     "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_verify_submit", "ibft_verify_poll",
     "ibft_verify_wait", "ibft_bind_groups", "ibft_verify_batch_device", "ibft_quorum_reduce_device",
-    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_engine_launch_count", "ibft_probe_int_peak", "ibft_debug_op",
+    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_probe_int_peak", "ibft_debug_op",
 ]
 
 
@@ -80,6 +80,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.ibft_quorum_reduce_device.argtypes = [c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]
     lib.ibft_get_voted_bitmap.argtypes = [c_void_p, c_uint32, c_void_p, c_uint32]
     lib.ibft_keccak256_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_uint32, c_void_p]
+    lib.ibft_sign_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]
     lib.ibft_probe_int_peak.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double)]
     lib.ibft_debug_op.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_uint32]
     if path is None:
@@ -214,6 +215,18 @@ class Engine:
         arena = np.frombuffer(b"".join(messages), dtype=np.uint8) if int(lens.sum()) else np.zeros(0, dtype=np.uint8)
         out = np.zeros((n, 32), dtype=np.uint8)
         self._check(self.lib.ibft_keccak256_batch(self.handle, _ptr(arena) if len(arena) else None, len(arena), _ptr(offs), _ptr(lens), n, _ptr(out)))
+        return [bytes(out[i]) for i in range(n)]
+
+    # ---- signing (MessageConstructor side)
+    def sign_batch(self, privkeys: list[int], digests: list[bytes], nonces: list[int] | None = None) -> list[bytes]:
+        n = len(privkeys)
+        if n == 0:
+            return []
+        D = np.frombuffer(b"".join(x.to_bytes(32, "big") for x in privkeys), dtype=np.uint8)
+        Z = np.frombuffer(b"".join(digests), dtype=np.uint8)
+        K = np.frombuffer(b"".join(x.to_bytes(32, "big") for x in nonces), dtype=np.uint8) if nonces is not None else None
+        out = np.zeros((n, 65), dtype=np.uint8)
+        self._check(self.lib.ibft_sign_batch(self.handle, _ptr(D), _ptr(Z), _ptr(K), n, _ptr(out)))
         return [bytes(out[i]) for i in range(n)]
 
     # ---- primitive parity hooks (tests)

@@ -172,6 +172,14 @@ int ibft_get_voted_bitmap(ibft_engine* e, uint32_t group, uint32_t* words_out, u
 int ibft_keccak256_batch(ibft_engine* e, const uint8_t* arena, size_t arena_len, const uint32_t* offsets,
                          const uint32_t* lens, uint32_t n, uint8_t* out32);
 
+/* signing (the MessageConstructor side) --------------------------------------------------------------- */
+/* Batched ECDSA signing for MessageConstructor (core/backend.go:12-34: every Build*Message must be signed by the validator,
+ * BuildCommitMessage must create the committed seal).  privkeys, digests: n x 32 bytes big-endian; nonces: n x 32 bytes or
+ * NULL (then k = Keccak-256(d || z || ctr) mod-checked, deterministic per (key, digest)); sigs65_out: n x 65 bytes R||S||V,
+ * s in the low half.  An unusable nonce yields an all-zero signature.  HOST buffers. */
+int ibft_sign_batch(ibft_engine* e, const uint8_t* privkeys, const uint8_t* digests, const uint8_t* nonces, uint32_t n,
+                    uint8_t* sigs65_out);
+
 /* measurement / test hooks ------------------------------------------------------------------------- */
 /* Number of kernel launches issued by this engine since creation (bench.py reports gpu_launches from it). */
 uint64_t ibft_engine_launch_count(ibft_engine* e);

@@ -71,3 +71,10 @@ int emul_debug_op(int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, 
   }
 }
 }
+
+extern "C" int emul_sign(const uint8_t* d, const uint8_t* z, const uint8_t* k, uint8_t* sig65) {
+  gtab_view G{IBFT_GTABLE};
+  uint32_t rtab[IBFT_RTAB_WORDS];
+  rtab_view T{rtab, 1};
+  return ecdsa_sign(d, z, k, G, T, sig65) ? 1 : 0;
+}
