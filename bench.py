@@ -321,6 +321,17 @@ def main():
         except Exception:
             pass
     hbm_gbs = kernel_rate * ALGO_BYTES_PER_VERIFY / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this same configuration (per launch)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if int(tj.get("items_per_launch", 0)) == n_local:
+                traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
+                traffic_src = tj.get("capture")
+        except Exception:
+            pass
     line = {
         "metric": "secp256k1_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -330,7 +341,8 @@ def main():
                 "steps": e2e_steps, "api": "ibft_verify_batch (host buffers -> pinned staging -> H2D -> kernels -> D2H bitmap + quorum)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "int32-imad-issue", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-class instr/s",
-                     "frac": achieved / imad_peak, "traffic": None,
+                     "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per k_recover launch (ncu)",
+                     "traffic_source": traffic_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VERIFY * n_local,
                      "kernel": "k_recover", "kernel_ms": ms_kernel, "kernel_verifies_per_s_per_gpu": kernel_rate,
                      "algorithmic_instr_per_verify": ALGO_IMAD_PER_VERIFY,
                      "peak_source": "dependent-free mad.lo.u32 probe on this GPU (ibft_probe_int_peak), measured live",
