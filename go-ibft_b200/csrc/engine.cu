@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(BLOCK, (IBFT_MIN_BLOCKS * IBFT_BLOCK) / BLOCK)
 k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
           uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
           const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
-          uint8_t* __restrict__ recovered) {
+          uint8_t* __restrict__ recovered, uint8_t* __restrict__ status) {
 #if IBFT_GTAB_SMEM
   __shared__ uint32_t s_gtab[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];
 #else
@@ -127,18 +127,21 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
   }
   __syncthreads();  // the staging area becomes the R tables from here on
   if (idx < shard_hi) {
-    uint8_t z[32], addr[20];
-    bool have = item_digest(it, arena, arena_len, z);
+    uint8_t addr[20];
+    resolved_item ri;
+    bool have = false;
+    int st = resolve_item(it, arena, arena_len, ri, &have);  // raw frames are parsed here (IBFT_KIND_WIRE*)
+    if (status != nullptr) status[idx] = (uint8_t)st;
     gtab_view G{s_gtab};
     rtab_view T{s_rtab + tid, (uint32_t)BLOCK};
-    bool rec = have && ecrecover_address(it.r, it.s, it.v, z, G, T, addr);
+    bool rec = have && ecrecover_address(ri.r, ri.s, ri.v, ri.z, G, T, addr);
     if (!rec) {
 #pragma unroll
       for (int i = 0; i < 20; i++) addr[i] = 0;
     }
     ok = rec;
 #pragma unroll
-    for (int i = 0; i < 20; i++) ok = ok && (addr[i] == it.signer[i]);
+    for (int i = 0; i < 20; i++) ok = ok && (addr[i] == ri.signer[i]);
     // validator-set membership at the message's height (reference core/backend.go:44)
     if (ok && groups != nullptr) {
       if (it.group >= n_groups) {
@@ -147,7 +150,7 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
         uint32_t slot = groups[it.group].table_slot;
         if (slot != IBFT_NO_TABLE) {
           if (slot >= n_slots || !slots[slot].valid) ok = false;
-          else ok = lookup_validator(slots[slot], it.signer) >= 0;
+          else ok = lookup_validator(slots[slot], ri.signer) >= 0;
         }
       }
     }
@@ -169,7 +172,8 @@ struct group_dev {
   uint32_t n_words;
 };
 
-__global__ void k_quorum_mark(const ibft_sig_item* __restrict__ items, uint32_t n, const uint32_t* __restrict__ bitmap,
+__global__ void k_quorum_mark(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
+                              const uint32_t* __restrict__ bitmap,
                               const ibft_group_desc* __restrict__ groups, const group_dev* __restrict__ gdev,
                               uint32_t n_groups, const slot_dev* __restrict__ slots, uint32_t n_slots,
                               uint32_t* __restrict__ voted, uint32_t* __restrict__ n_valid) {
@@ -183,8 +187,8 @@ __global__ void k_quorum_mark(const ibft_sig_item* __restrict__ items, uint32_t 
   uint32_t slot = groups[g].table_slot;
   if (slot == IBFT_NO_TABLE || slot >= n_slots || !slots[slot].valid) return;
   uint8_t addr[20];
-#pragma unroll
-  for (int k = 0; k < 20; k++) addr[k] = it->signer[k];
+  ibft_sig_item local = *it;
+  if (!item_signer(local, arena, arena_len, addr)) return;
   int v = lookup_validator(slots[slot], addr);
   if (v >= 0) atomicOr(&voted[gdev[g].voted_off + ((uint32_t)v >> 5)], 1u << (v & 31));
 }
@@ -476,6 +480,9 @@ struct ibft_engine {
   uint8_t* d_arena = nullptr;
   uint32_t* d_bitmap = nullptr;
   uint8_t* d_recovered = nullptr;
+  uint8_t* d_status = nullptr;
+  uint8_t* h_status = nullptr;
+  uint32_t last_status_n = 0;
   ibft_group_desc* d_groups = nullptr;
   group_dev* d_gdev = nullptr;
   ibft_group_result* d_results = nullptr;
@@ -498,6 +505,8 @@ struct ibft_engine {
   pending_call pending;
   uint64_t launches = 0;
   int sm_count = 148;
+  const uint8_t* dev_arena = nullptr;
+  size_t dev_arena_len = 0;
   cudaFuncAttributes recover_attr{};
 };
 
@@ -511,6 +520,7 @@ static void engine_free(ibft_engine* e) {
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_powers) cudaFree(s.d_powers);
   }
+  cudaFree(e->d_status); cudaFreeHost(e->h_status);
   cudaFree(e->d_items); cudaFree(e->d_arena); cudaFree(e->d_bitmap); cudaFree(e->d_recovered); cudaFree(e->d_groups);
   cudaFree(e->d_gdev); cudaFree(e->d_results); cudaFree(e->d_voted); cudaFree(e->d_nvalid); cudaFree(e->d_slots);
   cudaFreeHost(e->h_items); cudaFreeHost(e->h_arena); cudaFreeHost(e->h_bitmap); cudaFreeHost(e->h_recovered);
@@ -533,6 +543,8 @@ static int engine_alloc(ibft_engine* e) {
   CU(cudaMalloc(&e->d_arena, std::max<size_t>(p.max_payload_bytes, 16)));
   CU(cudaMalloc(&e->d_bitmap, std::max<size_t>(words, 1) * 4));
   CU(cudaMalloc(&e->d_recovered, n * 20));
+  CU(cudaMalloc(&e->d_status, n));
+  CU(cudaHostAlloc(&e->h_status, n, cudaHostAllocDefault));
   CU(cudaMalloc(&e->d_groups, (size_t)p.max_groups * sizeof(ibft_group_desc)));
   CU(cudaMalloc(&e->d_gdev, (size_t)p.max_groups * sizeof(group_dev)));
   CU(cudaMalloc(&e->d_results, (size_t)p.max_groups * sizeof(ibft_group_result)));
@@ -593,7 +605,7 @@ extern "C" int ibft_engine_device_info(ibft_engine* e, ibft_device_info* out) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, e->p.device));
   memset(out, 0, sizeof *out);
-  snprintf(out->name, sizeof out->name, "%s", prop.name);
+  snprintf(out->name, sizeof out->name, "%.63s", prop.name);
   out->sm_count = prop.multiProcessorCount;
   out->cc_major = prop.major;
   out->cc_minor = prop.minor;
@@ -735,30 +747,30 @@ static int plan_groups(ibft_engine* e, const ibft_group_desc* groups, uint32_t n
 
 static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len,
                           uint32_t lo, uint32_t hi, const ibft_group_desc* d_groups, uint32_t n_groups, uint32_t* d_bitmap,
-                          uint8_t* d_recovered, cudaStream_t st) {
+                          uint8_t* d_recovered, cudaStream_t st, uint8_t* d_status = nullptr) {
   if (hi <= lo) return IBFT_OK;
   if (hi - lo <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs (latency path)
     uint32_t blocks = (hi - lo + 31) / 32;
     k_recover<32><<<blocks, 32, 32 * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                         e->p.max_table_slots, d_bitmap, d_recovered);
+                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status);
   } else {
     uint32_t blocks = (hi - lo + IBFT_BLOCK - 1) / IBFT_BLOCK;
     k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                                         e->p.max_table_slots, d_bitmap, d_recovered);
+                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status);
   }
   e->launches++;
   CU(cudaGetLastError());
   return IBFT_OK;
 }
 
-static int launch_quorum(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint32_t* d_bitmap,
+static int launch_quorum(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len, const uint32_t* d_bitmap,
                          const ibft_group_desc* d_groups, const group_dev* d_gdev, uint32_t n_groups, size_t voted_words,
                          ibft_group_result* d_results, cudaStream_t st) {
   if (n_groups == 0) return IBFT_OK;
   CU(cudaMemsetAsync(e->d_voted, 0, std::max<size_t>(voted_words, 1) * 4, st));
   CU(cudaMemsetAsync(e->d_nvalid, 0, (size_t)n_groups * 4, st));
   if (n) {
-    k_quorum_mark<<<(n + 255) / 256, 256, 0, st>>>(d_items, n, d_bitmap, d_groups, d_gdev, n_groups, e->d_slots,
+    k_quorum_mark<<<(n + 255) / 256, 256, 0, st>>>(d_items, n, d_arena, arena_len, d_bitmap, d_groups, d_gdev, n_groups, e->d_slots,
                                                     e->p.max_table_slots, e->d_voted, e->d_nvalid);
     e->launches++;
     CU(cudaGetLastError());
@@ -825,15 +837,16 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
       CU(cudaStreamWaitEvent(st, e->chunk_ev[c], 0));
     }
     rc = launch_recover(e, e->d_items, n, e->d_arena, arena_len, lo, hi, n_groups ? e->d_groups : nullptr, n_groups, e->d_bitmap,
-                        recovered_out ? e->d_recovered : nullptr, st);
+                        recovered_out ? e->d_recovered : nullptr, st, e->d_status);
     if (rc != IBFT_OK) return rc;
   }
   if (n_groups && results_out) {
-    rc = launch_quorum(e, e->d_items, n, e->d_bitmap, e->d_groups, e->d_gdev, n_groups, voted_words, e->d_results, st);
+    rc = launch_quorum(e, e->d_items, n, e->d_arena, arena_len, e->d_bitmap, e->d_groups, e->d_gdev, n_groups, voted_words, e->d_results, st);
     if (rc != IBFT_OK) return rc;
     CU(cudaMemcpyAsync(e->h_results, e->d_results, (size_t)n_groups * sizeof(ibft_group_result), cudaMemcpyDeviceToHost, st));
   }
   if (n) {
+    CU(cudaMemcpyAsync(e->h_status, e->d_status, (size_t)n, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(e->h_bitmap, e->d_bitmap, (size_t)((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
     if (recovered_out) CU(cudaMemcpyAsync(e->h_recovered, e->d_recovered, (size_t)n * 20, cudaMemcpyDeviceToHost, st));
   }
@@ -858,6 +871,7 @@ static int wait_locked(ibft_engine* e) {
     set_err("device execution failed: %s", cudaGetErrorString(ce));
     return IBFT_ERR_CUDA;
   }
+  e->last_status_n = pc.n;
   if (pc.n) {
     size_t words = (pc.n + 31) / 32;
     memcpy(pc.bitmap_out, e->h_bitmap, words * 4);
@@ -876,6 +890,15 @@ extern "C" int ibft_verify_batch(ibft_engine* e, const ibft_sig_item* items, uin
   int rc = submit_locked(e, items, n, arena, arena_len, groups, n_groups, bitmap_out, results_out, recovered_out);
   if (rc != IBFT_OK) return rc;
   return wait_locked(e);
+}
+
+extern "C" int ibft_last_item_status(ibft_engine* e, uint8_t* status_out, uint32_t n) {
+  if (!e || (n && !status_out)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->pending.active) { set_err("a submitted call is still pending"); return IBFT_ERR_INVALID_ARG; }
+  if (n > e->last_status_n) { set_err("last call had %u items", e->last_status_n); return IBFT_ERR_INVALID_ARG; }
+  memcpy(status_out, e->h_status, n);
+  return IBFT_OK;
 }
 
 extern "C" int ibft_verify_submit(ibft_engine* e, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
@@ -914,6 +937,8 @@ extern "C" int ibft_verify_batch_device(ibft_engine* e, const void* d_items, uin
   std::lock_guard<std::mutex> lk(e->mu);
   CU(cudaSetDevice(e->p.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  e->dev_arena = (const uint8_t*)d_arena;  // remembered for ibft_quorum_reduce_device (raw-frame items carry their signer in the arena)
+  e->dev_arena_len = arena_len;
   // membership is applied by ibft_quorum_reduce_device / the host mirror in this mode when no groups are bound
   return launch_recover(e, (const ibft_sig_item*)d_items, n, (const uint8_t*)d_arena, arena_len, shard_lo, shard_hi,
                         e->last_groups.empty() ? nullptr : e->d_groups, (uint32_t)e->last_groups.size(), (uint32_t*)d_bitmap,
@@ -952,8 +977,8 @@ extern "C" int ibft_quorum_reduce_device(ibft_engine* e, const void* d_items, ui
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
   size_t voted_words = 0;
   for (auto& g : e->last_gdev) voted_words += g.n_words;
-  return launch_quorum(e, (const ibft_sig_item*)d_items, n, (const uint32_t*)d_bitmap, e->d_groups, e->d_gdev, n_groups,
-                       voted_words, (ibft_group_result*)d_results, st);
+  return launch_quorum(e, (const ibft_sig_item*)d_items, n, e->dev_arena, e->dev_arena_len, (const uint32_t*)d_bitmap, e->d_groups,
+                       e->d_gdev, n_groups, voted_words, (ibft_group_result*)d_results, st);
 }
 
 extern "C" int ibft_get_voted_bitmap(ibft_engine* e, uint32_t group, uint32_t* words_out, uint32_t n_words) {

@@ -121,6 +121,32 @@ IBFT_HD void keccak256_bytes(const uint8_t* data, uint32_t len, uint8_t* out) {
     for (int j = 0; j < 8; j++) out[8 * i + j] = (uint8_t)(st[i] >> (8 * j));
 }
 
+// Keccak-256 of the concatenation of two byte spans (a wire frame with its signature field cut out).
+IBFT_HD void keccak256_two_spans(const uint8_t* p1, uint32_t n1, const uint8_t* p2, uint32_t n2, uint8_t* out) {
+  uint64_t st[25];
+#pragma unroll
+  for (int i = 0; i < 25; i++) st[i] = 0;
+  uint32_t pos = 0;
+  for (int span = 0; span < 2; span++) {
+    const uint8_t* p = span ? p2 : p1;
+    uint32_t n = span ? n2 : n1;
+    for (uint32_t i = 0; i < n; i++) {
+      st[pos >> 3] ^= (uint64_t)p[i] << (8 * (pos & 7));
+      if (++pos == 136) {
+        keccak_f1600(st);
+        pos = 0;
+      }
+    }
+  }
+  st[pos >> 3] ^= (uint64_t)0x01 << (8 * (pos & 7));
+  st[16] ^= 0x8000000000000000ULL;
+  keccak_f1600(st);
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) out[8 * i + j] = (uint8_t)(st[i] >> (8 * j));
+}
+
 // Keccak-256 of exactly 64 bytes given as two field elements (X||Y big-endian) -> last 20 bytes (the address)
 // as five big-endian-loaded words: addr[0] = bytes 12..15 of the digest, ...
 IBFT_HD void keccak256_xy_address(const fe& x, const fe& y, uint8_t* addr20) {

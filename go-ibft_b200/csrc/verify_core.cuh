@@ -47,6 +47,185 @@ IBFT_HD bool item_digest(const ibft_sig_item& it, const uint8_t* arena, size_t a
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Raw gossip frames (IBFT_KIND_WIRE / IBFT_KIND_WIRE_SEAL): top-level parse of a proto3 IbftMessage
+// (reference messages/proto/messages.proto:24-44) with a canonical-encoding check.  protobuf-go emits fields in
+// field-number order, omits zero scalars / empty bytes and uses minimal varints; only for such a frame does
+// "frame minus the signature TLV" equal PayloadNoSig (clone, Signature = nil, Marshal: messages/proto/helper.go:13-27).
+// Anything else is handed back to the host (status NEEDS_HOST), never guessed.
+// ------------------------------------------------------------------------------------------------------------
+struct wire_frame {
+  uint32_t from_off, from_len;      // value of field 2
+  uint32_t sig_tag_off, sig_end;    // the whole field-3 TLV
+  uint32_t sig_off, sig_len;        // its value
+  uint32_t type;                    // field 4
+  uint32_t payload_field;           // 0, 6 (prepareData) or 7 (commitData)
+  uint32_t hash_off, hash_len;      // proposalHash inside the payload
+  uint32_t seal_off, seal_len;      // committedSeal (commitData only)
+  bool has_view;
+};
+
+IBFT_HD bool wire_varint(const uint8_t* w, uint32_t len, uint32_t& pos, uint64_t& v) {  // minimal encoding required
+  v = 0;
+  for (int shift = 0; shift < 64; shift += 7) {
+    if (pos >= len) return false;
+    uint8_t b = w[pos++];
+    v |= (uint64_t)(b & 0x7F) << shift;
+    if (!(b & 0x80)) return !(b == 0 && shift > 0);  // a trailing zero group is a non-minimal encoding
+  }
+  return false;
+}
+// LEN field: reads the length, returns the value span; empty values are non-canonical (proto3 omits them)
+IBFT_HD bool wire_len(const uint8_t* w, uint32_t len, uint32_t& pos, uint32_t& off, uint32_t& n, bool allow_empty) {
+  uint64_t l;
+  if (!wire_varint(w, len, pos, l)) return false;
+  if (l > (uint64_t)(len - pos)) return false;
+  if (l == 0 && !allow_empty) return false;
+  off = pos;
+  n = (uint32_t)l;
+  pos += n;
+  return true;
+}
+
+// true: canonical flat PREPARE/COMMIT-payload frame, `f` filled.  false: hand back to the host.
+IBFT_HD bool parse_wire_frame(const uint8_t* w, uint32_t len, wire_frame& f) {
+  f.from_off = f.from_len = f.sig_tag_off = f.sig_end = f.sig_off = f.sig_len = f.type = f.payload_field = 0;
+  f.hash_off = f.hash_len = f.seal_off = f.seal_len = 0;
+  f.has_view = false;
+  f.sig_tag_off = f.sig_end = 0xFFFFFFFFu;
+  uint32_t pos = 0, last_field = 0;
+  while (pos < len) {
+    uint32_t tag_off = pos;
+    uint64_t key;
+    if (!wire_varint(w, len, pos, key)) return false;
+    uint32_t field = (uint32_t)(key >> 3), wt = (uint32_t)(key & 7);
+    if (key >> 35) return false;
+    if (field <= last_field) return false;  // strictly increasing field numbers (also rejects duplicates)
+    last_field = field;
+    uint32_t off, n;
+    switch (field) {
+      case 1: {  // View { height = 1, round = 2 } : present-but-empty is canonical ("0a 00")
+        if (wt != 2 || !wire_len(w, len, pos, off, n, true)) return false;
+        f.has_view = true;
+        uint32_t p = off, end = off + n, lastv = 0;
+        while (p < end) {
+          uint64_t k2, v2;
+          if (!wire_varint(w, end, p, k2)) return false;
+          uint32_t f2 = (uint32_t)(k2 >> 3);
+          if ((k2 & 7) != 0 || f2 < 1 || f2 > 2 || f2 <= lastv) return false;
+          lastv = f2;
+          if (!wire_varint(w, end, p, v2) || v2 == 0) return false;  // zero scalars are omitted
+        }
+        break;
+      }
+      case 2:
+        if (wt != 2 || !wire_len(w, len, pos, off, n, false)) return false;
+        f.from_off = off;
+        f.from_len = n;
+        break;
+      case 3:
+        if (wt != 2 || !wire_len(w, len, pos, off, n, false)) return false;
+        f.sig_tag_off = tag_off;
+        f.sig_end = pos;
+        f.sig_off = off;
+        f.sig_len = n;
+        break;
+      case 4: {
+        uint64_t v;
+        if (wt != 0 || !wire_varint(w, len, pos, v) || v == 0 || v > 0xFFFFFFFFull) return false;
+        f.type = (uint32_t)v;
+        break;
+      }
+      case 6:
+      case 7: {  // PrepareMessage { proposalHash = 1 } / CommitMessage { proposalHash = 1, committedSeal = 2 }
+        if (wt != 2 || !wire_len(w, len, pos, off, n, true)) return false;
+        f.payload_field = field;
+        uint32_t p = off, end = off + n, lastv = 0;
+        while (p < end) {
+          uint64_t k2;
+          if (!wire_varint(w, end, p, k2)) return false;
+          uint32_t f2 = (uint32_t)(k2 >> 3), o2, n2;
+          if ((k2 & 7) != 2 || f2 < 1 || f2 > (field == 7 ? 2u : 1u) || f2 <= lastv) return false;
+          lastv = f2;
+          if (!wire_len(w, end, p, o2, n2, false)) return false;
+          if (f2 == 1) { f.hash_off = o2; f.hash_len = n2; }
+          else { f.seal_off = o2; f.seal_len = n2; }
+        }
+        last_field = 8;  // the oneof holds at most one member
+        break;
+      }
+      default:
+        return false;  // preprepareData / roundChangeData (nested messages) and unknown fields: host path
+    }
+  }
+  if (f.sig_tag_off == 0xFFFFFFFFu) { f.sig_tag_off = f.sig_end = len; }  // no signature field: nothing to cut out
+  return true;
+}
+
+// Everything ecrecover needs for one item, whatever its kind.  Returns IBFT_ITEM_OK or IBFT_ITEM_NEEDS_HOST; *valid is false when
+// the item is structurally invalid (verdict 0 without any arithmetic).
+struct resolved_item {
+  uint8_t r[32], s[32], z[32], signer[20];
+  uint8_t v;
+};
+IBFT_HD int resolve_item(const ibft_sig_item& it, const uint8_t* arena, size_t arena_len, resolved_item& o, bool* valid) {
+  *valid = false;
+  if (it.kind == IBFT_KIND_WIRE || it.kind == IBFT_KIND_WIRE_SEAL) {
+    if ((size_t)it.payload_off + it.payload_len > arena_len) return IBFT_ITEM_OK;
+    const uint8_t* w = arena + it.payload_off;
+    wire_frame f;
+    if (!parse_wire_frame(w, it.payload_len, f)) return IBFT_ITEM_NEEDS_HOST;
+    if (f.from_len != 20) return IBFT_ITEM_OK;  // can never equal a recovered address
+#pragma unroll
+    for (int i = 0; i < 20; i++) o.signer[i] = w[f.from_off + i];
+    if (it.kind == IBFT_KIND_WIRE) {
+      // IsValidValidator (core/backend.go:41-45): needs a view (for the height) and a 65-byte signature
+      if (!f.has_view || f.sig_len != 65) return IBFT_ITEM_OK;
+#pragma unroll
+      for (int i = 0; i < 32; i++) { o.r[i] = w[f.sig_off + i]; o.s[i] = w[f.sig_off + 32 + i]; }
+      o.v = w[f.sig_off + 64];
+      keccak256_two_spans(w, f.sig_tag_off, w + f.sig_end, it.payload_len - f.sig_end, o.z);
+    } else {
+      // IsValidCommittedSeal on the frame: ExtractCommitHash needs type == COMMIT and commitData (messages/helpers.go:51-62),
+      // the seal is commitData.committedSeal with Signer = From (:38-48)
+      if (f.type != 2 || f.payload_field != 7 || f.hash_len != 32 || f.seal_len != 65) return IBFT_ITEM_OK;
+      uint8_t buf[33];
+#pragma unroll
+      for (int i = 0; i < 32; i++) buf[i] = w[f.hash_off + i];
+      buf[32] = 0x02;
+      keccak256_bytes(buf, 33, o.z);
+#pragma unroll
+      for (int i = 0; i < 32; i++) { o.r[i] = w[f.seal_off + i]; o.s[i] = w[f.seal_off + 32 + i]; }
+      o.v = w[f.seal_off + 64];
+    }
+    *valid = true;
+    return IBFT_ITEM_OK;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; i++) { o.r[i] = it.r[i]; o.s[i] = it.s[i]; }
+#pragma unroll
+  for (int i = 0; i < 20; i++) o.signer[i] = it.signer[i];
+  o.v = it.v;
+  *valid = item_digest(it, arena, arena_len, o.z);
+  return IBFT_ITEM_OK;
+}
+
+// the expected signer of an item (for the quorum kernels); false when it has none
+IBFT_HD bool item_signer(const ibft_sig_item& it, const uint8_t* arena, size_t arena_len, uint8_t* signer20) {
+  if (it.kind == IBFT_KIND_WIRE || it.kind == IBFT_KIND_WIRE_SEAL) {
+    if ((size_t)it.payload_off + it.payload_len > arena_len) return false;
+    const uint8_t* w = arena + it.payload_off;
+    wire_frame f;
+    if (!parse_wire_frame(w, it.payload_len, f) || f.from_len != 20) return false;
+#pragma unroll
+    for (int i = 0; i < 20; i++) signer20[i] = w[f.from_off + i];
+    return true;
+  }
+#pragma unroll
+  for (int i = 0; i < 20; i++) signer20[i] = it.signer[i];
+  return true;
+}
+
 // Recover the signer of (r, s, v) over digest z.  Returns false when the signature is invalid; addr20 then zero.
 IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t v, const uint8_t* z_be,
                                const gtab_view& G, const rtab_view& T, uint8_t* addr20) {

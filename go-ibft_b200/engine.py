@@ -14,7 +14,8 @@ import numpy as np
 from . import build as _build
 
 IBFT_OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_CAPACITY, ERR_VOTING_POWER, ERR_NO_TABLE = range(7)
-KIND_DIGEST, KIND_PAYLOAD, KIND_SEAL, KIND_INVALID = 0, 1, 2, 255
+KIND_DIGEST, KIND_PAYLOAD, KIND_SEAL, KIND_WIRE, KIND_WIRE_SEAL, KIND_INVALID = 0, 1, 2, 3, 4, 255
+ITEM_OK, ITEM_NEEDS_HOST = 0, 1
 NO_TABLE = 0xFFFF
 DBG = dict(FE_MUL=1, FE_SQR=2, FE_INV=3, FE_SQRT=4, SC_MUL=5, SC_INV=6, ECMULT=7, FE_ADD=8, FE_SUB=9, GLV=10)
 
@@ -29,7 +30,7 @@ assert ITEM_DTYPE.itemsize == 128 and GROUP_DTYPE.itemsize == 8 and RESULT_DTYPE
 
 EXPORTS = [
     "ibft_abi_version", "ibft_last_error", "ibft_engine_create", "ibft_engine_destroy", "ibft_engine_device_info",
-    "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_verify_submit", "ibft_verify_poll",
+    "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_last_item_status", "ibft_verify_submit", "ibft_verify_poll",
     "ibft_verify_wait", "ibft_bind_groups", "ibft_verify_batch_device", "ibft_quorum_reduce_device",
     "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_probe_int_peak", "ibft_debug_op",
 ]
@@ -73,6 +74,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.ibft_get_quorum.argtypes = [c_void_p, c_uint32, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint32)]
     for name in ("ibft_verify_batch", "ibft_verify_submit"):
         getattr(lib, name).argtypes = [c_void_p, c_void_p, c_uint32, c_void_p, c_size_t, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]
+    lib.ibft_last_item_status.argtypes = [c_void_p, c_void_p, c_uint32]
     lib.ibft_verify_poll.argtypes = [c_void_p, POINTER(c_int)]
     lib.ibft_verify_wait.argtypes = [c_void_p]
     lib.ibft_bind_groups.argtypes = [c_void_p, c_void_p, c_uint32]
@@ -167,6 +169,11 @@ class Engine:
                                                _ptr(arena_np) if len(arena_np) else None, len(arena_np),
                                                _ptr(groups) if ng else None, ng, _ptr(bitmap), _ptr(results), _ptr(recovered)))
         return bitmap[: (n + 31) // 32], results, recovered
+
+    def last_item_status(self, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.ibft_last_item_status(self.handle, _ptr(out) if n else None, n))
+        return out
 
     def verify_submit(self, items, arena, groups, bitmap, results, recovered=None):
         """Async variant; caller owns (and keeps alive) the output arrays until wait()."""

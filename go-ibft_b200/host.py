@@ -49,6 +49,10 @@ def load_host() -> ctypes.CDLL:
         lib.ibfthost_set_validators.argtypes = [c_void_p, c_uint64, c_char_p, POINTER(c_uint32), c_char_p, c_uint32]
         lib.ibfthost_set_batching.argtypes = [c_void_p, c_int]
         lib.ibfthost_set_batching.restype = None
+        lib.ibfthost_set_wire_frames.argtypes = [c_void_p, c_int]
+        lib.ibfthost_set_wire_frames.restype = None
+        lib.ibfthost_gpu_frames_handed_back.argtypes = [c_void_p]
+        lib.ibfthost_gpu_frames_handed_back.restype = c_uint64
         lib.ibfthost_set_state.argtypes = [c_void_p, c_uint64, c_uint64, c_int, c_char_p, c_size_t]
         lib.ibfthost_get_state_name.argtypes = [c_void_p]
         for f in ("ibfthost_store_add", "ibfthost_add_message", "ibfthost_is_acceptable", "ibfthost_is_valid_validator"):
@@ -147,6 +151,12 @@ class HostContext:
 
     def set_batching(self, on: bool):
         self.lib.ibfthost_set_batching(self.ctx, int(on))
+
+    def set_wire_frames(self, on: bool):
+        self.lib.ibfthost_set_wire_frames(self.ctx, int(on))
+
+    def gpu_frames_handed_back(self) -> int:
+        return int(self.lib.ibfthost_gpu_frames_handed_back(self.ctx))
 
     def set_state(self, height: int, rnd: int, state_name: int = 0, proposal_wire: bytes | None = None) -> int:
         return self.lib.ibfthost_set_state(self.ctx, height, rnd, state_name, proposal_wire, len(proposal_wire) if proposal_wire else 0)

@@ -111,6 +111,9 @@ int ibfthost_set_validators(ibfthost_ctx* c, uint64_t height, const uint8_t* add
 }
 
 void ibfthost_set_batching(ibfthost_ctx* c, int on) { c->ibft->batching = on != 0; }
+// GPU verifier: submit PREPARE / COMMIT messages as raw frames (IBFT_KIND_WIRE)
+void ibfthost_set_wire_frames(ibfthost_ctx* c, int on) { if (c->gpu) c->gpu->use_wire_frames = on != 0; }
+uint64_t ibfthost_gpu_frames_handed_back(ibfthost_ctx* c) { return c->gpu ? c->gpu->frames_handed_back() : 0; }
 
 // state.view / state.name / state.proposalMessage
 int ibfthost_set_state(ibfthost_ctx* c, uint64_t height, uint64_t round, int state_name, const uint8_t* proposal_wire, size_t len) {

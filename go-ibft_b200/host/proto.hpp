@@ -59,6 +59,7 @@ struct IbftMessage {  // messages.proto:24-44
   Bytes from, signature;
   uint32_t type = PREPREPARE;
   PayloadKind payload_kind = PAYLOAD_NONE;  // which oneof member is set (independent of `type`, as in Go)
+  Bytes raw_wire;  // the frame this message was decoded from (top-level decode only); lets the GPU verifier submit raw frames
   PrePrepareMessage preprepare;
   PrepareMessage prepare;
   CommitMessage commit;
@@ -313,6 +314,10 @@ inline MessagePtr decode_message(wire::Reader r) {
   return m;
 }
 
-inline MessagePtr decode_message(const uint8_t* data, size_t len) { return decode_message(wire::Reader{data, data + len}); }
+inline MessagePtr decode_message(const uint8_t* data, size_t len) {
+  MessagePtr m = decode_message(wire::Reader{data, data + len});
+  m->raw_wire.assign((const char*)data, len);
+  return m;
+}
 
 }  // namespace ibft::host

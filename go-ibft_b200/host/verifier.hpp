@@ -60,6 +60,10 @@ class GpuVerifier : public Verifier {
   std::function<bool(const Bytes&, uint64_t, uint64_t)> isProposerFn;
   std::function<bool(const Bytes&)> isValidProposalFn;
   Bytes id;
+  // Submit PREPARE / COMMIT messages as RAW FRAMES (IBFT_KIND_WIRE*): the device derives PayloadNoSig, From and the
+  // signature from the gossip frame itself, so the host never re-marshals.  Frames the device hands back
+  // (IBFT_ITEM_NEEDS_HOST: non-canonical encoding) are re-submitted through the marshalled path.
+  bool use_wire_frames = false;
 
   explicit GpuVerifier(const ibft_engine_params& params) {
     params_ = params;
@@ -164,6 +168,7 @@ class GpuVerifier : public Verifier {
 
   uint64_t device_calls() const { return device_calls_; }
   uint64_t items_verified() const { return items_verified_; }
+  uint64_t frames_handed_back() const { return frames_handed_back_; }
 
  private:
   struct Pending {
@@ -171,6 +176,7 @@ class GpuVerifier : public Verifier {
     ibft_sig_item item;
     Bytes payload;
     uint64_t height;
+    const IbftMessage* fallback_payload_msg = nullptr;  // raw-frame items: the message to re-marshal if the device hands it back
   };
   ibft_engine_params params_{};
   ibft_engine* engine_ = nullptr;
@@ -179,7 +185,7 @@ class GpuVerifier : public Verifier {
   std::unordered_map<Bytes, Bytes> hash_cache_;
   std::map<uint32_t, uint64_t> slot_height_;
   uint64_t current_height_ = 0;
-  uint64_t device_calls_ = 0, items_verified_ = 0;
+  uint64_t device_calls_ = 0, items_verified_ = 0, frames_handed_back_ = 0;
 
   bool keccak(const Bytes& data, uint8_t out[32]) {
     uint32_t off = 0, len = (uint32_t)data.size();
@@ -199,8 +205,18 @@ class GpuVerifier : public Verifier {
   // msg.View.Height (backend.go:41-45).  Structurally invalid => false without touching the device.
   bool sender_item(const IbftMessage& m, Pending& p) {
     if (!m.view || m.from.size() != 20 || m.signature.size() != 65) return false;
-    p.payload = payload_no_sig(m);
     p.height = m.view->height;
+    if (use_wire_frames && !m.raw_wire.empty() && (m.payload_kind == PAYLOAD_PREPARE || m.payload_kind == PAYLOAD_COMMIT)) {
+      memset(&p.item, 0, sizeof p.item);
+      p.item.kind = IBFT_KIND_WIRE;
+      p.payload = m.raw_wire;
+      p.fallback_payload_msg = &m;
+      p.key.assign(1, 'W');
+      for (int j = 7; j >= 0; j--) p.key.push_back((char)(p.height >> (8 * j)));
+      p.key += m.raw_wire;
+      return true;
+    }
+    p.payload = payload_no_sig(m);
     put_sig(p.item, m.signature, m.from);
     p.item.kind = IBFT_KIND_PAYLOAD;
     p.key.assign(1, 'S');
@@ -258,7 +274,7 @@ class GpuVerifier : public Verifier {
         }
         items[i] = p.item;
         items[i].group = g->second;
-        if (p.item.kind == IBFT_KIND_PAYLOAD) {
+        if (p.item.kind == IBFT_KIND_PAYLOAD || p.item.kind == IBFT_KIND_WIRE) {
           if (arena.size() + p.payload.size() > params_.max_payload_bytes) { n = i; break; }
           items[i].payload_off = (uint32_t)arena.size();
           items[i].payload_len = (uint32_t)p.payload.size();
@@ -277,12 +293,28 @@ class GpuVerifier : public Verifier {
         error_ = ibft_last_error();  // launch failure => NO verdict is cached; callers see `false`
       } else {
         items_verified_ += n;
+        std::vector<uint8_t> status(n, 0);
+        if (use_wire_frames) ibft_last_item_status(engine_, status.data(), (uint32_t)n);
+        std::vector<Pending> redo;
         for (size_t i = 0; i < n; i++) {
           bool pass = (bitmap[i >> 5] >> (i & 31)) & 1u;
           // membership requires a resident table for the item's height
           if (groups[items[i].group].table_slot == IBFT_NO_TABLE) pass = false;
-          cache_[batch[pos + i].key] = pass;
+          Pending& p = batch[pos + i];
+          if (status[i] == IBFT_ITEM_NEEDS_HOST && p.fallback_payload_msg) {
+            // the device declined the frame (not canonical): same check through the marshalled path, same cache key
+            Pending q;
+            bool saved = use_wire_frames;
+            use_wire_frames = false;
+            bool ok = sender_item(*p.fallback_payload_msg, q);
+            use_wire_frames = saved;
+            if (ok) { q.key = p.key; redo.push_back(std::move(q)); }
+            else cache_[p.key] = false;
+            continue;
+          }
+          cache_[p.key] = pass;
         }
+        if (!redo.empty()) { frames_handed_back_ += redo.size(); verify_pending(redo); }
       }
       pos += n;
     }

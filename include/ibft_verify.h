@@ -40,8 +40,19 @@ extern "C" {
                                 IbftMessage.PayloadNoSig() (messages/proto/helper.go:13-27) */
 #define IBFT_KIND_SEAL 2     /* `digest` holds proposalHash; z = Keccak-256(proposalHash || 0x02) -- IsValidCommittedSeal
                                 (0x02 = MessageType_COMMIT, messages/proto/messages.proto:10) */
+#define IBFT_KIND_WIRE 3      /* arena slice = the COMPLETE wire encoding of a PREPARE / COMMIT IbftMessage (a raw gossip frame).  The device
+                                finds From, Signature and the signed bytes itself: for a canonically encoded frame PayloadNoSig
+                                (messages/proto/helper.go:13-27) is the frame minus its field-3 TLV.  r/s/v/signer/digest of the tuple are
+                                ignored.  Frames that are not canonical, or carry a nested payload (PREPREPARE / ROUND_CHANGE), get verdict 0
+                                and item status IBFT_ITEM_NEEDS_HOST: the host re-submits those as IBFT_KIND_PAYLOAD. */
+#define IBFT_KIND_WIRE_SEAL 4 /* same frame; checks the committed seal instead: commitData.committedSeal over
+                                Keccak-256(commitData.proposalHash || 0x02), signer = From (IsValidCommittedSeal on the frame) */
 #define IBFT_KIND_INVALID 255 /* structurally invalid on the host side (nil seal, signature length != 65, ...):
                                  verdict is always 0.  Mirrors "malformed input => false" (messages/helpers.go:38-42). */
+
+/* per-item status of the last host-buffer verify call (ibft_last_item_status) */
+#define IBFT_ITEM_OK 0          /* the verdict bit is the answer */
+#define IBFT_ITEM_NEEDS_HOST 1  /* IBFT_KIND_WIRE*: frame not canonical / not a flat PREPARE or COMMIT; verdict bit is 0, re-submit as KIND_PAYLOAD */
 
 #define IBFT_NO_TABLE 0xFFFFu /* ibft_group_desc.table_slot: skip the validator-set membership test */
 
@@ -135,6 +146,9 @@ int ibft_get_quorum(ibft_engine* e, uint32_t table_slot, uint64_t quorum_out[5],
 int ibft_verify_batch(ibft_engine* e, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
                       const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
                       ibft_group_result* results_out, uint8_t* recovered_out);
+
+/* Per-item status (IBFT_ITEM_*) of the most recent completed ibft_verify_batch / ibft_verify_wait on this engine. */
+int ibft_last_item_status(ibft_engine* e, uint8_t* status_out, uint32_t n);
 
 /* Asynchronous variant: same arguments; inputs are copied into engine-owned pinned staging before the call
  * returns (cgo rule: no Go pointer is retained).  ibft_verify_poll returns IBFT_OK with *done = 0/1;

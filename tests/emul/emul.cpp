@@ -15,15 +15,19 @@ using namespace ibft;
 extern "C" {
 
 int emul_verify_item(const ibft_sig_item* it, const uint8_t* arena, size_t arena_len, uint8_t* recovered20) {
-  uint8_t z[32], addr[20];
+  uint8_t addr[20];
   memset(recovered20, 0, 20);
-  if (!item_digest(*it, arena, arena_len, z)) return 0;
+  resolved_item ri;
+  bool valid = false;
+  int st = resolve_item(*it, arena, arena_len, ri, &valid);
+  if (st != IBFT_ITEM_OK) return -1;  // NEEDS_HOST
+  if (!valid) return 0;
   gtab_view G{IBFT_GTABLE};
   uint32_t rtab[IBFT_RTAB_WORDS];
   rtab_view T{rtab, 1};
-  if (!ecrecover_address(it->r, it->s, it->v, z, G, T, addr)) return 0;
+  if (!ecrecover_address(ri.r, ri.s, ri.v, ri.z, G, T, addr)) return 0;
   memcpy(recovered20, addr, 20);
-  return memcmp(addr, it->signer, 20) == 0;
+  return memcmp(addr, ri.signer, 20) == 0;
 }
 
 void emul_keccak256(const uint8_t* d, uint32_t n, uint8_t* out) { keccak256_bytes(d, n, out); }

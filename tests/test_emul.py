@@ -111,3 +111,104 @@ def test_config2_fixture_bit_exact(emul):
         ok, _ = emul_item(emul, items[i:i + 1], arena)
         ok = ok and bytes(items[i]["signer"]) in members
         assert ok == bool((bm[i >> 5] >> (i & 31)) & 1), (i, d["tags"][i])
+
+
+# ----------------------------------------------------------------------------------------------- raw gossip frames
+def wire_expectation(wire: bytes, kind: int, members):
+    """(status, verdict) the device must produce for a KIND_WIRE / KIND_WIRE_SEAL item, derived from the oracle codec
+    (canonical <=> decode+encode reproduces the frame) and the oracle verifier."""
+    import workloads as wl
+    from oracle import ibft_proto as ip
+    try:
+        m = ip.decode_ibft_message(wire)
+    except (ip.DecodeError, RecursionError):
+        return 1, False
+    if ip.encode_ibft_message(m) != wire or not (m.payload is None or isinstance(m.payload, (ip.PrepareMessage, ip.CommitMessage))):
+        return 1, False
+    if len(m.from_) != 20:
+        return 0, False
+    if kind == 3:
+        if m.view is None or len(m.signature) != 65:
+            return 0, False
+        addr = co.ecrecover_address(co.keccak256(m.payload_no_sig()), m.signature)
+    else:
+        if m.type != ip.COMMIT or not isinstance(m.payload, ip.CommitMessage) or len(m.payload.proposal_hash) != 32 or len(m.payload.committed_seal) != 65:
+            return 0, False
+        addr = co.ecrecover_address(wl.seal_digest(m.payload.proposal_hash), m.payload.committed_seal)
+    return 0, addr == m.from_ and (members is None or m.from_ in members)
+
+
+def wire_item(kind, off, ln, group=0):
+    it = np.zeros(1, dtype=co.ITEM_DTYPE)
+    it["kind"], it["payload_off"], it["payload_len"], it["group"] = kind, off, ln, group
+    return it
+
+
+def sample_frames():
+    import workloads as wl
+    from oracle import ibft_proto as ip
+    vs = wl.ValidatorSet(77, 6)
+    ph = co.keccak256(b"blk")
+    frames = []
+    for i in range(6):
+        for t, payload in ((ip.PREPARE, ip.PrepareMessage(ph)), (ip.COMMIT, ip.CommitMessage(ph, wl.sign(vs.keys[i], wl.seal_digest(ph))))):
+            for view in (ip.View(1_000_000, i), ip.View(0, 0), ip.View(5, 0)):
+                m = ip.IbftMessage(view, vs.addrs[i], b"", t, payload)
+                m.signature = wl.sign(vs.keys[i], co.keccak256(m.payload_no_sig()))
+                frames.append(ip.encode_ibft_message(m))
+    m = ip.IbftMessage(ip.View(3, 1), vs.addrs[0], b"", ip.COMMIT, ip.CommitMessage(ph, wl.sign(vs.keys[1], wl.seal_digest(ph))))  # seal by someone else
+    m.signature = wl.sign(vs.keys[0], co.keccak256(m.payload_no_sig()))
+    frames.append(ip.encode_ibft_message(m))
+    extra = [
+        ip.IbftMessage(None, vs.addrs[0], b"\x01" * 65, ip.PREPARE, ip.PrepareMessage(ph)),                      # nil view
+        ip.IbftMessage(ip.View(1, 1), vs.addrs[0], b"", ip.PREPARE, ip.PrepareMessage(ph)),                        # no signature
+        ip.IbftMessage(ip.View(1, 1), b"short", b"\x01" * 65, ip.PREPARE, ip.PrepareMessage(ph)),                  # from != 20 bytes
+        ip.IbftMessage(ip.View(1, 1), vs.addrs[0], b"\x01" * 64, ip.COMMIT, ip.CommitMessage(ph, b"\x02" * 64)),   # 64-byte sig / seal
+        ip.IbftMessage(ip.View(1, 1), vs.addrs[0], b"\x01" * 65, ip.PREPARE, ip.CommitMessage(ph, b"\x02" * 65)),  # type/payload mismatch
+        ip.IbftMessage(ip.View(1, 1), vs.addrs[0], b"\x01" * 65, ip.COMMIT, None),                                 # no payload
+        ip.IbftMessage(ip.View(1, 1), vs.addrs[0], b"\x01" * 65, ip.PREPREPARE, ip.PrePrepareMessage(ip.Proposal(b"x", 1), ph, None)),  # nested -> host
+        ip.IbftMessage(ip.View(1, 1), vs.addrs[0], b"\x01" * 65, ip.ROUND_CHANGE, ip.RoundChangeMessage(None, None)),
+        ip.IbftMessage(ip.View(1, 1), vs.addrs[0], b"\x01" * 65, ip.PREPARE, ip.PrepareMessage()),                 # empty payload message
+    ]
+    frames += [ip.encode_ibft_message(m) for m in extra]
+    # hand-made non-canonical encodings of a valid frame
+    good = frames[0]
+    frames += [good + b"\x48\x01",                      # unknown field 9
+               good[:2] + b"\x80\x00"[:0] + good[2:],   # (identity) control
+               b"\x12\x00" + good,                      # empty `from` ahead, fields out of order
+               good.replace(b"\x20\x01", b"\x20\x81\x00", 1),  # non-minimal varint for `type`
+               good[::-1], b"", b"\x0a"]
+    return vs, frames
+
+
+def test_raw_frame_kinds_canonical_and_mutated(emul):
+    vs, frames = sample_frames()
+    members = set(vs.addrs)
+    rnd = random.Random(8)
+    mutated = []
+    for f in frames[:24]:
+        for _ in range(12):
+            b = bytearray(f)
+            op = rnd.randrange(4)
+            if op == 0 and b:
+                b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+            elif op == 1 and b:
+                del b[rnd.randrange(len(b))]
+            elif op == 2:
+                b.insert(rnd.randrange(len(b) + 1), rnd.randrange(256))
+            else:
+                i = rnd.randrange(len(b) + 1)
+                b[i:i] = bytes([rnd.choice([0x0a, 0x12, 0x1a, 0x20, 0x32, 0x3a, 0x00, 0x80])])
+            mutated.append(bytes(b))
+    n_needs_host = n_true = 0
+    for wire in frames + mutated:
+        for kind in (3, 4):
+            want_status, want_ok = wire_expectation(wire, kind, None)
+            out = (ctypes.c_uint8 * 20)()
+            arena = np.frombuffer(wire, np.uint8) if wire else np.zeros(1, np.uint8)
+            rc = emul.emul_verify_item(wire_item(kind, 0, len(wire)).ctypes.data_as(ctypes.c_void_p), arena.ctypes.data_as(ctypes.c_void_p),
+                                       ctypes.c_size_t(len(wire)), out)
+            assert (1 if rc == -1 else 0, rc == 1) == (want_status, want_ok), (wire.hex(), kind, rc)
+            n_needs_host += want_status
+            n_true += want_ok
+    assert n_true >= 40 and n_needs_host >= 40

@@ -199,3 +199,30 @@ def test_quorum_from_gpu_voted_bitmap(engine):
         assert c.has_quorum_voted(voted) == bool(results[seal_group]["has_quorum"])
         valid_senders = [bytes(sub[i]["signer"]) for i in range(take) if (int(d["bitmap"][(2000 + i) >> 5]) >> ((2000 + i) & 31)) & 1]
         assert c.has_quorum_senders(valid_senders) == bool(results[seal_group]["has_quorum"])
+
+
+def test_raw_frame_mode_same_decisions_and_fallback():
+    """GpuVerifier with use_wire_frames: PREPARE/COMMIT sender signatures go to the device as raw gossip frames (no host-side
+    PayloadNoSig marshal); a non-canonically encoded frame is handed back and takes the marshalled path -- same verdicts."""
+    n, height = 20, 4242
+    vs, raw, ph, pp, prepares, commits = make_round(n, height, 0, seed=29)
+    proposer_of = lambda a, h, r: a == vs.addrs[0]  # noqa: E731
+    o = L.IBFT(oracle_backend({height: set(vs.addrs)}, height, proposer_of), L.ValidatorManager(lambda h: dict(zip(vs.addrs, vs.powers))))
+    o.vm.init(height)
+    o.state.view = ip.View(height, 0)
+    c = gpu_ctx(proposer_of)
+    c.set_wire_frames(True)
+    assert c.set_validators(height, vs.addrs, vs.powers) == 0
+    c.set_state(height, 0, L.NEW_ROUND, None)
+    frames = [enc(m) for m in prepares + commits]
+    frames[3] = frames[3] + b"\x48\x01"                        # unknown field 9 appended: decodes fine, not canonical
+    frames[5] = frames[5][:-1] + bytes([frames[5][-1] ^ 1])    # corrupted payload byte: canonical frame, bad signature
+    inbound = [ip.decode_ibft_message(f) for f in frames]
+    for m in inbound:
+        o.add_message(m)
+    c.add_messages(frames)
+    assert c.gpu_frames_handed_back() == 1
+    for t in (ip.PREPARE, ip.COMMIT):
+        assert c.store_senders(height, 0, t) == sorted(m.from_ for m in o.messages.maps[t].get(height, {}).get(0, {}).values())
+    assert c.num_messages(height, 0, ip.PREPARE) == len(prepares) - 1
+    c.close()

@@ -142,10 +142,11 @@ def test_malformed_items_are_false_never_crash(engine):
     assert int(bitmap[0]) == 0b1000001
     assert int(results[0]["n_valid"]) == 2 and int(results[0]["n_distinct"]) == 1
     # a group that references an unset table slot is an error, not a verdict
-    g = groups_for(1, slot=15)
+    e2 = ib.Engine(device=0, max_items=64, max_payload_bytes=1024, max_groups=4, max_table_slots=4, max_validators=16)
     with pytest.raises(ib.EngineError) as ei:
-        engine.verify_batch(its, b"", g)
+        e2.verify_batch(its, b"", groups_for(1, slot=3))
     assert ei.value.code == 6
+    e2.close()
     # no table: membership skipped, pure recover+compare
     g = groups_for(1, slot=ib.NO_TABLE)
     outsider = wl.privkey(999, 0)
