@@ -46,24 +46,32 @@ IBFT_HD fe fe_beta() {
 #define PSQR fe_sqr
 #endif
 
+#if defined(IBFT_DBL_INLINE)
+#define DMUL fe_mul_i
+#define DSQR fe_sqr_i
+#else
+#define DMUL PMUL
+#define DSQR PSQR
+#endif
+
 // dbl-2009-l: 2M + 5S
 IBFT_PT jac jac_double(const jac& p) {
   jac r;
   // Y = 0 never happens on secp256k1 (no points of order 2), so no exceptional case besides infinity.
-  fe a = PSQR(p.x);
-  fe b = PSQR(p.y);
-  fe c = PSQR(b);
+  fe a = DSQR(p.x);
+  fe b = DSQR(p.y);
+  fe c = DSQR(b);
   fe t = fe_add(p.x, b);
-  t = PSQR(t);
+  t = DSQR(t);
   t = fe_sub(t, a);
   t = fe_sub(t, c);
   fe d = fe_dbl(t);
   fe e = fe_add(fe_dbl(a), a);
-  fe f = PSQR(e);
+  fe f = DSQR(e);
   r.x = fe_sub(f, fe_dbl(d));
   fe c8 = fe_dbl(fe_dbl(fe_dbl(c)));
-  r.y = fe_sub(PMUL(e, fe_sub(d, r.x)), c8);
-  r.z = fe_dbl(PMUL(p.y, p.z));
+  r.y = fe_sub(DMUL(e, fe_sub(d, r.x)), c8);
+  r.z = fe_dbl(DMUL(p.y, p.z));
   r.inf = p.inf;
   return r;
 }

@@ -13,6 +13,7 @@
 //                   ever invented) and last_error() says why.
 #pragma once
 #include <functional>
+#include <mutex>
 #include <unordered_map>
 
 #include "../../include/ibft_verify.h"
@@ -85,6 +86,7 @@ class GpuVerifier : public Verifier {
   // left out of the device table.
   bool SetValidators(uint64_t height, const std::vector<Bytes>& addrs, const std::vector<u320>& powers) {
     if (!engine_) return false;
+    std::lock_guard<std::recursive_mutex> lk(mu_);
     std::vector<uint8_t> a, p;
     for (size_t i = 0; i < addrs.size(); i++) {
       if (addrs[i].size() != 20) continue;
@@ -104,18 +106,26 @@ class GpuVerifier : public Verifier {
     return true;
   }
   // committed seals carry no height: they are checked against the validators of the running sequence
-  void SetCurrentHeight(uint64_t h) { current_height_ = h; }
+  void SetCurrentHeight(uint64_t h) {
+    std::lock_guard<std::recursive_mutex> lk(mu_);
+    current_height_ = h;
+  }
 
   bool IsValidProposal(const Bytes& raw) override { return isValidProposalFn ? isValidProposalFn(raw) : true; }
   bool IsProposer(const Bytes& i, uint64_t h, uint64_t r) override { return isProposerFn ? isProposerFn(i, h, r) : false; }
   Bytes ID() override { return id; }
 
+  // The reference calls the verifier concurrently (gossip goroutines through AddMessage, the round goroutine and two
+  // watchers: core/ibft.go:335-347, :1128) while the store holds its per-type mutex: every entry point below is serialised
+  // on one lock and never calls back into the store.
   bool IsValidValidator(const IbftMessage& m) override {
+    std::lock_guard<std::recursive_mutex> lk(mu_);
     Pending p;
     if (!sender_item(m, p)) return false;
     return lookup_or_verify(p);
   }
   bool IsValidCommittedSeal(const Bytes* proposal_hash, const CommittedSeal* seal) override {
+    std::lock_guard<std::recursive_mutex> lk(mu_);
     Pending p;
     if (!seal_item(proposal_hash, seal, p)) return false;
     return lookup_or_verify(p);
@@ -124,6 +134,7 @@ class GpuVerifier : public Verifier {
   // embedders hash an RLP header (out of scope).  Hashing runs on the device (ibft_keccak256_batch), once per proposal.
   bool IsValidProposalHash(const Proposal* proposal, const Bytes* hash) override {
     if (!engine_ || !proposal || !hash || hash->size() != 32) return false;
+    std::lock_guard<std::recursive_mutex> lk(mu_);
     Bytes key = proposal->raw_proposal;
     for (int j = 7; j >= 0; j--) key.push_back((char)(proposal->round >> (8 * j)));
     auto it = hash_cache_.find(key);
@@ -139,6 +150,7 @@ class GpuVerifier : public Verifier {
   }
 
   void Prefetch(const std::vector<MessagePtr>& msgs, bool with_seals) override {
+    std::lock_guard<std::recursive_mutex> lk(mu_);
     std::vector<Pending> batch;
     std::unordered_map<Bytes, size_t> seen;
     std::function<void(const IbftMessage&)> visit = [&](const IbftMessage& m) {
@@ -178,6 +190,7 @@ class GpuVerifier : public Verifier {
     uint64_t height;
     const IbftMessage* fallback_payload_msg = nullptr;  // raw-frame items: the message to re-marshal if the device hands it back
   };
+  std::recursive_mutex mu_;
   ibft_engine_params params_{};
   ibft_engine* engine_ = nullptr;
   std::string error_;
