@@ -176,9 +176,9 @@ __global__ void k_quorum_mark(const ibft_sig_item* __restrict__ items, uint32_t 
                               const uint32_t* __restrict__ bitmap,
                               const ibft_group_desc* __restrict__ groups, const group_dev* __restrict__ gdev,
                               uint32_t n_groups, const slot_dev* __restrict__ slots, uint32_t n_slots,
-                              uint32_t* __restrict__ voted, uint32_t* __restrict__ n_valid) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                              uint32_t* __restrict__ voted, uint32_t* __restrict__ n_valid, uint32_t lo, uint32_t hi) {
+  uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi || i >= n) return;
   if (!((bitmap[i >> 5] >> (i & 31)) & 1u)) return;
   const ibft_sig_item* it = items + i;
   uint32_t g = it->group;
@@ -191,6 +191,20 @@ __global__ void k_quorum_mark(const ibft_sig_item* __restrict__ items, uint32_t 
   if (!item_signer(local, arena, arena_len, addr)) return;
   int v = lookup_validator(slots[slot], addr);
   if (v >= 0) atomicOr(&voted[gdev[g].voted_off + ((uint32_t)v >> 5)], 1u << (v & 31));
+}
+
+// multi-GPU: OR the ranks' partial voted sets and add their valid counts (partial layout: voted words, then one count per group)
+__global__ void k_quorum_merge(const uint32_t* __restrict__ parts, uint32_t n_parts, uint32_t part_stride, uint32_t voted_words,
+                               uint32_t n_groups, uint32_t* __restrict__ voted, uint32_t* __restrict__ n_valid) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= voted_words + n_groups) return;
+  uint32_t acc = 0;
+  for (uint32_t r = 0; r < n_parts; r++) {
+    uint32_t v = parts[(size_t)r * part_stride + i];
+    acc = i < voted_words ? (acc | v) : (acc + v);
+  }
+  if (i < voted_words) voted[i] = acc;
+  else n_valid[i - voted_words] = acc;
 }
 
 // one CTA per group: 320-bit sum of the voting power of the voted validators, compared with the threshold
@@ -771,7 +785,7 @@ static int launch_quorum(ibft_engine* e, const ibft_sig_item* d_items, uint32_t 
   CU(cudaMemsetAsync(e->d_nvalid, 0, (size_t)n_groups * 4, st));
   if (n) {
     k_quorum_mark<<<(n + 255) / 256, 256, 0, st>>>(d_items, n, d_arena, arena_len, d_bitmap, d_groups, d_gdev, n_groups, e->d_slots,
-                                                    e->p.max_table_slots, e->d_voted, e->d_nvalid);
+                                                    e->p.max_table_slots, e->d_voted, e->d_nvalid, 0u, n);
     e->launches++;
     CU(cudaGetLastError());
   }
@@ -979,6 +993,61 @@ extern "C" int ibft_quorum_reduce_device(ibft_engine* e, const void* d_items, ui
   for (auto& g : e->last_gdev) voted_words += g.n_words;
   return launch_quorum(e, (const ibft_sig_item*)d_items, n, e->dev_arena, e->dev_arena_len, (const uint32_t*)d_bitmap, e->d_groups,
                        e->d_gdev, n_groups, voted_words, (ibft_group_result*)d_results, st);
+}
+
+extern "C" int ibft_quorum_partial_words(ibft_engine* e, uint32_t* words_out) {
+  if (!e || !words_out) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  size_t voted_words = 0;
+  for (auto& g : e->last_gdev) voted_words += g.n_words;
+  *words_out = (uint32_t)(voted_words + e->last_groups.size());
+  return IBFT_OK;
+}
+
+extern "C" int ibft_quorum_mark_device(ibft_engine* e, const void* d_items, uint32_t n, uint32_t shard_lo, uint32_t shard_hi,
+                                       const void* d_bitmap, void* d_partial, void* stream) {
+  if (!e || !d_partial || (n && (!d_items || !d_bitmap))) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  if (shard_hi > n || shard_lo > shard_hi) { set_err("bad shard"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  uint32_t n_groups = (uint32_t)e->last_groups.size();
+  if (n_groups == 0) { set_err("call ibft_bind_groups first"); return IBFT_ERR_INVALID_ARG; }
+  CU(cudaSetDevice(e->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  size_t voted_words = 0;
+  for (auto& g : e->last_gdev) voted_words += g.n_words;
+  uint32_t* part = (uint32_t*)d_partial;
+  CU(cudaMemsetAsync(part, 0, (voted_words + n_groups) * 4, st));
+  if (shard_hi > shard_lo) {
+    k_quorum_mark<<<(shard_hi - shard_lo + 255) / 256, 256, 0, st>>>((const ibft_sig_item*)d_items, n, e->dev_arena, e->dev_arena_len,
+                                                                     (const uint32_t*)d_bitmap, e->d_groups, e->d_gdev, n_groups, e->d_slots,
+                                                                     e->p.max_table_slots, part, part + voted_words, shard_lo, shard_hi);
+    e->launches++;
+    CU(cudaGetLastError());
+  }
+  return IBFT_OK;
+}
+
+extern "C" int ibft_quorum_merge_device(ibft_engine* e, const void* d_partials, uint32_t n_parts, uint32_t part_stride_words,
+                                        void* d_results, void* stream) {
+  if (!e || !d_partials || !d_results || n_parts == 0) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  uint32_t n_groups = (uint32_t)e->last_groups.size();
+  if (n_groups == 0) { set_err("call ibft_bind_groups first"); return IBFT_ERR_INVALID_ARG; }
+  CU(cudaSetDevice(e->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  size_t voted_words = 0;
+  for (auto& g : e->last_gdev) voted_words += g.n_words;
+  if (part_stride_words < voted_words + n_groups) { set_err("partial stride too small"); return IBFT_ERR_INVALID_ARG; }
+  uint32_t total = (uint32_t)(voted_words + n_groups);
+  k_quorum_merge<<<(total + 255) / 256, 256, 0, st>>>((const uint32_t*)d_partials, n_parts, part_stride_words, (uint32_t)voted_words,
+                                                      n_groups, e->d_voted, e->d_nvalid);
+  e->launches++;
+  CU(cudaGetLastError());
+  k_quorum_reduce<<<n_groups, 256, 0, st>>>(e->d_groups, e->d_gdev, n_groups, e->d_slots, e->p.max_table_slots, e->d_voted, e->d_nvalid,
+                                            (ibft_group_result*)d_results);
+  e->launches++;
+  CU(cudaGetLastError());
+  return IBFT_OK;
 }
 
 extern "C" int ibft_get_voted_bitmap(ibft_engine* e, uint32_t group, uint32_t* words_out, uint32_t n_words) {

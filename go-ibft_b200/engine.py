@@ -31,7 +31,7 @@ assert ITEM_DTYPE.itemsize == 128 and GROUP_DTYPE.itemsize == 8 and RESULT_DTYPE
 EXPORTS = [
     "ibft_abi_version", "ibft_last_error", "ibft_engine_create", "ibft_engine_destroy", "ibft_engine_device_info",
     "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_last_item_status", "ibft_verify_submit", "ibft_verify_poll",
-    "ibft_verify_wait", "ibft_bind_groups", "ibft_verify_batch_device", "ibft_quorum_reduce_device",
+    "ibft_verify_wait", "ibft_bind_groups", "ibft_verify_batch_device", "ibft_quorum_reduce_device", "ibft_quorum_partial_words", "ibft_quorum_mark_device", "ibft_quorum_merge_device",
     "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_probe_int_peak", "ibft_debug_op",
 ]
 
@@ -80,6 +80,9 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.ibft_bind_groups.argtypes = [c_void_p, c_void_p, c_uint32]
     lib.ibft_verify_batch_device.argtypes = [c_void_p, c_void_p, c_uint32, c_void_p, c_size_t, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
     lib.ibft_quorum_reduce_device.argtypes = [c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p]
+    lib.ibft_quorum_partial_words.argtypes = [c_void_p, POINTER(c_uint32)]
+    lib.ibft_quorum_mark_device.argtypes = [c_void_p, c_void_p, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
+    lib.ibft_quorum_merge_device.argtypes = [c_void_p, c_void_p, c_uint32, c_uint32, c_void_p, c_void_p]
     lib.ibft_get_voted_bitmap.argtypes = [c_void_p, c_uint32, c_void_p, c_uint32]
     lib.ibft_keccak256_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_uint32, c_void_p]
     lib.ibft_sign_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]
@@ -205,6 +208,17 @@ class Engine:
 
     def quorum_reduce_device(self, d_items: int, n: int, d_bitmap: int, n_groups: int, d_results: int, stream: int = 0):
         self._check(self.lib.ibft_quorum_reduce_device(self.handle, d_items, n, d_bitmap, None, n_groups, d_results, stream or None))
+
+    def quorum_partial_words(self) -> int:
+        w = c_uint32()
+        self._check(self.lib.ibft_quorum_partial_words(self.handle, ctypes.byref(w)))
+        return int(w.value)
+
+    def quorum_mark_device(self, d_items: int, n: int, lo: int, hi: int, d_bitmap: int, d_partial: int, stream: int = 0):
+        self._check(self.lib.ibft_quorum_mark_device(self.handle, d_items, n, lo, hi, d_bitmap, d_partial, stream or None))
+
+    def quorum_merge_device(self, d_partials: int, n_parts: int, stride_words: int, d_results: int, stream: int = 0):
+        self._check(self.lib.ibft_quorum_merge_device(self.handle, d_partials, n_parts, stride_words, d_results, stream or None))
 
     def voted_bitmap(self, group: int, n_validators: int) -> np.ndarray:
         words = np.zeros((n_validators + 31) // 32, dtype=np.uint32)

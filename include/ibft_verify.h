@@ -175,6 +175,18 @@ int ibft_verify_batch_device(ibft_engine* e, const void* d_items, uint32_t n, co
 int ibft_quorum_reduce_device(ibft_engine* e, const void* d_items, uint32_t n, const void* d_bitmap,
                               const void* d_groups, uint32_t n_groups, void* d_results, void* stream);
 
+/* Multi-GPU form of the reduction (each rank resolves only ITS shard, so no work is repeated across ranks):
+ *   ibft_quorum_partial_words  -> W = words of one rank's partial result (voted sets of all bound groups, then one valid
+ *                                 count per group); depends only on the bound groups, identical on every rank
+ *   ibft_quorum_mark_device    -> marks items [shard_lo, shard_hi) with a set bitmap bit into d_partial (W words, device)
+ *   (all-gather the partials -- they can ride in the same collective as the bitmap words)
+ *   ibft_quorum_merge_device   -> ORs / sums n_parts partials (part_stride_words apart) and reduces against the thresholds */
+int ibft_quorum_partial_words(ibft_engine* e, uint32_t* words_out);
+int ibft_quorum_mark_device(ibft_engine* e, const void* d_items, uint32_t n, uint32_t shard_lo, uint32_t shard_hi,
+                            const void* d_bitmap, void* d_partial, void* stream);
+int ibft_quorum_merge_device(ibft_engine* e, const void* d_partials, uint32_t n_parts, uint32_t part_stride_words,
+                             void* d_results, void* stream);
+
 /* Per-group voted set of the most recent reduce: bit i = validator i of the group's table has >= 1 valid item.
  * words_out: caller-allocated, (table_n+31)/32 words.  This is the bitmap core/validator_manager.go's quorum
  * check reads in the Go shim. */

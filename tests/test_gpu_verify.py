@@ -249,3 +249,33 @@ def test_replicated_large_batch_properties(engine):
     exp, _ = expected_groups(items, d["bitmap"], d["addrs"], d["powers"])
     for g in range(len(groups)):
         assert int(results[g]["n_distinct"]) == exp[g][1] and int(results[g]["n_valid"]) == reps * exp[g][0]
+
+
+def test_shard_local_quorum_mark_and_merge(engine):
+    """Multi-GPU form of the quorum reduction on one device: two 'ranks' mark only their own shard into partial buffers, the
+    partials are merged (OR / sum) and reduced -- identical to the single-pass reduction over the whole bitmap."""
+    import torch
+    d, items = load_fixture("config3.npz")
+    engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+    n = len(items)
+    groups = groups_for(len(d["groups"]))
+    engine.bind_groups(groups)
+    t_items = torch.from_numpy(items.view(np.uint8).reshape(-1, 128).copy()).cuda()
+    t_arena = torch.from_numpy(np.ascontiguousarray(d["arena"]).copy()).cuda()
+    t_bm = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    engine.verify_device(t_items.data_ptr(), n, t_arena.data_ptr(), t_arena.numel(), 0, n, t_bm.data_ptr(), 0, st)
+    W = engine.quorum_partial_words()
+    assert W == len(groups) * ((len(d["addrs"]) + 31) // 32) + len(groups)
+    parts = torch.full((3, W + 5), -1, dtype=torch.int32, device="cuda")     # stride larger than W, garbage-filled
+    bounds = [(0, 6400), (6400, 13312), (13312, n)]
+    for r, (lo, hi) in enumerate(bounds):
+        engine.quorum_mark_device(t_items.data_ptr(), n, lo, hi, t_bm.data_ptr(), parts[r].data_ptr(), st)
+    res_a = torch.zeros(len(groups) * ib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    res_b = torch.zeros_like(res_a)
+    engine.quorum_merge_device(parts.data_ptr(), 3, W + 5, res_a.data_ptr(), st)
+    engine.quorum_reduce_device(t_items.data_ptr(), n, t_bm.data_ptr(), len(groups), res_b.data_ptr(), st)
+    torch.cuda.synchronize()
+    a, b = res_a.cpu().numpy().view(ib.RESULT_DTYPE), res_b.cpu().numpy().view(ib.RESULT_DTYPE)
+    assert a.tobytes() == b.tobytes() and int(a[0]["n_valid"]) > 9000
+    engine.bind_groups(None)
