@@ -301,7 +301,7 @@ def main():
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = n_global * e2e_steps / float(e2e_dt[0])
     h2d = host_local.nbytes + arena_host.nbytes + groups.nbytes
-    d2h = (n_local // 8) + len(groups) * ib.RESULT_DTYPE.itemsize
+    d2h = (n_local // 8) + n_local + len(groups) * ib.RESULT_DTYPE.itemsize  # bitmap + per-item status bytes + quorum results
 
     if rank != 0:
         if world > 1:
