@@ -89,6 +89,25 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None, "samples": len(self.samples)}
 
 
+def effective_cpus() -> int:
+    """Host threads this process can actually run in parallel: the cgroup CPU quota (the GPU boxes expose 128 logical CPUs but
+    cap the container at 16 CPUs' worth of time -- oversubscribing the quota makes the CPU baseline SLOWER), else affinity."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:
+            pass
+    return n
+
+
 def cpu_baseline(d, items, n_threads: int, target_seconds: float = 12.0):
     """Times the C oracle (oracle/liboracle.so, kind "port") on a bounded sample of the same workload."""
     from oracle import coracle as co
@@ -116,7 +135,7 @@ def run_reference(args):
         return
     d = load_workload()
     items = np.ascontiguousarray(d["items"]).view(_item_dtype()).reshape(-1)
-    cores = os.cpu_count() or 1
+    cores = effective_cpus()
     from oracle import coracle as co
     arena = d["arena"].tobytes()
     gt = [0] * len(d["groups"])
@@ -382,14 +401,14 @@ def main():
                               "device_only_p50": lat_dev[len(lat_dev) // 2], "device_only_p95": lat_dev[int(len(lat_dev) * 0.95)]},
     }
     if not args.no_cpu_baseline and n_gpus == 1:
-        cores = os.cpu_count() or 1
+        cores = effective_cpus()
         v, n_s, bm = cpu_baseline(d, base_items, cores)
         v1, n1, _ = cpu_baseline(d, base_items, 1, target_seconds=3.0)
         gold_bits = np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(base_items)]
         ok = np.array_equal(np.unpackbits(bm.view(np.uint8), bitorder="little")[:n_s], np.tile(gold_bits, n_s // len(base_items) + 1)[:n_s])
         line["cpu_baseline"] = {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_s} items (the config-3 batch repeated), C oracle (oracle/c/ibft_oracle.c), {cores} threads, ~12 s",
-                                "single_thread": v1, "matches_golden": bool(ok)}
+                                "single_thread": v1, "matches_golden": bool(ok), "logical_cpus_visible": os.cpu_count()}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
