@@ -279,3 +279,24 @@ def test_shard_local_quorum_mark_and_merge(engine):
     a, b = res_a.cpu().numpy().view(ib.RESULT_DTYPE), res_b.cpu().numpy().view(ib.RESULT_DTYPE)
     assert a.tobytes() == b.tobytes() and int(a[0]["n_valid"]) > 9000
     engine.bind_groups(None)
+
+
+def test_no_groups_and_capacity_errors(engine):
+    """groups=NULL: pure recover + signer compare (no membership, no quorum); over-capacity batches are refused, not truncated."""
+    d, items = load_fixture("config2.npz")
+    sub = items[:200].copy()
+    bitmap, results, _ = engine.verify_batch(sub, d["arena"], None)
+    assert results is None
+    want = co.verify_batch(sub, d["arena"].tobytes())          # oracle without tables
+    assert np.array_equal(bitmap, want)
+    small = ib.Engine(device=0, max_items=64, max_payload_bytes=256, max_groups=2, max_table_slots=2, max_validators=8)
+    with pytest.raises(ib.EngineError) as ei:
+        small.verify_batch(items[:100], b"", None)
+    assert ei.value.code == 4                                  # IBFT_ERR_CAPACITY
+    with pytest.raises(ib.EngineError) as ei:
+        small.verify_batch(items[:10], bytes(1000), None)
+    assert ei.value.code == 4
+    with pytest.raises(ib.EngineError) as ei:
+        small.set_validators(0, 1, np.zeros((9, 20), np.uint8), None)
+    assert ei.value.code == 4
+    small.close()
