@@ -49,6 +49,9 @@ def load_host() -> ctypes.CDLL:
         lib.ibfthost_set_validators.argtypes = [c_void_p, c_uint64, c_char_p, POINTER(c_uint32), c_char_p, c_uint32]
         lib.ibfthost_set_batching.argtypes = [c_void_p, c_int]
         lib.ibfthost_set_batching.restype = None
+        lib.ibfthost_verify_committed_seals.argtypes = [c_void_p, c_char_p, c_size_t, c_char_p, c_char_p, c_uint32, POINTER(c_uint32)]
+        lib.ibfthost_set_incremental_quorum.argtypes = [c_void_p, c_int]
+        lib.ibfthost_set_incremental_quorum.restype = None
         lib.ibfthost_set_wire_frames.argtypes = [c_void_p, c_int]
         lib.ibfthost_set_wire_frames.restype = None
         lib.ibfthost_gpu_frames_handed_back.argtypes = [c_void_p]
@@ -152,6 +155,9 @@ class HostContext:
     def set_batching(self, on: bool):
         self.lib.ibfthost_set_batching(self.ctx, int(on))
 
+    def set_incremental_quorum(self, on: bool):
+        self.lib.ibfthost_set_incremental_quorum(self.ctx, int(on))
+
     def set_wire_frames(self, on: bool):
         self.lib.ibfthost_set_wire_frames(self.ctx, int(on))
 
@@ -241,6 +247,13 @@ class HostContext:
     def is_valid_proposal_hash(self, raw: bytes | None, rnd: int, phash: bytes | None) -> bool:
         return bool(self.lib.ibfthost_is_valid_proposal_hash(self.ctx, raw or b"", len(raw) if raw else 0, rnd, int(raw is not None),
                                                              phash, len(phash) if phash else 0))
+
+    def verify_committed_seals(self, phash: bytes, seals: list[tuple[bytes, bytes]]):
+        """InsertProposal-side check: (has_quorum, n_valid) for (signer, signature) pairs over one proposal hash."""
+        nv = c_uint32()
+        rc = self.lib.ibfthost_verify_committed_seals(self.ctx, phash, len(phash), b"".join(s for s, _ in seals),
+                                                      b"".join(g for _, g in seals), len(seals), ctypes.byref(nv))
+        return bool(rc == 1), int(nv.value)
 
     def gpu_device_calls(self) -> int:
         return int(self.lib.ibfthost_gpu_device_calls(self.ctx))

@@ -111,6 +111,7 @@ int ibfthost_set_validators(ibfthost_ctx* c, uint64_t height, const uint8_t* add
 }
 
 void ibfthost_set_batching(ibfthost_ctx* c, int on) { c->ibft->batching = on != 0; }
+void ibfthost_set_incremental_quorum(ibfthost_ctx* c, int on) { c->ibft->incremental_quorum = on != 0; }
 // GPU verifier: submit PREPARE / COMMIT messages as raw frames (IBFT_KIND_WIRE)
 void ibfthost_set_wire_frames(ibfthost_ctx* c, int on) { if (c->gpu) c->gpu->use_wire_frames = on != 0; }
 uint64_t ibfthost_gpu_frames_handed_back(ibfthost_ctx* c) { return c->gpu ? c->gpu->frames_handed_back() : 0; }
@@ -235,6 +236,22 @@ size_t ibfthost_reencode(const uint8_t* wire, size_t len, int with_signature, ui
   Bytes e = encode_message(*m, with_signature != 0);
   if (out && cap >= e.size()) memcpy(out, e.data(), e.size());
   return e.size();
+}
+
+// InsertProposal-side check (core/backend.go:78-81): n seals = n signers (20 bytes each) + n signatures (65 bytes each) over one
+// proposal hash; returns 1 when the valid seals' distinct signers carry quorum, and the number of valid seals in *n_valid.
+int ibfthost_verify_committed_seals(ibfthost_ctx* c, const uint8_t* hash, size_t hlen, const uint8_t* signers, const uint8_t* sigs,
+                                    uint32_t n, uint32_t* n_valid) {
+  if (!c->gpu) return -1;
+  std::vector<CommittedSeal> seals;
+  for (uint32_t i = 0; i < n; i++) seals.push_back(CommittedSeal{B(signers + 20 * (size_t)i, 20), B(sigs + 65 * (size_t)i, 65)});
+  auto valid = c->gpu->VerifyCommittedSeals(B(hash, hlen), seals);
+  std::set<Bytes> who;
+  uint32_t cnt = 0;
+  for (uint32_t i = 0; i < n; i++)
+    if (valid[i]) { cnt++; who.insert(seals[i].signer); }
+  if (n_valid) *n_valid = cnt;
+  return (int)c->vm.HasQuorum(who);
 }
 
 uint64_t ibfthost_gpu_device_calls(ibfthost_ctx* c) { return c->gpu ? c->gpu->device_calls() : 0; }

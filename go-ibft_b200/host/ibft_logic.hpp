@@ -40,10 +40,11 @@ class IBFT {
   Messages& messages;
   State state;
   bool batching = true;
+  bool incremental_quorum = false;  // O(log N) quorum probe in AddMessage instead of the reference's O(N) recomputation
   uint64_t commits_sent = 0;
   std::vector<std::string> log_errors;
 
-  IBFT(Verifier& b, ValidatorManager& vm, Messages& ms) : backend(b), validatorManager(vm), messages(ms) {}
+  IBFT(Verifier& b, ValidatorManager& vm, Messages& ms) : backend(b), validatorManager(vm), messages(ms) { messages.SetPowerSource(&vm); }
 
   // core/ibft.go:1273-1284
   bool hasQuorumByMsgType(const std::vector<MessagePtr>& msgs, uint32_t type) {
@@ -219,11 +220,47 @@ class IBFT {
     if (isAcceptableMessage(*message)) {
       messages.AddMessage(message);
       if (message->view->height == state.view.height) {
-        auto msgs = messages.GetValidMessages(*message->view, message->type, [](const MessagePtr&) { return true; });
-        if (hasQuorumByMsgType(msgs, message->type)) messages.SignalEvent(message->type, *message->view);
+        bool quorum;
+        if (!(incremental_quorum && quorumFromAccumulators(*message->view, message->type, &quorum))) {
+          auto msgs = messages.GetValidMessages(*message->view, message->type, [](const MessagePtr&) { return true; });
+          quorum = hasQuorumByMsgType(msgs, message->type);
+        }
+        if (quorum) messages.SignalEvent(message->type, *message->view);
       }
     }
   }
+  // hasQuorumByMsgType (core/ibft.go:1273-1284) evaluated from the store's incremental accumulators: same decision as
+  // building the address set and summing (validator_manager.go:77-127), without touching the N stored messages.
+  bool quorumFromAccumulators(const View& view, uint32_t type, bool* quorum) {
+    u320 power;
+    size_t count = 0;
+    bool proposer_among_senders = false;
+    const Bytes* proposer = (type == PREPARE && state.proposal_message) ? &state.proposal_message->from : nullptr;
+    if (!messages.ViewPower(view, type, &power, &count, proposer, &proposer_among_senders)) return false;
+    switch (type) {
+      case PREPREPARE: *quorum = count >= 1; return true;
+      case PREPARE: {
+        if (!state.proposal_message) {  // validator_manager.go:101-109
+          if (state.name == PREPARE_STATE) log_errors.push_back("HasPrepareQuorum - proposalMessage is not set");
+          *quorum = false;
+          return true;
+        }
+        if (proposer_among_senders) {  // :116-121
+          log_errors.push_back("HasPrepareQuorum - proposer is among signers but it is not expected to be");
+          *quorum = false;
+          return true;
+        }
+        u320 p;
+        if (validatorManager.Lookup(*proposer, p)) power.add(p);
+        *quorum = validatorManager.PowerReachesQuorum(power);
+        return true;
+      }
+      case ROUND_CHANGE:
+      case COMMIT: *quorum = validatorManager.PowerReachesQuorum(power); return true;
+      default: *quorum = false; return true;
+    }
+  }
+
   // Bulk ingress: verify every inbound sender signature in one launch, then run the reference's
   // per-message AddMessage logic against the cache.
   void AddMessages(const std::vector<MessagePtr>& batch) {

@@ -33,6 +33,14 @@ struct u320 {
     return r;
   }
   bool is_zero() const { return (l[0] | l[1] | l[2] | l[3] | l[4]) == 0; }
+  void sub(const u320& o) {  // precondition: *this >= o
+    unsigned __int128 b = 0;
+    for (int i = 0; i < 5; i++) {
+      unsigned __int128 t = (unsigned __int128)l[i] - o.l[i] - b;
+      l[i] = (uint64_t)t;
+      b = (t >> 64) & 1;
+    }
+  }
   void add(const u320& o) {
     unsigned __int128 c = 0;
     for (int i = 0; i < 5; i++) {
@@ -92,7 +100,22 @@ class ValidatorManager {
     for (size_t i = 0; i < order.size(); i++) power_[order[i]] = powers[i];
     quorum_ = total.quorum();
     initialised_ = true;
+    epoch_++;
     return true;
+  }
+  // for the store's incremental per-view power accumulators: voting power of one address, and a counter that changes
+  // whenever the table does (accumulators computed under another epoch are recomputed lazily)
+  bool Lookup(const Bytes& addr, u320& out) const {
+    std::shared_lock<std::shared_mutex> lk(mu_);
+    auto it = power_.find(addr);
+    if (it == power_.end()) return false;
+    out = it->second;
+    return true;
+  }
+  uint64_t epoch() const { return epoch_; }
+  bool PowerReachesQuorum(const u320& power) const {
+    std::shared_lock<std::shared_mutex> lk(mu_);
+    return initialised_ && power.cmp(quorum_) >= 0;
   }
   bool initialised() const { return initialised_; }
   u320 quorum_size() const { return quorum_; }
@@ -139,6 +162,7 @@ class ValidatorManager {
  private:
   mutable std::shared_mutex mu_;  // vpLock
   bool initialised_ = false;
+  uint64_t epoch_ = 0;
   std::map<Bytes, u320> power_;
   std::vector<Bytes> order_;
   std::vector<u320> powers_;

@@ -12,6 +12,7 @@
 #include <set>
 
 #include "proto.hpp"
+#include "quorum.hpp"
 
 namespace ibft::host {
 
@@ -110,10 +111,37 @@ class Messages {
   using SignalFn = std::function<void(uint32_t type, uint64_t height, uint64_t round)>;
   SignalFn on_signal;  // stands in for the event manager (messages.go:68-72)
 
+  // Incremental quorum bookkeeping.  The reference recomputes, for EVERY inbound message, a copy of all
+  // N stored messages of the view, an N-entry address set and an N-term big.Int sum (core/ibft.go:1113-1120,
+  // validator_manager.go:77-96, :147-155): O(N^2) per round.  With a power source attached, every view bucket keeps the
+  // summed voting power of its distinct senders up to date on insert / prune, and ViewPower answers in O(log N).
+  void SetPowerSource(const ValidatorManager* vm) { vm_ = vm; }
+
   void AddMessage(const MessagePtr& m) {  // :54-65
     if (!m || !m->view || m->type > ROUND_CHANGE) return;
     std::lock_guard<std::mutex> lk(mux_[m->type]);
-    maps_[m->type][m->view->height][m->view->round][m->from] = m;
+    ViewBucket& b = maps_[m->type][m->view->height][m->view->round];
+    auto ins = b.msgs.insert_or_assign(m->from, m);
+    if (ins.second && vm_ && b.epoch == vm_->epoch()) {  // a NEW sender (a replacement leaves the sender set unchanged)
+      u320 p;
+      if (vm_->Lookup(m->from, p)) b.power.add(p);
+    }
+  }
+  // summed voting power and number of the distinct senders stored for (view, type); has_sender tests one address.
+  // Returns false when no power source is attached.
+  bool ViewPower(const View& v, uint32_t type, u320* power, size_t* count, const Bytes* probe, bool* has_probe) {
+    if (!vm_) return false;
+    std::lock_guard<std::mutex> lk(mux_[type]);
+    *power = u320();
+    *count = 0;
+    if (has_probe) *has_probe = false;
+    ViewBucket* b = bucket(type, v);
+    if (!b) return true;
+    refresh(*b);
+    *power = b->power;
+    *count = b->msgs.size();
+    if (probe && has_probe) *has_probe = b->msgs.count(*probe) != 0;
+    return true;
   }
   void SignalEvent(uint32_t type, const View& v) {
     if (on_signal) on_signal(type, v.height, v.round);
@@ -141,7 +169,16 @@ class Messages {
       if (!is_valid(kv.second)) { invalid_keys.push_back(kv.first); continue; }
       valid.push_back(kv.second);
     }
-    for (auto& k : invalid_keys) msgs->erase(k);
+    if (!invalid_keys.empty()) {
+      ViewBucket* b = bucket(type, v);
+      for (auto& k : invalid_keys) {
+        if (vm_ && b && b->epoch == vm_->epoch()) {
+          u320 p;
+          if (vm_->Lookup(k, p)) b->power.sub(p);
+        }
+        msgs->erase(k);
+      }
+    }
     return valid;
   }
   // Snapshot of the stored messages of a view (no validation, no pruning): what the batching shim feeds to the GPU
@@ -159,7 +196,7 @@ class Messages {
     auto it = maps_[type].find(height);
     if (it != maps_[type].end())
       for (auto& rm : it->second)
-        for (auto& kv : rm.second) out.push_back(kv.second);
+        for (auto& kv : rm.second.msgs) out.push_back(kv.second);
     return out;
   }
   // :202-245 -- highest round whose valid messages satisfy isValidRCC; does not prune.  `found` distinguishes the Go nil
@@ -176,7 +213,7 @@ class Messages {
         uint64_t round = rm.first;
         if (round <= highest) continue;
         std::vector<MessagePtr> valid;
-        for (auto& kv : rm.second)
+        for (auto& kv : rm.second.msgs)
           if (is_valid_msg(kv.second)) valid.push_back(kv.second);
         if (!is_valid_rcc(round, valid)) continue;
         highest = round;
@@ -197,10 +234,10 @@ class Messages {
     if (it != maps_[ROUND_CHANGE].end()) {
       for (auto& rm : it->second) {
         if (rm.first < min_round) continue;
-        if (rm.second.size() > best) { best_round = rm.first; best = rm.second.size(); }
+        if (rm.second.msgs.size() > best) { best_round = rm.first; best = rm.second.msgs.size(); }
       }
       if (best_round != 0)
-        for (auto& kv : it->second[best_round]) out.push_back(kv.second);
+        for (auto& kv : it->second[best_round].msgs) out.push_back(kv.second);
     }
     if (found) *found = best_round != 0;
     return out;
@@ -208,16 +245,35 @@ class Messages {
 
  private:
   using ProtoMessages = std::map<Bytes, MessagePtr>;            // sender -> message   (messages.go:296)
-  using RoundMap = std::map<uint64_t, ProtoMessages>;            // round  -> messages  (:293)
+  struct ViewBucket {
+    ProtoMessages msgs;
+    u320 power;                         // sum of votingPower over the distinct senders that are validators
+    uint64_t epoch = ~0ull;             // ValidatorManager epoch `power` was computed under (~0: never)
+  };
+  using RoundMap = std::map<uint64_t, ViewBucket>;               // round  -> messages  (:293)
   using HeightMap = std::map<uint64_t, RoundMap>;                // height -> rounds    (:290)
   HeightMap maps_[4];
   std::mutex mux_[4];  // one lock per message type (:44-49)
+  const ValidatorManager* vm_ = nullptr;
 
-  ProtoMessages* find(uint32_t type, const View& v) {
+  ViewBucket* bucket(uint32_t type, const View& v) {
     auto h = maps_[type].find(v.height);
     if (h == maps_[type].end()) return nullptr;
     auto r = h->second.find(v.round);
     return r == h->second.end() ? nullptr : &r->second;
+  }
+  ProtoMessages* find(uint32_t type, const View& v) {
+    ViewBucket* b = bucket(type, v);
+    return b ? &b->msgs : nullptr;
+  }
+  void refresh(ViewBucket& b) {  // the validator table changed (new height): recompute once, O(N)
+    if (!vm_ || b.epoch == vm_->epoch()) return;
+    b.power = u320();
+    for (auto& kv : b.msgs) {
+      u320 p;
+      if (vm_->Lookup(kv.first, p)) b.power.add(p);
+    }
+    b.epoch = vm_->epoch();
   }
 };
 

@@ -178,6 +178,28 @@ class GpuVerifier : public Verifier {
     verify_pending(batch);
   }
 
+  // Re-verification of the >= Q committed seals of an imported block (Backend.InsertProposal, core/backend.go:78-81; the same
+  // check a syncing node performs): all seals in ONE launch.  valid[i] = IsValidCommittedSeal(hash, seals[i]).
+  std::vector<bool> VerifyCommittedSeals(const Bytes& proposal_hash, const std::vector<CommittedSeal>& seals) {
+    std::lock_guard<std::recursive_mutex> lk(mu_);
+    std::vector<Pending> batch;
+    std::vector<Bytes> keys(seals.size());
+    std::unordered_map<Bytes, size_t> seen;
+    for (size_t i = 0; i < seals.size(); i++) {
+      Pending p;
+      if (!seal_item(&proposal_hash, &seals[i], p)) continue;
+      keys[i] = p.key;
+      if (!cache_.count(p.key) && seen.emplace(p.key, batch.size()).second) batch.push_back(std::move(p));
+    }
+    verify_pending(batch);
+    std::vector<bool> valid(seals.size(), false);
+    for (size_t i = 0; i < seals.size(); i++) {
+      auto it = keys[i].empty() ? cache_.end() : cache_.find(keys[i]);
+      valid[i] = it != cache_.end() && it->second;
+    }
+    return valid;
+  }
+
   uint64_t device_calls() const { return device_calls_; }
   uint64_t items_verified() const { return items_verified_; }
   uint64_t frames_handed_back() const { return frames_handed_back_; }

@@ -332,3 +332,51 @@ def test_randomised_differential_commit_rounds():
         d.handle_commit(7, 0)
         d.c.prune_by_height(8)
         assert d.c.num_messages(7, 0, ip.COMMIT) == 0
+
+
+def test_incremental_quorum_accumulators_match_reference_semantics():
+    """AddMessage with O(log N) incremental voting-power accumulators must signal exactly when the
+    reference's recompute-everything path (core/ibft.go:1113-1120) does -- under replacement, pruning, table changes, the
+    PREPARE proposer rule, unknown senders."""
+    rnd = random.Random(77)
+    for trial in range(30):
+        n = rnd.randint(4, 10)
+        powers = {b"node %d" % i: rnd.randint(1, 4) for i in range(n)}
+        d = Dual(n, powers=powers, is_valid_proposal_hash=lambda p, h: h == HASH)
+        d.c.set_incremental_quorum(True)
+        proposal = ip.IbftMessage(ip.View(3, 0), b"node 0", b"", ip.PREPREPARE, ip.PrePrepareMessage(ip.Proposal(b"b", 0), HASH))
+        d.set_state(3, 0, L.PREPARE_STATE if rnd.random() < 0.7 else L.NEW_ROUND, proposal if rnd.random() < 0.8 else None)
+        for step in range(40):
+            who = b"node %d" % rnd.randint(0, n + 1)                  # includes two non-validators
+            t = rnd.choice([ip.PREPARE, ip.COMMIT, ip.ROUND_CHANGE, ip.PREPREPARE])
+            view = ip.View(3, rnd.choice([0, 0, 0, 1]))
+            payload = {ip.PREPARE: ip.PrepareMessage(HASH if rnd.random() < 0.8 else b"x"), ip.COMMIT: ip.CommitMessage(HASH, b"s"),
+                       ip.ROUND_CHANGE: ip.RoundChangeMessage(), ip.PREPREPARE: ip.PrePrepareMessage(ip.Proposal(b"b", 0), HASH)}[t]
+            d.add_message(ip.IbftMessage(view, who, bytes([step]), t, payload))
+            assert d.c.signal_count() == len(d.o.messages.signals), (trial, step)
+            if rnd.random() < 0.15:
+                d.handle_prepare(3, 0)                                   # prunes bad-hash PREPAREs: accumulators must follow
+                d.set_state(3, 0, L.PREPARE_STATE, proposal)
+            if rnd.random() < 0.05:                                      # validator table changes (new epoch)
+                powers = {k: rnd.randint(1, 4) for k in powers}
+                d.vm.set_current_voting_power(powers)
+                names = sorted(powers)
+                assert d.c.set_validators(3, names, [powers[k] for k in names]) == 0
+
+
+def test_incremental_quorum_is_faster_on_a_large_round():
+    import time
+    n = 3000
+    addrs = [b"v%05d" % i for i in range(n)]
+    wires = [enc(ip.IbftMessage(ip.View(1, 0), a, b"", ip.COMMIT, ip.CommitMessage(HASH, b"s"))) for a in addrs]
+    times = {}
+    for inc in (False, True):
+        c = host.HostContext("callback")
+        assert c.set_validators(1, addrs, None) == 0
+        c.set_state(1, 0)
+        c.set_incremental_quorum(inc)
+        t0 = time.perf_counter()
+        c.add_messages(wires)
+        times[inc] = time.perf_counter() - t0
+        assert c.signal_count() == n - (2 * n // 3 + 1) + 1          # one signal per arrival from the quorum-th sender on
+    assert times[True] * 5 < times[False], times
