@@ -226,3 +226,34 @@ def test_raw_frame_mode_same_decisions_and_fallback():
         assert c.store_senders(height, 0, t) == sorted(m.from_ for m in o.messages.maps[t].get(height, {}).get(0, {}).values())
     assert c.num_messages(height, 0, ip.PREPARE) == len(prepares) - 1
     c.close()
+
+
+def test_insert_proposal_seal_reverification_one_launch():
+    """the >= Q committed seals handed to Backend.InsertProposal (core/backend.go:78-81) are re-verified
+    in one launch (what a syncing node does for every imported block)."""
+    n, height = 64, 12
+    vs = wl.ValidatorSet(33, n, weighted=True)
+    ph = co.keccak256(b"imported block")
+    sd = wl.seal_digest(ph)
+    c = gpu_ctx(lambda a, h, r: False)
+    assert c.set_validators(height, vs.addrs, vs.powers) == 0
+    c.set_state(height, 0)
+    seals = [(vs.addrs[i], wl.sign(vs.keys[i], sd)) for i in range(n)]
+    quorum = 2 * sum(vs.powers) // 3 + 1
+    calls0 = c.gpu_device_calls()
+    ok, nv = c.verify_committed_seals(ph, seals)
+    assert ok and nv == n and c.gpu_device_calls() - calls0 == 1
+    # corrupt seals until the valid ones stay just below quorum
+    order = sorted(range(n), key=lambda i: -vs.powers[i])
+    kept, power = [], 0
+    for i in order:
+        if power + vs.powers[i] < quorum:
+            kept.append(i)
+            power += vs.powers[i]
+    bad = [(vs.addrs[i], wl.sign(vs.keys[i], sd)) if i in kept else (vs.addrs[i], wl.sign(vs.keys[(i + 1) % n], sd)) for i in range(n)]
+    ok, nv = c.verify_committed_seals(ph, bad)
+    assert not ok and nv == len(kept)
+    extra = [i for i in range(n) if i not in kept][0]
+    ok, nv = c.verify_committed_seals(ph, bad + [seals[extra]])
+    assert nv == len(kept) + 1 and ok == (power + vs.powers[extra] >= quorum)
+    c.close()
