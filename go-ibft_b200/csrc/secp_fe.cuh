@@ -429,6 +429,48 @@ IBFT_HD fe fe_reduce512(const uint32_t* R) {
   fe r;
 #if IBFT_PTX
   uint32_t S[8], s8, s9;
+#if defined(IBFT_REDUCE_SHIFT)
+  // H*977 on the ALU pipe instead of 8 wide MACs on the (saturated) FMA pipe: 977 = 2^10 - 2^6 + 2^4 + 1, so
+  // T = (H<<10) - (H<<6) + (H<<4) + H with funnel shifts and three carry chains (9 limbs, T[8] < 2^10).
+  {
+    const uint32_t* H = R + 8;
+    uint32_t A[9], B6[9], B4[9];
+    A[0] = H[0] << 10; B6[0] = H[0] << 6; B4[0] = H[0] << 4;
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+      A[i] = __funnelshift_l(H[i - 1], H[i], 10);
+      B6[i] = __funnelshift_l(H[i - 1], H[i], 6);
+      B4[i] = __funnelshift_l(H[i - 1], H[i], 4);
+    }
+    A[8] = H[7] >> 22; B6[8] = H[7] >> 26; B4[8] = H[7] >> 28;
+    uint32_t U[9];  // U = B4 + H
+    asm("add.cc.u32 %0,%9,%18;\n\taddc.cc.u32 %1,%10,%19;\n\taddc.cc.u32 %2,%11,%20;\n\taddc.cc.u32 %3,%12,%21;\n\t"
+        "addc.cc.u32 %4,%13,%22;\n\taddc.cc.u32 %5,%14,%23;\n\taddc.cc.u32 %6,%15,%24;\n\taddc.cc.u32 %7,%16,%25;\n\t"
+        "addc.u32 %8,%17,0;"
+        : "=r"(U[0]), "=r"(U[1]), "=r"(U[2]), "=r"(U[3]), "=r"(U[4]), "=r"(U[5]), "=r"(U[6]), "=r"(U[7]), "=r"(U[8])
+        : "r"(B4[0]), "r"(B4[1]), "r"(B4[2]), "r"(B4[3]), "r"(B4[4]), "r"(B4[5]), "r"(B4[6]), "r"(B4[7]), "r"(B4[8]), "r"(H[0]), "r"(H[1]),
+          "r"(H[2]), "r"(H[3]), "r"(H[4]), "r"(H[5]), "r"(H[6]), "r"(H[7]));
+    // U = U + A - B6   (two chains; every partial result fits in 9 limbs and the final one is non-negative)
+    asm("add.cc.u32 %0,%0,%9;\n\taddc.cc.u32 %1,%1,%10;\n\taddc.cc.u32 %2,%2,%11;\n\taddc.cc.u32 %3,%3,%12;\n\t"
+        "addc.cc.u32 %4,%4,%13;\n\taddc.cc.u32 %5,%5,%14;\n\taddc.cc.u32 %6,%6,%15;\n\taddc.cc.u32 %7,%7,%16;\n\t"
+        "addc.u32 %8,%8,%17;"
+        : "+r"(U[0]), "+r"(U[1]), "+r"(U[2]), "+r"(U[3]), "+r"(U[4]), "+r"(U[5]), "+r"(U[6]), "+r"(U[7]), "+r"(U[8])
+        : "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(A[8]));
+    asm("sub.cc.u32 %0,%0,%9;\n\tsubc.cc.u32 %1,%1,%10;\n\tsubc.cc.u32 %2,%2,%11;\n\tsubc.cc.u32 %3,%3,%12;\n\t"
+        "subc.cc.u32 %4,%4,%13;\n\tsubc.cc.u32 %5,%5,%14;\n\tsubc.cc.u32 %6,%6,%15;\n\tsubc.cc.u32 %7,%7,%16;\n\t"
+        "subc.u32 %8,%8,%17;"
+        : "+r"(U[0]), "+r"(U[1]), "+r"(U[2]), "+r"(U[3]), "+r"(U[4]), "+r"(U[5]), "+r"(U[6]), "+r"(U[7]), "+r"(U[8])
+        : "r"(B6[0]), "r"(B6[1]), "r"(B6[2]), "r"(B6[3]), "r"(B6[4]), "r"(B6[5]), "r"(B6[6]), "r"(B6[7]), "r"(B6[8]));
+    // S = L + T[0..7], s8 = T[8] + carry
+    asm("add.cc.u32 %0,%9,%17;\n\taddc.cc.u32 %1,%10,%18;\n\taddc.cc.u32 %2,%11,%19;\n\taddc.cc.u32 %3,%12,%20;\n\t"
+        "addc.cc.u32 %4,%13,%21;\n\taddc.cc.u32 %5,%14,%22;\n\taddc.cc.u32 %6,%15,%23;\n\taddc.cc.u32 %7,%16,%24;\n\t"
+        "addc.u32 %8,%25,0;"
+        : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5]), "=r"(S[6]), "=r"(S[7]), "=r"(s8)
+        : "r"(R[0]), "r"(R[1]), "r"(R[2]), "r"(R[3]), "r"(R[4]), "r"(R[5]), "r"(R[6]), "r"(R[7]), "r"(U[0]), "r"(U[1]), "r"(U[2]),
+          "r"(U[3]), "r"(U[4]), "r"(U[5]), "r"(U[6]), "r"(U[7]), "r"(U[8]));
+    s9 = 0;
+  }
+#else
   uint32_t t0, t1, t2, t3, t4, t5, t6, t7, u0, u1, u2, u3, u4, u5, u6, u7;
   mulw(t0, t1, R[8], IBFT_PC); mulw(t2, t3, R[10], IBFT_PC); mulw(t4, t5, R[12], IBFT_PC); mulw(t6, t7, R[14], IBFT_PC);
   mulw(u0, u1, R[9], IBFT_PC); mulw(u2, u3, R[11], IBFT_PC); mulw(u4, u5, R[13], IBFT_PC); mulw(u6, u7, R[15], IBFT_PC);
@@ -445,6 +487,7 @@ IBFT_HD fe fe_reduce512(const uint32_t* R) {
       "addc.u32 %8,0,0;"
       : "+r"(S[1]), "+r"(S[2]), "+r"(S[3]), "+r"(S[4]), "+r"(S[5]), "+r"(S[6]), "+r"(S[7]), "+r"(s8), "=r"(s9)
       : "r"(u0), "r"(u1), "r"(u2), "r"(u3), "r"(u4), "r"(u5), "r"(u6), "r"(u7));
+#endif
   // S[1..8] += H ; S[9] += carry
   asm("add.cc.u32 %0,%0,%9;\n\taddc.cc.u32 %1,%1,%10;\n\taddc.cc.u32 %2,%2,%11;\n\taddc.cc.u32 %3,%3,%12;\n\t"
       "addc.cc.u32 %4,%4,%13;\n\taddc.cc.u32 %5,%5,%14;\n\taddc.cc.u32 %6,%6,%15;\n\taddc.cc.u32 %7,%7,%16;\n\t"
