@@ -841,11 +841,23 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
     CU(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[n_chunks], 0));
   }
   int rc = IBFT_OK;
+  // A caller that already holds the tuples in page-locked memory (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory)
+  // is copied from directly; pageable memory (Go heap through cgo) goes through the engine's pinned staging first.
+  bool caller_pinned = false;
+  if (n) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, items) == cudaSuccess) caller_pinned = pa.type == cudaMemoryTypeHost;
+    else (void)cudaGetLastError();
+  }
   for (uint32_t c = 0; c < n_chunks; c++) {
     uint32_t lo = c * CHUNK, hi = std::min(n, lo + CHUNK);
-    memcpy(e->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
+    const ibft_sig_item* src = items + lo;
+    if (!caller_pinned) {
+      memcpy(e->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
+      src = e->h_items + lo;
+    }
     cudaStream_t cs = n_chunks > 1 ? e->copy_stream : st;
-    CU(cudaMemcpyAsync(e->d_items + lo, e->h_items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(e->d_items + lo, src, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, cs));
     if (n_chunks > 1) {
       CU(cudaEventRecord(e->chunk_ev[c], cs));
       CU(cudaStreamWaitEvent(st, e->chunk_ev[c], 0));
