@@ -30,7 +30,7 @@ static_assert(IBFT_GTABLE_WG == IBFT_WG, "regenerate secp_gtable.inc (tools/gen_
 
 #define IBFT_BLOCK 128
 #ifndef IBFT_GTAB_SMEM
-#define IBFT_GTAB_SMEM (IBFT_WG <= 8)
+#define IBFT_GTAB_SMEM (IBFT_WG <= 8 && IBFT_WC == 0)  // with a combined table the recover kernel never reads the small one
 #endif
 #define IBFT_ITEM_ROW_WORDS 33  // 128-byte item + 1 pad word: conflict-free per-thread reads from shared memory
 
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(BLOCK, (IBFT_MIN_BLOCKS * IBFT_BLOCK) / BLOCK)
 k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
           uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
           const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
-          uint8_t* __restrict__ recovered, uint8_t* __restrict__ status) {
+          uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable) {
 #if IBFT_GTAB_SMEM
   __shared__ uint32_t s_gtab[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];
 #else
@@ -133,6 +133,7 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
     int st = resolve_item(it, arena, arena_len, ri, &have);  // raw frames are parsed here (IBFT_KIND_WIRE*)
     if (status != nullptr) status[idx] = (uint8_t)st;
     gtab_view G{s_gtab};
+    G.comb = ctable;
     rtab_view T{s_rtab + tid, (uint32_t)BLOCK};
     bool rec = have && ecrecover_address(ri.r, ri.s, ri.v, ri.z, G, T, addr);
     if (!rec) {
@@ -300,6 +301,50 @@ __global__ void k_keccak_batch(const uint8_t* __restrict__ arena, size_t arena_l
 #pragma unroll
   for (int k = 0; k < 32; k++) out[(size_t)i * 32 + k] = h[k];
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// combined generator table (IBFT_WC > 0): entry (d1, d2) = d1*G + d2*lambda*G, computed with the kernel's own scalar
+// multiplication as (d1 + d2*lambda mod n) * G and checked against the oracle in tests/test_gpu_primitives.py
+// ------------------------------------------------------------------------------------------------------------
+#if IBFT_WC > 0
+__global__ void __launch_bounds__(64)
+k_build_ctable(uint32_t* __restrict__ out) {
+  __shared__ uint32_t s_gtab[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];
+  __shared__ uint32_t s_rtab[64 * IBFT_RTAB_WORDS];
+  for (uint32_t i = threadIdx.x; i < IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES; i += 64) s_gtab[i] = g_gtable[i];
+  __syncthreads();
+  size_t e = (size_t)blockIdx.x * 64 + threadIdx.x;
+  if (e >= (size_t)IBFT_CTAB_ENTRIES) return;
+  int d1 = (int)(e / IBFT_CTAB_D2), d2 = (int)(e % IBFT_CTAB_D2) - (1 << (IBFT_WC - 1));
+  const uint32_t lam[8] = {0x1B23BD72u, 0xDF02967Cu, 0x20816678u, 0x122E22EAu, 0x8812645Au, 0xA5261C02u, 0xC05C30E0u, 0x5363AD4Cu};
+  sc a, b, l;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { a.v[i] = 0; b.v[i] = 0; l.v[i] = lam[i]; }
+  a.v[0] = (uint32_t)d1;
+  b.v[0] = (uint32_t)(d2 < 0 ? -d2 : d2);
+  sc t = sc_mul(b, l);
+  if (d2 < 0) t = sc_neg(t);
+  sc k = sc_add(a, t);
+  uint32_t* o = out + IBFT_GTAB_ENTRY_WORDS * e;
+  gtab_view G{s_gtab};
+  rtab_view T{s_rtab + threadIdx.x, 64u};
+  aff g1;
+  G.load(0, g1.x, g1.y);
+  sc zero;
+#pragma unroll
+  for (int i = 0; i < 8; i++) zero.v[i] = 0;
+  jac P = ecmult_double(k, zero, g1, G, T);
+  if (P.inf || fe_is_zero(P.z)) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) o[i] = 0;  // (0, 0): never looked up
+    return;
+  }
+  fe zi = IBFT_FE_INV(P.z), zi2 = fe_sqr(zi);
+  fe x = fe_normalize(fe_mul(P.x, zi2)), y = fe_normalize(fe_mul(P.y, fe_mul(zi2, zi)));
+#pragma unroll
+  for (int i = 0; i < 8; i++) { o[i] = x.v[i]; o[8 + i] = y.v[i]; }
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------------------
 // batched signing (MessageConstructor side)
@@ -521,6 +566,7 @@ struct ibft_engine {
   int sm_count = 148;
   const uint8_t* dev_arena = nullptr;
   size_t dev_arena_len = 0;
+  uint32_t* d_ctable = nullptr;  // combined generator table (IBFT_WC > 0)
   cudaFuncAttributes recover_attr{};
 };
 
@@ -535,6 +581,7 @@ static void engine_free(ibft_engine* e) {
     if (s.d_powers) cudaFree(s.d_powers);
   }
   cudaFree(e->d_status); cudaFreeHost(e->h_status);
+  cudaFree(e->d_ctable);
   cudaFree(e->d_items); cudaFree(e->d_arena); cudaFree(e->d_bitmap); cudaFree(e->d_recovered); cudaFree(e->d_groups);
   cudaFree(e->d_gdev); cudaFree(e->d_results); cudaFree(e->d_voted); cudaFree(e->d_nvalid); cudaFree(e->d_slots);
   cudaFreeHost(e->h_items); cudaFreeHost(e->h_arena); cudaFreeHost(e->h_bitmap); cudaFreeHost(e->h_recovered);
@@ -585,8 +632,37 @@ static int engine_alloc(ibft_engine* e) {
     CU(cudaGetDeviceProperties(&prop, p.device));
     e->sm_count = prop.multiProcessorCount;
   }
+#if IBFT_WC > 0
+  {
+    size_t entries = (size_t)IBFT_CTAB_ENTRIES;
+    CU(cudaMalloc(&e->d_ctable, entries * IBFT_GTAB_ENTRY_WORDS * 4));
+    k_build_ctable<<<(unsigned)((entries + 63) / 64), 64, 0, e->stream>>>(e->d_ctable);
+    e->launches++;
+    CU(cudaGetLastError());
+  }
+#endif
   CU(cudaDeviceSynchronize());
   return IBFT_OK;
+}
+
+// test hook: copy `count` entries of the combined generator table starting at entry `first` (64 bytes each, x then y as 8
+// little-endian words); returns IBFT_ERR_INVALID_ARG when the library was built without a combined table
+extern "C" int ibft_debug_ctable(ibft_engine* e, uint32_t first, uint32_t count, uint8_t* out, int* wc, uint32_t* entries) {
+  if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
+  if (wc) *wc = IBFT_WC;
+#if IBFT_WC > 0
+  if (entries) *entries = (uint32_t)IBFT_CTAB_ENTRIES;
+  if (count == 0) return IBFT_OK;
+  if (!out || (size_t)first + count > (size_t)IBFT_CTAB_ENTRIES) { set_err("range"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->p.device));
+  CU(cudaMemcpy(out, e->d_ctable + (size_t)first * IBFT_GTAB_ENTRY_WORDS, (size_t)count * 64, cudaMemcpyDeviceToHost));
+  return IBFT_OK;
+#else
+  if (entries) *entries = 0;
+  (void)first; (void)out;
+  return count == 0 ? IBFT_OK : IBFT_ERR_INVALID_ARG;
+#endif
 }
 
 extern "C" int ibft_engine_create(const ibft_engine_params* params, ibft_engine** out) {
@@ -766,11 +842,11 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
   if (hi - lo <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs (latency path)
     uint32_t blocks = (hi - lo + 31) / 32;
     k_recover<32><<<blocks, 32, 32 * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status);
+                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
   } else {
     uint32_t blocks = (hi - lo + IBFT_BLOCK - 1) / IBFT_BLOCK;
     k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status);
+                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
   }
   e->launches++;
   CU(cudaGetLastError());

@@ -116,12 +116,37 @@ IBFT_PT jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
 #define IBFT_WR 4  // per-signature window: table {1..8} * R
 #define IBFT_GTAB_ENTRIES (1 << (IBFT_WG - 1))
 #define IBFT_NWIN_R 33  // ceil(130 / 4)
+#if IBFT_WC > 0
+static_assert(IBFT_WC % IBFT_WR == 0 && IBFT_WC <= 12, "combined window must be a multiple of the R window");
+#endif
 static_assert(IBFT_WG % IBFT_WR == 0, "generator window must be a multiple of the R window");
+
+// Optional COMBINED generator table (IBFT_WC = 8 or 12, 0 = off): entry (d1, d2), 0 <= d1 <= 2^(WC-1), |d2| <= 2^(WC-1), holds
+// d1*G + d2*lambda*G (affine x, y), so the two generator digit streams cost ONE addition per window instead of two.  The
+// other half of the (d1, d2) plane is reached by negating y.  (2^(WC-1)+1) * (2^WC+1) * 64 bytes: 2.1 MB for WC = 8
+// (L2 resident), 537 MB for WC = 12 (HBM; 704 B of gathers per signature) -- built on the device at engine creation.
+#ifndef IBFT_WC
+#define IBFT_WC 8  // measured on B200: off 34.9 M, 8 -> 37.8 M (+8 %), 12 -> 38.8 M verifies/s
+#endif
+#define IBFT_CTAB_D2 ((1 << IBFT_WC) + 1)
+#define IBFT_CTAB_ENTRIES (((1 << (IBFT_WC - 1)) + 1) * IBFT_CTAB_D2)
 
 // Generator table accessor: entry i (0-based) = (i+1)*G as 16 words x[8] y[8] (shared memory on the device).
 #define IBFT_GTAB_ENTRY_WORDS 16
 struct gtab_view {
   const uint32_t* base;
+  const uint32_t* comb = nullptr;  // combined table (global memory) or nullptr
+  IBFT_HD void load_comb(int d1, int d2, fe& x, fe& y) const {
+    const uint32_t* e = comb + (size_t)IBFT_GTAB_ENTRY_WORDS * ((size_t)d1 * IBFT_CTAB_D2 + (size_t)(d2 + (1 << (IBFT_WC > 0 ? IBFT_WC - 1 : 0))));
+#if defined(__CUDA_ARCH__)
+    const uint4* q = reinterpret_cast<const uint4*>(e);
+    uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w; x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
+    y.v[0] = c.x; y.v[1] = c.y; y.v[2] = c.z; y.v[3] = c.w; y.v[4] = d.x; y.v[5] = d.y; y.v[6] = d.z; y.v[7] = d.w;
+#else
+    for (int i = 0; i < 8; i++) { x.v[i] = e[i]; y.v[i] = e[8 + i]; }
+#endif
+  }
   IBFT_HD void load(int idx, fe& x, fe& y) const {
     const uint32_t* e = base + IBFT_GTAB_ENTRY_WORDS * idx;
 #pragma unroll
@@ -231,20 +256,42 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
       IBFT_ROLLED
       for (int t = 0; t < IBFT_WR; t++) acc = jac_double(acc);
     }
-    // streams 0,1: R and lambda*R every window; streams 2,3: G and lambda*G every (WG/WR)-th window
+    // streams 0,1: R and lambda*R every window; streams 2,3: G and lambda*G every (WG/WR)-th window -- or, with a combined
+    // table, ONE stream for both generator halves every (WC/WR)-th window
+#if IBFT_WC > 0
+    const bool comb = G.comb != nullptr;
+    const int ns = comb ? ((j % (IBFT_WC / IBFT_WR) == 0) ? 3 : 2) : ((j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2);
+#else
     const int ns = (j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2;
+#endif
     IBFT_ROLLED
     for (int s = 0; s < ns; s++) {
-      int d = s < 2 ? booth_digit<IBFT_WR>(ks[s], j) : booth_digit<IBFT_WG>(ks[s], j / (IBFT_WG / IBFT_WR));
-      if (d != 0) {
+      fe x, y;
+      bool neg, use_beta = false;
+#if IBFT_WC > 0
+      if (comb && s == 2) {
+        int jg = j / (IBFT_WC / IBFT_WR);
+        int d1 = booth_digit<IBFT_WC>(ks[2], jg), d2 = booth_digit<IBFT_WC>(ks[3], jg);
+        if (kneg[2]) d1 = -d1;
+        if (kneg[3]) d2 = -d2;
+        if ((d1 | d2) == 0) continue;
+        neg = d1 < 0 || (d1 == 0 && d2 < 0);
+        if (neg) { d1 = -d1; d2 = -d2; }
+        G.load_comb(d1, d2, x, y);
+      } else
+#endif
+      {
+        int d = s < 2 ? booth_digit<IBFT_WR>(ks[s], j) : booth_digit<IBFT_WG>(ks[s], j / (IBFT_WG / IBFT_WR));
+        if (d == 0) continue;
         int idx = (d < 0 ? -d : d) - 1;
-        fe x, y;
         if (s < 2) T.load(idx, x, y);
         else G.load(idx, x, y);
-        if (s & 1) x = fe_mul(x, beta);  // lambda * (x, y) = (beta x, y)
-        if ((d < 0) != kneg[s]) y = fe_neg(y);
-        acc = jac_add_affine(acc, x, y);
+        use_beta = (s & 1) != 0;
+        neg = (d < 0) != kneg[s];
       }
+      if (use_beta) x = fe_mul(x, beta);  // lambda * (x, y) = (beta x, y)
+      if (neg) y = fe_neg(y);
+      acc = jac_add_affine(acc, x, y);
     }
   }
   return acc;

@@ -32,7 +32,7 @@ EXPORTS = [
     "ibft_abi_version", "ibft_last_error", "ibft_engine_create", "ibft_engine_destroy", "ibft_engine_device_info",
     "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_last_item_status", "ibft_verify_submit", "ibft_verify_poll",
     "ibft_verify_wait", "ibft_bind_groups", "ibft_verify_batch_device", "ibft_quorum_reduce_device", "ibft_quorum_partial_words", "ibft_quorum_mark_device", "ibft_quorum_merge_device",
-    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_probe_int_peak", "ibft_debug_op",
+    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_probe_int_peak", "ibft_debug_op", "ibft_debug_ctable",
 ]
 
 
@@ -87,6 +87,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.ibft_keccak256_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_uint32, c_void_p]
     lib.ibft_sign_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]
     lib.ibft_probe_int_peak.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double)]
+    lib.ibft_debug_ctable.argtypes = [c_void_p, c_uint32, c_uint32, c_void_p, POINTER(c_int), POINTER(c_uint32)]
     lib.ibft_debug_op.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_uint32]
     if path is None:
         _LIB = lib
@@ -249,6 +250,16 @@ class Engine:
         out = np.zeros((n, 65), dtype=np.uint8)
         self._check(self.lib.ibft_sign_batch(self.handle, _ptr(D), _ptr(Z), _ptr(K), n, _ptr(out)))
         return [bytes(out[i]) for i in range(n)]
+
+    def combined_table_info(self):
+        wc, n = c_int(), c_uint32()
+        self._check(self.lib.ibft_debug_ctable(self.handle, 0, 0, None, ctypes.byref(wc), ctypes.byref(n)))
+        return int(wc.value), int(n.value)
+
+    def combined_table_entries(self, first: int, count: int) -> np.ndarray:
+        out = np.zeros((count, 16), dtype=np.uint32)
+        self._check(self.lib.ibft_debug_ctable(self.handle, first, count, _ptr(out), None, None))
+        return out
 
     # ---- primitive parity hooks (tests)
     def debug_op(self, op: str, a: list[int], b: list[int] | None = None, c: list[bytes] | None = None, out_stride: int = 32):

@@ -225,6 +225,10 @@ int ibft_probe_int_peak(ibft_engine* e, double* imad_per_s, double* wide_mac_per
 #define IBFT_DBG_FE_ADD 8   /* out = a+b mod p */
 #define IBFT_DBG_FE_SUB 9   /* out = a-b mod p */
 #define IBFT_DBG_GLV 10     /* out(64) = |k1| (16B BE) || |k2| (16B BE) || sign1 || sign2 padded -- see tests */
+/* Combined generator table (builds with IBFT_WC > 0): *wc = window (0 when absent), *entries = table size; copies `count`
+ * 64-byte entries (x, y as 8 little-endian words each) starting at `first`.  Entry index = d1 * (2^wc + 1) + d2 + 2^(wc-1)
+ * holds d1*G + d2*lambda*G. */
+int ibft_debug_ctable(ibft_engine* e, uint32_t first, uint32_t count, uint8_t* out, int* wc, uint32_t* entries);
 int ibft_debug_op(ibft_engine* e, int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint32_t n,
                   uint8_t* out, uint32_t out_stride);
 

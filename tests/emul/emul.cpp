@@ -10,7 +10,65 @@
 #include "../../go-ibft_b200/csrc/verify_core.cuh"
 #include "../../go-ibft_b200/csrc/secp_gtable.inc"
 
+#include <cstdio>
+#include <thread>
+#include <vector>
+
 using namespace ibft;
+
+// Combined generator table for the emulation: built once with the portable code (all host threads) and cached next to this
+// file (tests/emul/ctable_wc<W>.bin, git-ignored).  The GPU builds its own copy in k_build_ctable.
+#if IBFT_WC > 0
+static const uint32_t* emul_ctable() {
+  static std::vector<uint32_t> tab;
+  if (!tab.empty()) return tab.data();
+  const size_t entries = (size_t)IBFT_CTAB_ENTRIES;
+  tab.assign(entries * 16, 0);
+  char path[512];
+  snprintf(path, sizeof path, "%s/ctable_wc%d.bin", EMUL_DIR, IBFT_WC);
+  if (FILE* f = fopen(path, "rb")) {
+    size_t got = fread(tab.data(), 4, tab.size(), f);
+    fclose(f);
+    if (got == tab.size()) return tab.data();
+  }
+  const uint32_t lam[8] = {0x1B23BD72u, 0xDF02967Cu, 0x20816678u, 0x122E22EAu, 0x8812645Au, 0xA5261C02u, 0xC05C30E0u, 0x5363AD4Cu};
+  unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([&, t]() {
+      gtab_view G{IBFT_GTABLE};
+      uint32_t rtab[IBFT_RTAB_WORDS];
+      rtab_view T{rtab, 1};
+      for (size_t e = t; e < entries; e += nt) {
+        int d1 = (int)(e / IBFT_CTAB_D2), d2 = (int)(e % IBFT_CTAB_D2) - (1 << (IBFT_WC - 1));
+        sc a, b, l, zero;
+        for (int i = 0; i < 8; i++) { a.v[i] = 0; b.v[i] = 0; zero.v[i] = 0; l.v[i] = lam[i]; }
+        a.v[0] = (uint32_t)d1;
+        b.v[0] = (uint32_t)(d2 < 0 ? -d2 : d2);
+        sc tt = sc_mul(b, l);
+        if (d2 < 0) tt = sc_neg(tt);
+        sc k = sc_add(a, tt);
+        aff g1;
+        G.load(0, g1.x, g1.y);
+        jac P = ecmult_double(k, zero, g1, G, T);
+        if (P.inf || fe_is_zero(P.z)) continue;
+        fe zi = IBFT_FE_INV(P.z), zi2 = fe_sqr(zi);
+        fe x = fe_normalize(fe_mul(P.x, zi2)), y = fe_normalize(fe_mul(P.y, fe_mul(zi2, zi)));
+        for (int i = 0; i < 8; i++) { tab[16 * e + i] = x.v[i]; tab[16 * e + 8 + i] = y.v[i]; }
+      }
+    });
+  for (auto& x : th) x.join();
+  if (FILE* f = fopen(path, "wb")) { fwrite(tab.data(), 4, tab.size(), f); fclose(f); }
+  return tab.data();
+}
+static gtab_view emul_gview() {
+  gtab_view G{IBFT_GTABLE};
+  G.comb = emul_ctable();
+  return G;
+}
+#else
+static gtab_view emul_gview() { return gtab_view{IBFT_GTABLE}; }
+#endif
 
 extern "C" {
 
@@ -22,7 +80,7 @@ int emul_verify_item(const ibft_sig_item* it, const uint8_t* arena, size_t arena
   int st = resolve_item(*it, arena, arena_len, ri, &valid);
   if (st != IBFT_ITEM_OK) return -1;  // NEEDS_HOST
   if (!valid) return 0;
-  gtab_view G{IBFT_GTABLE};
+  gtab_view G = emul_gview();
   uint32_t rtab[IBFT_RTAB_WORDS];
   rtab_view T{rtab, 1};
   if (!ecrecover_address(ri.r, ri.s, ri.v, ri.z, G, T, addr)) return 0;
@@ -57,7 +115,7 @@ int emul_debug_op(int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, 
       return 0;
     }
     case IBFT_DBG_ECMULT: {  // out = a*G + b*P, P = (c[0..31], c[32..63]) affine on the curve; all-zero out = infinity
-      gtab_view G{IBFT_GTABLE};
+      gtab_view G = emul_gview();
       aff P;
       P.x = fe_from_be(c);
       P.y = fe_from_be(c + 32);
@@ -77,7 +135,7 @@ int emul_debug_op(int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, 
 }
 
 extern "C" int emul_sign(const uint8_t* d, const uint8_t* z, const uint8_t* k, uint8_t* sig65) {
-  gtab_view G{IBFT_GTABLE};
+  gtab_view G = emul_gview();
   uint32_t rtab[IBFT_RTAB_WORDS];
   rtab_view T{rtab, 1};
   return ecdsa_sign(d, z, k, G, T, sig65) ? 1 : 0;

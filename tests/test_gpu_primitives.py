@@ -74,3 +74,22 @@ def test_ecmult(engine):
     for p, x, y, o in zip(pts, a, b, out):
         want = co.ecmult2(x, y, p[0].to_bytes(32, "big") + p[1].to_bytes(32, "big"))
         assert o == (want or bytes(64)), (x, y)
+
+
+def test_combined_generator_table_entries(engine):
+    """Entries of the device-built combined table (d1*G + d2*lambda*G) against the oracle's scalar multiplication."""
+    wc, n = engine.combined_table_info()
+    if wc == 0:
+        pytest.skip("library built without a combined generator table")
+    half, d2n = 1 << (wc - 1), (1 << wc) + 1
+    assert n == (half + 1) * d2n
+    rnd = random.Random(26)
+    picks = [(0, 1), (0, -1), (1, 0), (1, 1), (1, -1), (half, half), (half, -half), (0, half), (half, 0), (3, -7)]
+    picks += [(rnd.randint(0, half), rnd.randint(-half, half)) for _ in range(60)]
+    for d1, d2 in picks:
+        e = engine.combined_table_entries(d1 * d2n + d2 + half, 1)[0]
+        x = sum(int(e[i]) << (32 * i) for i in range(8))
+        y = sum(int(e[8 + i]) << (32 * i) for i in range(8))
+        want = co.ecmult2((d1 + d2 * LAM) % N, 0, None)
+        assert (x.to_bytes(32, "big") + y.to_bytes(32, "big")) == want, (d1, d2)
+    assert not engine.combined_table_entries(half, 1)[0].any()        # (0, 0) = infinity: zeros, never looked up
