@@ -369,7 +369,7 @@ def main():
             pass
     hbm_gbs = kernel_rate * ALGO_BYTES_PER_VERIFY / 1e9
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this same configuration (per launch)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, executed = None, None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         try:
@@ -377,6 +377,7 @@ def main():
             if int(tj.get("items_per_launch", 0)) == n_local:
                 traffic = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"])
                 traffic_src = tj.get("capture")
+                executed = tj.get("executed")
         except Exception:
             pass
     line = {
@@ -390,6 +391,10 @@ def main():
         "roofline": {"bound": "int32-imad-issue", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-class instr/s",
                      "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per k_recover launch (ncu)",
                      "traffic_source": traffic_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VERIFY * n_local,
+                     "executed_per_ncu": executed,
+                     "note": "frac uses SURVEY 8d's canonical-algorithm count (5.0e5 IMAD-class instr/verify); the kernel executes fewer "
+                             "multiply instructions than that (GLV, combined generator table, safegcd, fused IMAD.WIDE), so frac can "
+                             "exceed 1; executed_per_ncu gives the real instruction counts",
                      "kernel": "k_recover", "kernel_ms": ms_kernel, "kernel_verifies_per_s_per_gpu": kernel_rate,
                      "algorithmic_instr_per_verify": ALGO_IMAD_PER_VERIFY,
                      "peak_source": "dependent-free mad.lo.u32 probe on this GPU (ibft_probe_int_peak), measured live",
