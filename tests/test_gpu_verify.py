@@ -300,3 +300,31 @@ def test_no_groups_and_capacity_errors(engine):
         small.set_validators(0, 1, np.zeros((9, 20), np.uint8), None)
     assert ei.value.code == 4
     small.close()
+
+
+def test_random_tuples_recovered_addresses_match_oracle(engine):
+    """Fuzz: 20k random (r, s, v, digest) tuples -- half of all r are not abscissas, v is often invalid, some r/s are out of
+    range -- the recovered address (or its absence) must equal the oracle's for every one of them."""
+    rng = np.random.default_rng(123)
+    n = 20000
+    items = np.zeros(n, dtype=ib.ITEM_DTYPE)
+    items["r"] = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    items["s"] = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    items["digest"] = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    items["v"] = rng.choice([0, 1, 0, 1, 2, 27, 28, 255], size=n)
+    items["r"][::97] = 0
+    items["s"][::89] = 0
+    items["r"][5::101] = 0xFF                                  # >= n
+    items["digest"][::53] = 0                                   # z = 0
+    _, _, recovered = engine.verify_batch(items, b"", None, want_recovered=True)
+    import ctypes
+    lib = co.lib()
+    out = (ctypes.c_uint8 * 20)()
+    n_rec = 0
+    for i in range(n):
+        ok = lib.oracle_ecrecover_address(items["digest"][i].ctypes.data_as(ctypes.c_void_p), items["r"][i].ctypes.data_as(ctypes.c_void_p),
+                                          items["s"][i].ctypes.data_as(ctypes.c_void_p), ctypes.c_uint8(int(items["v"][i])), out)
+        want = bytes(out) if ok else bytes(20)
+        n_rec += bool(ok)
+        assert bytes(recovered[i]) == want, i
+    assert 2000 < n_rec < 8000
