@@ -130,6 +130,7 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
     uint8_t addr[20];
     resolved_item ri;
     bool have = false;
+    IBFT_STAGE(0);
     int st = resolve_item(it, arena, arena_len, ri, &have);  // raw frames are parsed here (IBFT_KIND_WIRE*)
     if (status != nullptr) status[idx] = (uint8_t)st;
     gtab_view G{s_gtab};
@@ -163,6 +164,98 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
   // warp-ballot reduction of the 32 verdicts into one bitmap word (shard bounds are multiples of 32)
   uint32_t word = __ballot_sync(0xFFFFFFFFu, ok);
   if ((tid & 31) == 0 && idx < shard_hi) bitmap[idx >> 5] = word;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1 + K2, latency variant: FOUR LANES PER SIGNATURE.  A 10k-validator COMMIT round is one wave of independent serial
+// chains on the throughput kernel (~5.4k dependent field multiplications each); here the quad's lanes share each chain --
+// every lane holds the full state, the up-to-four independent products of a group-law level go one per lane and come back
+// through shared memory (secp_ec.cuh, exec_quad).  Everything outside the double-scalar multiplication (Keccak, sqrt,
+// inversions) is simply replicated: the kernel does ~4x the work of k_recover and is only used when the batch is too small
+// to fill the machine anyway.  CTA = 128 threads = 32 signatures = one bitmap word.
+// ------------------------------------------------------------------------------------------------------------
+#define IBFT_QUAD_SIGS 32
+__global__ void __launch_bounds__(4 * IBFT_QUAD_SIGS, 2)
+k_recover_quad(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
+               uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
+               const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
+               uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable) {
+  __shared__ uint32_t s_items[IBFT_QUAD_SIGS * IBFT_ITEM_ROW_WORDS];
+  __shared__ uint32_t s_rtab[IBFT_QUAD_SIGS * IBFT_QTAB_WORDS];  // projective (XYZZ) tables {1..8}*R
+  __shared__ uint4 s_xb[4 * 4 * IBFT_QUAD_SIGS];  // exec_quad's product exchange buffer (2 parities x 2 halves per thread)
+  __shared__ uint32_t s_word;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t q = tid >> 2;  // signature within the CTA
+  const uint32_t base = shard_lo + blockIdx.x * IBFT_QUAD_SIGS;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(items + base);
+    uint32_t avail = base < shard_hi ? min((uint32_t)IBFT_QUAD_SIGS, shard_hi - base) : 0u;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      uint32_t u = tid + k * 4 * IBFT_QUAD_SIGS;  // uint4 index within the CTA's tuple block (32 tuples x 8)
+      uint32_t row = u >> 3, col = u & 7;
+      if (row < avail) {
+        uint4 v = __ldg(src + u);
+        uint32_t* d = s_items + row * IBFT_ITEM_ROW_WORDS + col * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+    if (tid == 0) s_word = 0;
+  }
+  __syncthreads();
+  const uint32_t idx = base + q;
+  bool ok = false;
+  if (idx < shard_hi) {  // uniform over the quad
+    ibft_sig_item it;
+    {
+      uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+      const uint32_t* s = s_items + q * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+      for (int i = 0; i < 32; i++) w[i] = s[i];
+    }
+    exec_quad ex;
+    ex.role = (int)(tid & 3u);
+    ex.mask = 0xFu << (tid & 28u);
+    ex.xb = s_xb;
+    ex.par = 0;
+    uint8_t addr[20];
+    resolved_item ri;
+    bool have = false;
+    IBFT_STAGE(0);
+    int st = resolve_item(it, arena, arena_len, ri, &have);
+    gtab_view G{g_gtable};
+    G.comb = ctable;
+    rtab_view T{s_rtab + q, (uint32_t)IBFT_QUAD_SIGS};
+    bool rec = have && ecrecover_address_x(ex, ri.r, ri.s, ri.v, ri.z, G, T, addr);
+    if (!rec) {
+#pragma unroll
+      for (int i = 0; i < 20; i++) addr[i] = 0;
+    }
+    ok = rec;
+#pragma unroll
+    for (int i = 0; i < 20; i++) ok = ok && (addr[i] == ri.signer[i]);
+    if (ok && groups != nullptr) {
+      if (it.group >= n_groups) {
+        ok = false;
+      } else {
+        uint32_t slot = groups[it.group].table_slot;
+        if (slot != IBFT_NO_TABLE) {
+          if (slot >= n_slots || !slots[slot].valid) ok = false;
+          else ok = lookup_validator(slots[slot], ri.signer) >= 0;
+        }
+      }
+    }
+    if (ex.leader()) {
+      if (status != nullptr) status[idx] = (uint8_t)st;
+      if (recovered != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 20; i++) recovered[(size_t)idx * 20 + i] = addr[i];
+      }
+      if (ok) atomicOr(&s_word, 1u << q);
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && base < shard_hi) bitmap[base >> 5] = s_word;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -563,6 +656,7 @@ struct ibft_engine {
   std::vector<ibft_group_desc> last_groups;
   pending_call pending;
   uint64_t launches = 0;
+  int recover_path = IBFT_PATH_AUTO;
   int sm_count = 148;
   const uint8_t* dev_arena = nullptr;
   size_t dev_arena_len = 0;
@@ -839,12 +933,23 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
                           uint32_t lo, uint32_t hi, const ibft_group_desc* d_groups, uint32_t n_groups, uint32_t* d_bitmap,
                           uint8_t* d_recovered, cudaStream_t st, uint8_t* d_status = nullptr) {
   if (hi <= lo) return IBFT_OK;
-  if (hi - lo <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs (latency path)
-    uint32_t blocks = (hi - lo + 31) / 32;
+  // path selection (ibft_set_recover_path).  AUTO: a batch that fits ONE four-lane CTA per SM (<= SMs x 32 signatures, one warp
+  // per scheduler: 0.55 ms instead of 0.86 ms on a B200) takes the latency kernel; with more warps per scheduler the
+  // redundant work of the quads costs more than the shorter chain saves (10,000 signatures: 0.99 ms vs 0.86 ms), so larger
+  // batches stay on the one-thread-per-signature kernel -- one-warp CTAs while a single wave covers them, 128-thread CTAs beyond.
+  const uint32_t cnt = hi - lo;
+  int path = e->recover_path;
+  if (path == IBFT_PATH_AUTO) path = cnt <= (uint32_t)e->sm_count * IBFT_QUAD_SIGS ? IBFT_PATH_QUAD : IBFT_PATH_THREAD;
+  if (path == IBFT_PATH_QUAD) {
+    uint32_t blocks = (cnt + IBFT_QUAD_SIGS - 1) / IBFT_QUAD_SIGS;
+    k_recover_quad<<<blocks, 4 * IBFT_QUAD_SIGS, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
+  } else if (cnt <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs
+    uint32_t blocks = (cnt + 31) / 32;
     k_recover<32><<<blocks, 32, 32 * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                          e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
   } else {
-    uint32_t blocks = (hi - lo + IBFT_BLOCK - 1) / IBFT_BLOCK;
+    uint32_t blocks = (cnt + IBFT_BLOCK - 1) / IBFT_BLOCK;
     k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                                          e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
   }
@@ -1214,7 +1319,14 @@ done:
   return rc;
 }
 
-extern "C" uint64_t ibft_engine_launch_count(ibft_engine* e) { return e ? e->launches : 0; }
+extern "C" int ibft_set_recover_path(ibft_engine* e, int path) {
+  if (e == nullptr || path < IBFT_PATH_AUTO || path > IBFT_PATH_QUAD) { set_err("bad recover path"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> g(e->mu);
+  e->recover_path = path;
+  return IBFT_OK;
+}
+
+uint64_t ibft_engine_launch_count(ibft_engine* e) { return e ? e->launches : 0; }
 
 extern "C" int ibft_probe_int_peak(ibft_engine* e, double* imad_per_s, double* wide_mac_per_s) {
   if (!e || !imad_per_s || !wide_mac_per_s) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }

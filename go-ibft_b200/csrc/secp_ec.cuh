@@ -108,6 +108,169 @@ IBFT_PT jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lane executors.  The group law below is written as LEVELS of up to four independent field multiplications.
+//   exec_serial  one thread per signature (throughput path): the products of a level are computed one after the other.
+//   exec_quad    four lanes per signature (latency path, "several lanes per signature" of the north star): every lane keeps a
+//                full copy of the state, lane q of the quad computes product q of the level, and the four results are
+//                exchanged through shared memory.  On the XYZZ law below the critical path of a doubling is 3 multiplications, of
+//                an addition 4 (one thread: 7 and 11 on the Jacobian law of the throughput path).
+// ------------------------------------------------------------------------------------------------
+struct exec_serial {
+  IBFT_HD void mul4(const fe* a, const fe* b, int count, fe* out) const {
+    for (int k = 0; k < count; k++) out[k] = fe_mul(a[k], b[k]);
+  }
+  IBFT_HD bool leader() const { return true; }
+  IBFT_HD void sync() const {}
+};
+
+#if defined(__CUDACC__)
+struct exec_quad {
+  int role;       // lane & 3
+  unsigned mask;  // the four lanes of this quad: quads of one warp may diverge from each other, never the lanes of a quad
+  // operand of THIS lane's product: a two-level binary select on the role bits.  Written with selp so that the compiler
+  // keeps the candidates in registers (the C ternary chain was turned into a role-indexed LOCAL-memory array: 550 cycles).
+  __device__ __forceinline__ static uint32_t sel(uint32_t if_set, uint32_t if_clear, int bit) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.u32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(if_set), "r"(if_clear), "r"(bit));
+    return r;
+  }
+  __device__ __forceinline__ static fe pick(int role, const fe* v, int count) {
+    fe r;
+    const int b0 = role & 1, b1 = role & 2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint32_t lo = count > 1 ? sel(v[1].v[i], v[0].v[i], b0) : v[0].v[i];
+      uint32_t hi = count > 3 ? sel(v[3].v[i], v[2].v[i], b0) : (count > 2 ? v[2].v[i] : lo);
+      r.v[i] = count > 2 ? sel(hi, lo, b1) : lo;
+    }
+    return r;
+  }
+  // exchange buffer in shared memory: two parities x two halves x one uint4 per thread of the CTA (conflict-free: lane t owns
+  // slot t; the four lanes of a quad read the same four consecutive slots).  A warp shuffle costs ~10 cycles of issue on this
+  // part (330 cycles for the 32 shuffles of a four-product level); two STS.128 + 2k LDS.128 + one quad-level sync are cheaper.
+  uint4* xb;            // CTA-wide buffer, 4 * blockDim.x uint4
+  mutable uint32_t par; // level parity: double buffering, so one sync per level suffices
+  __device__ __forceinline__ void mul4(const fe* a, const fe* b, int count, fe* out) const {
+    fe p = fe_mul(pick(role, a, count), pick(role, b, count));
+    const uint32_t nt = blockDim.x * blockDim.y;
+    const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
+    uint4* buf = xb + par * 2u * nt;
+    par ^= 1u;
+    if (role < count) {
+      buf[t] = make_uint4(p.v[0], p.v[1], p.v[2], p.v[3]);
+      buf[nt + t] = make_uint4(p.v[4], p.v[5], p.v[6], p.v[7]);
+    }
+    __syncwarp(mask);
+    const uint32_t q0 = t & ~3u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k < count) {
+        uint4 lo = buf[q0 + k], hi = buf[nt + q0 + k];
+        out[k].v[0] = lo.x; out[k].v[1] = lo.y; out[k].v[2] = lo.z; out[k].v[3] = lo.w;
+        out[k].v[4] = hi.x; out[k].v[5] = hi.y; out[k].v[6] = hi.z; out[k].v[7] = hi.w;
+      }
+    }
+  }
+  __device__ __forceinline__ bool leader() const { return role == 0; }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+#endif
+
+// The latency path keeps its accumulator in XYZZ coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2): with four products per
+// level a doubling is 3 levels deep (9 products) and a FULL addition 4 levels (14 products) -- the same depth as a mixed
+// addition -- so the per-signature table needs no normalisation (no batched inversion) and one adder serves both the
+// R streams (XYZZ entries) and the generator stream (affine entries, ZZ = ZZZ = 1).  Jacobian dbl-2009-l / madd are 4 and 5
+// levels deep.  Formulas: EFD dbl-2008-s-1 and add-2008-s for short Weierstrass curves with a = 0.
+struct xyzz {
+  fe x, y, zz, zzz;
+  bool inf;
+};
+
+// levels: {U^2, X^2} -> {U*V, X*V, M^2, V*ZZ} -> {M*(S-X3), W*Y, W*ZZZ}        (U = 2Y, V = U^2, W = U*V, S = X*V, M = 3X^2)
+template <class EX>
+IBFT_HD xyzz xyzz_double_x(const EX& ex, const xyzz& p) {
+  xyzz r;
+  fe a[4], b[4], o[4];
+  fe U = fe_dbl(p.y);
+  a[0] = U; b[0] = U; a[1] = p.x; b[1] = p.x;
+  ex.mul4(a, b, 2, o);
+  fe V = o[0];
+  fe M = fe_add(fe_dbl(o[1]), o[1]);
+  a[0] = U; b[0] = V; a[1] = p.x; b[1] = V; a[2] = M; b[2] = M; a[3] = V; b[3] = p.zz;
+  ex.mul4(a, b, 4, o);
+  fe W = o[0], S = o[1];
+  r.x = fe_sub(o[2], fe_dbl(S));
+  r.zz = o[3];
+  a[0] = M; b[0] = fe_sub(S, r.x); a[1] = W; b[1] = p.y; a[2] = W; b[2] = p.zzz;
+  ex.mul4(a, b, 3, o);
+  r.y = fe_sub(o[0], o[1]);
+  r.zzz = o[2];
+  r.inf = p.inf;
+  return r;
+}
+
+// levels: {X1*ZZ2, X2*ZZ1, Y1*ZZZ2, Y2*ZZZ1} -> {P^2, R^2, ZZ1*ZZ2, ZZZ1*ZZZ2} -> {P*PP, U1*PP, ZZ12*PP}
+//         -> {R*(Q-X3), S1*PPP, ZZZ12*PPP}.   q is never the point at infinity (zero digits are skipped by the caller).
+template <class EX>
+IBFT_HD xyzz xyzz_add_x(const EX& ex, const xyzz& p, const xyzz& q) {
+  if (p.inf) return q;
+  xyzz r;
+  fe a[4], b[4], o[4];
+  a[0] = p.x; b[0] = q.zz; a[1] = q.x; b[1] = p.zz; a[2] = p.y; b[2] = q.zzz; a[3] = q.y; b[3] = p.zzz;
+  ex.mul4(a, b, 4, o);
+  fe U1 = o[0], S1 = o[2];
+  fe P = fe_sub(o[1], U1), R = fe_sub(o[3], S1);
+  a[0] = P; b[0] = P; a[1] = R; b[1] = R; a[2] = p.zz; b[2] = q.zz; a[3] = p.zzz; b[3] = q.zzz;
+  ex.mul4(a, b, 4, o);
+  fe PP = o[0], RR = o[1], ZZ12 = o[2], ZZZ12 = o[3];
+  a[0] = P; b[0] = PP; a[1] = U1; b[1] = PP; a[2] = ZZ12; b[2] = PP;
+  ex.mul4(a, b, 3, o);
+  fe PPP = o[0], Q = o[1];
+  r.zz = o[2];
+  r.x = fe_sub(fe_sub(RR, PPP), fe_dbl(Q));
+  a[0] = R; b[0] = fe_sub(Q, r.x); a[1] = S1; b[1] = PPP; a[2] = ZZZ12; b[2] = PPP;
+  ex.mul4(a, b, 3, o);
+  r.y = fe_sub(o[0], o[1]);
+  r.zzz = o[2];
+  r.inf = false;
+  // exceptional cases, tested last so that the zero tests overlap the generic computation: every lane of a quad holds the
+  // same state, so the whole quad takes these (rare) branches together
+  if (fe_is_zero(P)) {
+    if (fe_is_zero(R)) return xyzz_double_x(ex, p);  // same point
+    r.inf = true;                                     // opposite points
+  }
+  return r;
+}
+
+// per-signature table {1..8}*R in XYZZ (32 words per entry), same thread-interleaved shared-memory layout as rtab_view
+struct qtab_view {
+  uint32_t* base;
+  uint32_t stride;
+  IBFT_HD void store(int entry, const xyzz& p) const {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      base[(uint32_t)(entry * 32 + i) * stride] = p.x.v[i];
+      base[(uint32_t)(entry * 32 + 8 + i) * stride] = p.y.v[i];
+      base[(uint32_t)(entry * 32 + 16 + i) * stride] = p.zz.v[i];
+      base[(uint32_t)(entry * 32 + 24 + i) * stride] = p.zzz.v[i];
+    }
+  }
+  IBFT_HD xyzz load(int entry) const {
+    xyzz p;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      p.x.v[i] = base[(uint32_t)(entry * 32 + i) * stride];
+      p.y.v[i] = base[(uint32_t)(entry * 32 + 8 + i) * stride];
+      p.zz.v[i] = base[(uint32_t)(entry * 32 + 16 + i) * stride];
+      p.zzz.v[i] = base[(uint32_t)(entry * 32 + 24 + i) * stride];
+    }
+    p.inf = false;
+    return p;
+  }
+};
+#define IBFT_QTAB_WORDS 256  // 8 entries x 32 words per signature
+
+// ------------------------------------------------------------------------------------------------
 // u1*G + u2*R
 // ------------------------------------------------------------------------------------------------
 #ifndef IBFT_WG
@@ -215,6 +378,7 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
   // AFFINE with one shared inversion (Montgomery's trick over the seven Z's), so that every addition of the main loop
   // is a mixed addition (8M+3S instead of 12M+4S) and the loop holds a single adder.
   const fe beta = fe_beta();
+  IBFT_STAGE(4);
   {
     fe zs[8];  // Z of entry m
     T.store(0, R.x, R.y);
@@ -231,11 +395,13 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
       zs[m] = t.z;
     }
     // prefix products pre[m] = Z_1 * ... * Z_m (Z_0 = 1), one inversion, then peel the inverses off backwards
+    IBFT_STAGE(5);
     fe pre[8];
     pre[1] = zs[1];
     IBFT_ROLLED
     for (int m = 2; m < 8; m++) pre[m] = fe_mul(pre[m - 1], zs[m]);
     fe acc_inv = fe_inv_for_table(pre[7]);
+    IBFT_STAGE(6);
     IBFT_ROLLED
     for (int m = 7; m >= 1; m--) {
       fe zi = m > 1 ? fe_mul(acc_inv, pre[m - 1]) : acc_inv;  // 1 / Z_m
@@ -247,6 +413,7 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
     }
   }
 
+  IBFT_STAGE(7);
   jac acc;
   acc.x = fe_zero(); acc.y = fe_zero(); acc.z = fe_zero();
   acc.inf = true;
@@ -292,6 +459,98 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
       if (use_beta) x = fe_mul(x, beta);  // lambda * (x, y) = (beta x, y)
       if (neg) y = fe_neg(y);
       acc = jac_add_affine(acc, x, y);
+    }
+  }
+  return acc;
+}
+
+// The same double-scalar multiplication on the latency path: level-structured XYZZ group law driven by a lane executor
+// (exec_quad on the device; the serial executor in the host emulation).  Same digit streams as ecmult_double; the
+// per-signature table stays projective.  Table writes are done by the quad's leader lane, with a quad-level sync around them.
+template <class EX>
+IBFT_HD xyzz ecmult_double_x(const EX& ex, const sc& u1, const sc& u2, const aff& R, const gtab_view& G, const qtab_view& T) {
+  uint32_t ks[4][6];
+  bool kneg[4];
+  {
+    glv_half h1, h2;
+    glv_split(u2, h1, h2);
+#pragma unroll
+    for (int i = 0; i < 5; i++) { ks[0][i] = h1.k[i]; ks[1][i] = h2.k[i]; }
+    kneg[0] = h1.neg; kneg[1] = h2.neg;
+    glv_split(u1, h1, h2);
+#pragma unroll
+    for (int i = 0; i < 5; i++) { ks[2][i] = h1.k[i]; ks[3][i] = h2.k[i]; }
+    kneg[2] = h1.neg; kneg[3] = h2.neg;
+    ks[0][5] = ks[1][5] = ks[2][5] = ks[3][5] = 0;
+  }
+  const fe beta = fe_beta();
+  const fe one = fe_from_u32(1);
+  IBFT_STAGE(4);
+  {
+    xyzz e0;
+    e0.x = R.x; e0.y = R.y; e0.zz = one; e0.zzz = one; e0.inf = false;
+    if (ex.leader()) T.store(0, e0);
+    ex.sync();
+    IBFT_ROLLED
+    for (int m = 1; m < 8; m++) {
+      int src = (m & 1) ? ((m + 1) >> 1) - 1 : m - 1;
+      xyzz p = T.load(src);
+      xyzz t = (m & 1) ? xyzz_double_x(ex, p) : xyzz_add_x(ex, p, e0);
+      if (ex.leader()) T.store(m, t);
+      ex.sync();
+    }
+  }
+  IBFT_STAGE(5);
+  IBFT_STAGE(6);
+  IBFT_STAGE(7);
+  xyzz acc;
+  acc.x = fe_zero(); acc.y = fe_zero(); acc.zz = fe_zero(); acc.zzz = fe_zero();
+  acc.inf = true;
+  IBFT_ROLLED
+  for (int j = IBFT_NWIN_R - 1; j >= 0; j--) {
+    if (!acc.inf) {
+      IBFT_ROLLED
+      for (int t = 0; t < IBFT_WR; t++) acc = xyzz_double_x(ex, acc);
+    }
+#if IBFT_WC > 0
+    const bool comb = G.comb != nullptr;
+    const int ns = comb ? ((j % (IBFT_WC / IBFT_WR) == 0) ? 3 : 2) : ((j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2);
+#else
+    const int ns = (j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2;
+#endif
+    IBFT_ROLLED
+    for (int s = 0; s < ns; s++) {
+      xyzz q;
+      bool neg, use_beta = false;
+#if IBFT_WC > 0
+      if (comb && s == 2) {
+        int jg = j / (IBFT_WC / IBFT_WR);
+        int d1 = booth_digit<IBFT_WC>(ks[2], jg), d2 = booth_digit<IBFT_WC>(ks[3], jg);
+        if (kneg[2]) d1 = -d1;
+        if (kneg[3]) d2 = -d2;
+        if ((d1 | d2) == 0) continue;
+        neg = d1 < 0 || (d1 == 0 && d2 < 0);
+        if (neg) { d1 = -d1; d2 = -d2; }
+        G.load_comb(d1, d2, q.x, q.y);
+        q.zz = one; q.zzz = one; q.inf = false;
+      } else
+#endif
+      {
+        int d = s < 2 ? booth_digit<IBFT_WR>(ks[s], j) : booth_digit<IBFT_WG>(ks[s], j / (IBFT_WG / IBFT_WR));
+        if (d == 0) continue;
+        int idx = (d < 0 ? -d : d) - 1;
+        if (s < 2) {
+          q = T.load(idx);
+        } else {
+          G.load(idx, q.x, q.y);
+          q.zz = one; q.zzz = one; q.inf = false;
+        }
+        use_beta = (s & 1) != 0;
+        neg = (d < 0) != kneg[s];
+      }
+      if (use_beta) q.x = fe_mul(q.x, beta);  // lambda * (x, y) = (beta x, y)
+      if (neg) q.y = fe_neg(q.y);
+      acc = xyzz_add_x(ex, acc, q);
     }
   }
   return acc;

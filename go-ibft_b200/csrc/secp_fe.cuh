@@ -36,6 +36,19 @@
 #define IBFT_FN_ADD IBFT_HD
 #endif
 
+// Development instrumentation (tools/stage_clocks.cu): thread 0 of CTA 0 stamps clock64() at the pipeline's stage borders.
+// Never defined in the product build.
+#if defined(IBFT_STAGE_CLOCKS) && defined(__CUDACC__)
+__device__ unsigned long long g_stage_clk[16];
+#if defined(__CUDA_ARCH__)
+#define IBFT_STAGE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_stage_clk[i] = clock64(); } while (0)
+#else
+#define IBFT_STAGE(i) do { } while (0)
+#endif
+#else
+#define IBFT_STAGE(i) do { } while (0)
+#endif
+
 #if defined(__CUDA_ARCH__) && !defined(IBFT_PORTABLE_FE)
 #define IBFT_PTX 1
 #else

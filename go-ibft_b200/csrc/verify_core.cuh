@@ -226,14 +226,55 @@ IBFT_HD bool item_signer(const ibft_sig_item& it, const uint8_t* arena, size_t a
   return true;
 }
 
+// Executor dispatch of Q = u1*G + u2*R -> affine (false = point at infinity).  The throughput path keeps its hand-scheduled
+// Jacobian routine (ecmult_double); exec_levels runs the level-structured XYZZ routine of the latency path one product at a
+// time (host emulation: differential test of the level wiring); exec_quad runs it on four lanes.  T must hold
+// IBFT_RTAB_WORDS words per signature for the serial path, IBFT_QTAB_WORDS for the level-structured one.
+struct exec_levels : exec_serial {};
+IBFT_HD bool ecmult_affine(const exec_serial&, const sc& u1, const sc& u2, const aff& R, const gtab_view& G, const rtab_view& T,
+                           fe& qx, fe& qy) {
+  jac Q = ecmult_double(u1, u2, R, G, T);
+  IBFT_STAGE(8);
+  if (Q.inf || fe_is_zero(Q.z)) return false;
+  fe zi = IBFT_FE_INV(Q.z);
+  fe zi2 = fe_sqr(zi);
+  qx = fe_normalize(fe_mul(Q.x, zi2));
+  qy = fe_normalize(fe_mul(Q.y, fe_mul(zi2, zi)));
+  return true;
+}
+template <class EX>
+IBFT_HD bool ecmult_affine_levels(const EX& ex, const sc& u1, const sc& u2, const aff& R, const gtab_view& G, const rtab_view& T,
+                                  fe& qx, fe& qy) {
+  xyzz Q = ecmult_double_x(ex, u1, u2, R, G, qtab_view{T.base, T.stride});
+  IBFT_STAGE(8);
+  if (Q.inf || fe_is_zero(Q.zzz)) return false;
+  fe i3 = IBFT_FE_INV(Q.zzz);     // 1/Z^3
+  fe zi = fe_mul(Q.zz, i3);       // Z^2 / Z^3 = 1/Z
+  qx = fe_normalize(fe_mul(Q.x, fe_sqr(zi)));
+  qy = fe_normalize(fe_mul(Q.y, i3));
+  return true;
+}
+IBFT_HD bool ecmult_affine(const exec_levels& ex, const sc& u1, const sc& u2, const aff& R, const gtab_view& G, const rtab_view& T,
+                           fe& qx, fe& qy) {
+  return ecmult_affine_levels(ex, u1, u2, R, G, T, qx, qy);
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ bool ecmult_affine(const exec_quad& ex, const sc& u1, const sc& u2, const aff& R, const gtab_view& G,
+                                              const rtab_view& T, fe& qx, fe& qy) {
+  return ecmult_affine_levels(ex, u1, u2, R, G, T, qx, qy);
+}
+#endif
+
 // Recover the signer of (r, s, v) over digest z.  Returns false when the signature is invalid; addr20 then zero.
-IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t v, const uint8_t* z_be,
-                               const gtab_view& G, const rtab_view& T, uint8_t* addr20) {
+template <class EX>
+IBFT_HD bool ecrecover_address_x(const EX& ex, const uint8_t* r_be, const uint8_t* s_be, uint8_t v, const uint8_t* z_be,
+                                 const gtab_view& G, const rtab_view& T, uint8_t* addr20) {
 #pragma unroll
   for (int i = 0; i < 20; i++) addr20[i] = 0;
   sc r = sc_from_be(r_be), s = sc_from_be(s_be);
   if (v > 1) return false;
   if (sc_is_zero(r) || sc_is_zero(s) || sc_ge_n(r) || sc_ge_n(s)) return false;
+  IBFT_STAGE(1);
   // R = lift_x(r, v)   (r < n < p: always a canonical field element)
   fe x;
 #pragma unroll
@@ -246,19 +287,23 @@ IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t
   aff R;
   R.x = x;
   R.y = y;
+  IBFT_STAGE(2);
   // u1 = -z/r, u2 = s/r  (mod n)
   sc z = sc_reduce_once(sc_from_be(z_be));
   sc rinv = IBFT_SC_INV(r);
   sc u1 = sc_neg(sc_mul(z, rinv));
   sc u2 = sc_mul(s, rinv);
-  jac Q = ecmult_double(u1, u2, R, G, T);
-  if (Q.inf || fe_is_zero(Q.z)) return false;
-  fe zi = IBFT_FE_INV(Q.z);
-  fe zi2 = fe_sqr(zi);
-  fe qx = fe_normalize(fe_mul(Q.x, zi2));
-  fe qy = fe_normalize(fe_mul(Q.y, fe_mul(zi2, zi)));
+  IBFT_STAGE(3);
+  fe qx, qy;
+  if (!ecmult_affine(ex, u1, u2, R, G, T, qx, qy)) return false;
+  IBFT_STAGE(9);
   keccak256_xy_address(qx, qy, addr20);
+  IBFT_STAGE(10);
   return true;
+}
+IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t v, const uint8_t* z_be,
+                               const gtab_view& G, const rtab_view& T, uint8_t* addr20) {
+  return ecrecover_address_x(exec_serial{}, r_be, s_be, v, z_be, G, T, addr20);
 }
 
 // ECDSA signing with a given nonce (the MessageConstructor side: reference core/backend.go:12-34 requires every built

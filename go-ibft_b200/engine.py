@@ -32,7 +32,7 @@ EXPORTS = [
     "ibft_abi_version", "ibft_last_error", "ibft_engine_create", "ibft_engine_destroy", "ibft_engine_device_info",
     "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_last_item_status", "ibft_verify_submit", "ibft_verify_poll",
     "ibft_verify_wait", "ibft_bind_groups", "ibft_verify_batch_device", "ibft_quorum_reduce_device", "ibft_quorum_partial_words", "ibft_quorum_mark_device", "ibft_quorum_merge_device",
-    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_probe_int_peak", "ibft_debug_op", "ibft_debug_ctable",
+    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_set_recover_path", "ibft_probe_int_peak", "ibft_debug_op", "ibft_debug_ctable",
 ]
 
 
@@ -64,6 +64,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     so = path or os.environ.get("IBFT_LIB") or _build.build()  # IBFT_LIB: kernel-variant experiments (tools/quick_bench.py)
     lib = ctypes.CDLL(so)
     lib.ibft_last_error.restype = c_char_p
+    lib.ibft_set_recover_path.restype = c_int
+    lib.ibft_set_recover_path.argtypes = [c_void_p, c_int]
     lib.ibft_engine_launch_count.restype = c_uint64
     lib.ibft_engine_launch_count.argtypes = [c_void_p]
     lib.ibft_engine_create.argtypes = [POINTER(EngineParams), POINTER(c_void_p)]
@@ -131,6 +133,12 @@ class Engine:
         di = DeviceInfo()
         self._check(self.lib.ibft_engine_device_info(self.handle, ctypes.byref(di)))
         return {f: (getattr(di, f).decode() if f == "name" else getattr(di, f)) for f, _ in DeviceInfo._fields_}
+
+    PATH_AUTO, PATH_THREAD, PATH_QUAD = 0, 1, 2
+
+    def set_recover_path(self, path: int) -> None:
+        """Kernel selection of the recover step (include/ibft_verify.h IBFT_PATH_*): verdicts are identical on every path."""
+        self._check(self.lib.ibft_set_recover_path(self.handle, int(path)))
 
     def launch_count(self) -> int:
         return int(self.lib.ibft_engine_launch_count(self.handle))

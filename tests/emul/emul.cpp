@@ -88,6 +88,39 @@ int emul_verify_item(const ibft_sig_item* it, const uint8_t* arena, size_t arena
   return memcmp(addr, ri.signer, 20) == 0;
 }
 
+// the same item through the LEVEL-structured group law of the four-lane kernel (products of a level computed one by one)
+int emul_verify_item_levels(const ibft_sig_item* it, const uint8_t* arena, size_t arena_len, uint8_t* recovered20) {
+  uint8_t addr[20];
+  memset(recovered20, 0, 20);
+  resolved_item ri;
+  bool valid = false;
+  int st = resolve_item(*it, arena, arena_len, ri, &valid);
+  if (st != IBFT_ITEM_OK) return -1;
+  if (!valid) return 0;
+  gtab_view G = emul_gview();
+  uint32_t rtab[IBFT_QTAB_WORDS];
+  rtab_view T{rtab, 1};
+  if (!ecrecover_address_x(exec_levels{}, ri.r, ri.s, ri.v, ri.z, G, T, addr)) return 0;
+  memcpy(recovered20, addr, 20);
+  return memcmp(addr, ri.signer, 20) == 0;
+}
+
+// out(64) = a*G + b*P through the level-structured XYZZ routine of the latency path; returns 1 for infinity
+int emul_ecmult_levels(const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* out) {
+  gtab_view G = emul_gview();
+  aff P;
+  P.x = fe_from_be(c);
+  P.y = fe_from_be(c + 32);
+  uint32_t rtab[IBFT_QTAB_WORDS];
+  rtab_view T{rtab, 1};
+  fe qx, qy;
+  memset(out, 0, 64);
+  if (!ecmult_affine(exec_levels{}, sc_reduce_once(sc_from_be(a)), sc_reduce_once(sc_from_be(b)), P, G, T, qx, qy)) return 1;
+  fe_to_be(qx, out);
+  fe_to_be(qy, out + 32);
+  return 0;
+}
+
 void emul_keccak256(const uint8_t* d, uint32_t n, uint8_t* out) { keccak256_bytes(d, n, out); }
 
 // op codes = IBFT_DBG_* of include/ibft_verify.h

@@ -212,3 +212,39 @@ def test_raw_frame_kinds_canonical_and_mutated(emul):
             n_needs_host += want_status
             n_true += want_ok
     assert n_true >= 40 and n_needs_host >= 40
+
+
+# ------------------------------------------------------------------------ level-structured group law (four-lane kernel)
+def ecm_levels(E, a, b, pt):
+    out = (ctypes.c_uint8 * 64)()
+    rc = E.emul_ecmult_levels(B(a.to_bytes(32, "big")), B(b.to_bytes(32, "big")), B(pt[0].to_bytes(32, "big") + pt[1].to_bytes(32, "big")), out)
+    o = bytes(out)
+    return None if rc else (int.from_bytes(o[:32], "big"), int.from_bytes(o[32:], "big"))
+
+
+def test_level_structured_ecmult_matches_oracle(emul):
+    """secp_ec.cuh jac_double_x / jac_add_affine_x (the product LEVELS exec_quad distributes over four lanes), run with the
+    serial executor: same exceptional-case coverage as the one-thread routine."""
+    rnd = random.Random(15)
+    G = ec.G
+    pt = ec.point_mul(54321, G)
+    cases = [(0, 0), (1, 0), (0, 1), (2, 0), (0, 2), (N - 1, 0), (0, N - 1), (1, N - 1), (5, 7), (N - 1, N - 1), (LAM, 0), (0, LAM), (N - LAM, LAM)]
+    cases += [(rnd.getrandbits(256) % N, rnd.getrandbits(256) % N) for _ in range(12)]
+    for a, b in cases:
+        assert ecm_levels(emul, a, b, pt) == ec.point_add(ec.point_mul(a, G), ec.point_mul(b, pt))
+    for p2 in [G, ec.point_neg(G), ec.point_mul(2, G), ec.point_mul(LAM, G), ec.point_mul(N - LAM, G), ec.point_mul(8, G), ec.point_mul(N - 8, G)]:
+        for a, b in [(1, 1), (1, N - 1), (2, N - 1), (N - 2, 1), (8, 1), (8, N - 1), (3, 5), (LAM, 1), (1, LAM), (N - 1, N - 1), (7, 1), (16, N - 2)]:
+            assert ecm_levels(emul, a, b, p2) == ec.point_add(ec.point_mul(a, G), ec.point_mul(b, p2)), (a, b)
+
+
+def test_level_structured_recover_config2(emul):
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "config2.npz"))
+    items = np.ascontiguousarray(d["items"]).view(co.ITEM_DTYPE).reshape(-1)
+    arena = d["arena"].tobytes()
+    a = np.frombuffer(arena, np.uint8)
+    for i in range(0, len(items), 3):
+        o1, o2 = (ctypes.c_uint8 * 20)(), (ctypes.c_uint8 * 20)()
+        it = items[i:i + 1]
+        r1 = emul.emul_verify_item(it.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(arena)), o1)
+        r2 = emul.emul_verify_item_levels(it.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(arena)), o2)
+        assert (r1, bytes(o1)) == (r2, bytes(o2)), i
