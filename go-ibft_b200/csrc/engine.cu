@@ -258,6 +258,262 @@ k_recover_quad(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
   if (tid == 0 && base < shard_hi) bitmap[base >> 5] = s_word;
 }
 
+#if IBFT_WC > 0
+// ------------------------------------------------------------------------------------------------------------
+// K1 + K2, mid-size latency variant: CHAIN warps + one HELPER warp per CTA, one CTA per SM, one warp per scheduler.
+// A 10k-validator COMMIT round is 313 warps on the one-thread kernel -- 279 of the 592 schedulers idle while every busy one
+// walks the whole serial chain.  Here CTA = 3 chain warps (96 signatures, one per lane) + 1 helper warp that serves all
+// three: the helper takes the digest, r^-1, the GLV splits, the square root and u1*G (a comb without doublings) off the
+// chain, which only computes u2*R -- on an isomorphic curve, so that it does not have to wait for the root (verify_core.cuh,
+// "Split pipeline").  Hand-off through shared memory and named barriers (bar.arrive by the helper, bar.sync by the chain).
+// Capacity of one wave: SMs x 96 signatures (14,208 on a B200).
+// ------------------------------------------------------------------------------------------------------------
+#define IBFT_SPLIT_CHAINS 3
+#define IBFT_SPLIT_SIGS (32 * IBFT_SPLIT_CHAINS)
+#define IBFT_SLOT_WORDS 27  // [0..4] |k1|, [5..9] |k2| of u2, [10] flags, [11..18] y then gx, [19..26] gy ; see below
+#define IBFT_SPLIT_SMEM ((IBFT_SPLIT_SIGS * (IBFT_ITEM_ROW_WORDS + IBFT_RTAB_WORDS + IBFT_SLOT_WORDS + 8)) * 4)
+#define IBFT_SF_VALID 1u   // phase 1: (r, s, v) in range, digits posted
+#define IBFT_SF_NEG0 2u
+#define IBFT_SF_NEG1 4u
+#define IBFT_SF_ROOT 8u    // phase 2: r is an abscissa, y posted
+#define IBFT_SF_GINF 16u   // phase 2: u1*G is the point at infinity
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+__global__ void __launch_bounds__(32 * (IBFT_SPLIT_CHAINS + 1), 1)
+k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
+                uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
+                const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
+                uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable) {
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t* s_items = s_dyn;                                              // 96 packed tuples, 33-word rows
+  uint32_t* s_rtab = s_items + IBFT_SPLIT_SIGS * IBFT_ITEM_ROW_WORDS;     // 96 tables {1..8}*phi(R), signature-interleaved
+  uint32_t* s_slot = s_rtab + IBFT_SPLIT_SIGS * IBFT_RTAB_WORDS;          // hand-off slots, word w of signature i at [w*96 + i]
+  uint32_t* s_y = s_slot + IBFT_SPLIT_SIGS * IBFT_SLOT_WORDS;             // the root y, 8 words per signature, same interleave
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint32_t base = shard_lo + blockIdx.x * IBFT_SPLIT_SIGS;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(items + base);
+    uint32_t avail = base < shard_hi ? min((uint32_t)IBFT_SPLIT_SIGS, shard_hi - base) : 0u;
+#pragma unroll
+    for (int k = 0; k < (IBFT_SPLIT_SIGS * 8) / (32 * (IBFT_SPLIT_CHAINS + 1)); k++) {
+      uint32_t u = tid + k * 32 * (IBFT_SPLIT_CHAINS + 1);
+      uint32_t row = u >> 3, col = u & 7;
+      if (row < avail) {
+        uint4 v = __ldg(src + u);
+        uint32_t* d = s_items + row * IBFT_ITEM_ROW_WORDS + col * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+  }
+  __syncthreads();
+  gtab_view G{g_gtable};
+  G.comb = ctable;
+  if (warp == IBFT_SPLIT_CHAINS) {
+    // ------------------------------------------------------------------ helper warp: lane l serves signature 32p + l of
+    // every chain warp p.  Order of work = order in which the chains need it:
+    //   1a  range checks, ONE scalar inversion for the lane's three signatures (Montgomery's trick), digits of u2 -> posted
+    //       while the chains are still building their tables;
+    //   1b/2 per pass: digest, digits of u1, square root, u1*G comb, affine -> posted long before the chain's loop ends.
+    // Between the steps the lane's per-signature state (r, s, then r^-1) is parked in the result area of the hand-off slot,
+    // which phase 2 overwrites only after reading it -- nothing big is carried in registers across the passes.
+    uint32_t okmask = 0;
+    IBFT_ROLLED
+    for (uint32_t p = 0; p < IBFT_SPLIT_CHAINS; p++) {
+      const uint32_t i = 32 * p + lane, idx = base + i;
+      bool have = false;
+      if (idx < shard_hi) {
+        ibft_sig_item it;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+        const uint32_t* src = s_items + i * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+        for (int k = 0; k < 32; k++) w[k] = src[k];
+        resolved_item ri;
+        resolve_item(it, arena, arena_len, ri, &have, false);
+        have = have && split_sig_in_range(ri);
+        if (have) {
+          sc r = sc_from_be(ri.r), sv = sc_from_be(ri.s);
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            s_slot[(11 + k) * IBFT_SPLIT_SIGS + i] = r.v[k];
+            s_slot[(19 + k) * IBFT_SPLIT_SIGS + i] = sv.v[k];
+          }
+        }
+      }
+      if (have) okmask |= 1u << p;
+    }
+    {
+      // prefix products of the valid r's (an invalid one contributes 1), one inversion, peel backwards
+      sc one;
+#pragma unroll
+      for (int k = 0; k < 8; k++) one.v[k] = k == 0;
+      sc rr[IBFT_SPLIT_CHAINS], pre[IBFT_SPLIT_CHAINS];
+#pragma unroll
+      for (uint32_t p = 0; p < IBFT_SPLIT_CHAINS; p++) {
+        rr[p] = one;
+        if ((okmask >> p) & 1u) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) rr[p].v[k] = s_slot[(11 + k) * IBFT_SPLIT_SIGS + 32 * p + lane];
+        }
+        pre[p] = p ? sc_mul(pre[p - 1], rr[p]) : rr[p];
+      }
+      sc inv = IBFT_SC_INV(pre[IBFT_SPLIT_CHAINS - 1]);
+#pragma unroll
+      for (int p = IBFT_SPLIT_CHAINS - 1; p >= 0; p--) {
+        sc ri = p ? sc_mul(inv, pre[p - 1]) : inv;
+        if (p) inv = sc_mul(inv, rr[p]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_slot[(11 + k) * IBFT_SPLIT_SIGS + 32 * p + lane] = ri.v[k];  // r^-1 replaces r
+      }
+    }
+    IBFT_ROLLED
+    for (uint32_t p = 0; p < IBFT_SPLIT_CHAINS; p++) {
+      const uint32_t i = 32 * p + lane;
+      uint32_t flags = 0;
+      if ((okmask >> p) & 1u) {
+        sc sv, rinv;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          rinv.v[k] = s_slot[(11 + k) * IBFT_SPLIT_SIGS + i];
+          sv.v[k] = s_slot[(19 + k) * IBFT_SPLIT_SIGS + i];
+        }
+        ecmult_digits dg;
+        ecmult_split_into(sc_mul(sv, rinv), dg, 0);
+        flags = IBFT_SF_VALID | (dg.kneg[0] ? IBFT_SF_NEG0 : 0u) | (dg.kneg[1] ? IBFT_SF_NEG1 : 0u);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          s_slot[k * IBFT_SPLIT_SIGS + i] = dg.ks[0][k];
+          s_slot[(5 + k) * IBFT_SPLIT_SIGS + i] = dg.ks[1][k];
+        }
+      }
+      s_slot[10 * IBFT_SPLIT_SIGS + i] = flags;
+      __threadfence_block();
+      named_bar_arrive(1 + p, 64);
+    }
+    IBFT_ROLLED
+    for (uint32_t p = 0; p < IBFT_SPLIT_CHAINS; p++) {
+      const uint32_t i = 32 * p + lane;
+      if ((okmask >> p) & 1u) {
+        uint32_t flags = s_slot[10 * IBFT_SPLIT_SIGS + i];
+        ibft_sig_item it;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+        const uint32_t* src = s_items + i * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+        for (int k = 0; k < 32; k++) w[k] = src[k];
+        resolved_item ri;
+        bool have = false;
+        resolve_item(it, arena, arena_len, ri, &have, true);  // this time with the digest
+        sc rinv;
+#pragma unroll
+        for (int k = 0; k < 8; k++) rinv.v[k] = s_slot[(11 + k) * IBFT_SPLIT_SIGS + i];
+        ecmult_digits dg;
+#pragma unroll
+        for (int k = 0; k < 6; k++) dg.ks[0][k] = dg.ks[1][k] = 0;
+        dg.kneg[0] = dg.kneg[1] = false;
+        split_helper_u1(ri, rinv, dg);
+        fe y, gx, gy;
+        bool g_inf = false;
+        if (split_helper_point(ri, dg, G, y, g_inf, gx, gy)) {
+          flags |= IBFT_SF_ROOT | (g_inf ? IBFT_SF_GINF : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            s_y[k * IBFT_SPLIT_SIGS + i] = y.v[k];
+            if (!g_inf) {
+              s_slot[(11 + k) * IBFT_SPLIT_SIGS + i] = gx.v[k];
+              s_slot[(19 + k) * IBFT_SPLIT_SIGS + i] = gy.v[k];
+            }
+          }
+        }
+        s_slot[10 * IBFT_SPLIT_SIGS + i] = flags;
+      }
+      __threadfence_block();
+      named_bar_arrive(1 + IBFT_SPLIT_CHAINS + p, 64);
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- chain warp
+  const uint32_t i = tid, idx = base + i;  // tid = 32 * warp + lane
+  const bool active = idx < shard_hi;
+  ibft_sig_item it;
+  resolved_item ri;
+  bool have = false;
+  int st = IBFT_ITEM_OK;
+  rtab_view T{s_rtab + i, (uint32_t)IBFT_SPLIT_SIGS};
+  if (active) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+    const uint32_t* src = s_items + i * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+    for (int k = 0; k < 32; k++) w[k] = src[k];
+    st = resolve_item(it, arena, arena_len, ri, &have, false);  // fields only: the chain never needs the digest
+    if (have) ecmult_build_rtable(split_chain_point(ri.r), T);
+  }
+  named_bar_sync(1 + warp, 64);  // the helper has posted the digits of u2
+  jac acc;
+  acc.x = fe_zero(); acc.y = fe_zero(); acc.z = fe_zero();
+  acc.inf = true;
+  bool go = false;
+  if (active && have) {
+    uint32_t flags = s_slot[10 * IBFT_SPLIT_SIGS + i];
+    if (flags & IBFT_SF_VALID) {
+      ecmult_digits dg;
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        dg.ks[0][k] = s_slot[k * IBFT_SPLIT_SIGS + i];
+        dg.ks[1][k] = s_slot[(5 + k) * IBFT_SPLIT_SIGS + i];
+        dg.ks[2][k] = dg.ks[3][k] = 0;
+      }
+      dg.ks[0][5] = dg.ks[1][5] = dg.ks[2][5] = dg.ks[3][5] = 0;
+      dg.kneg[0] = flags & IBFT_SF_NEG0; dg.kneg[1] = flags & IBFT_SF_NEG1;
+      dg.kneg[2] = dg.kneg[3] = false;
+      acc = ecmult_streams(dg, G, T, false);
+      go = true;
+    }
+  }
+  named_bar_sync(1 + IBFT_SPLIT_CHAINS + warp, 64);  // the helper has posted y and u1*G
+  uint8_t addr[20];
+#pragma unroll
+  for (int k = 0; k < 20; k++) addr[k] = 0;
+  bool ok = false;
+  if (go) {
+    uint32_t flags = s_slot[10 * IBFT_SPLIT_SIGS + i];
+    if (flags & IBFT_SF_ROOT) {
+      fe y, gx, gy;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        y.v[k] = s_y[k * IBFT_SPLIT_SIGS + i];
+        gx.v[k] = s_slot[(11 + k) * IBFT_SPLIT_SIGS + i];
+        gy.v[k] = s_slot[(19 + k) * IBFT_SPLIT_SIGS + i];
+      }
+      ok = split_chain_finish(acc, y, (flags & IBFT_SF_GINF) != 0, gx, gy, addr);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 20; k++) ok = ok && (addr[k] == ri.signer[k]);
+    if (ok && groups != nullptr) {
+      if (it.group >= n_groups) {
+        ok = false;
+      } else {
+        uint32_t slot = groups[it.group].table_slot;
+        if (slot != IBFT_NO_TABLE) {
+          if (slot >= n_slots || !slots[slot].valid) ok = false;
+          else ok = lookup_validator(slots[slot], ri.signer) >= 0;
+        }
+      }
+    }
+    if (status != nullptr) status[idx] = (uint8_t)st;
+    if (recovered != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 20; k++) recovered[(size_t)idx * 20 + k] = addr[k];
+    }
+  } else {
+    ok = false;
+  }
+  uint32_t word = __ballot_sync(0xFFFFFFFFu, ok);
+  if (lane == 0 && active) bitmap[idx >> 5] = word;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------------------
 // K3: quorum
 // ------------------------------------------------------------------------------------------------------------
@@ -401,7 +657,7 @@ __global__ void k_keccak_batch(const uint8_t* __restrict__ arena, size_t arena_l
 // ------------------------------------------------------------------------------------------------------------
 #if IBFT_WC > 0
 __global__ void __launch_bounds__(64)
-k_build_ctable(uint32_t* __restrict__ out) {
+k_build_ctable(uint32_t* __restrict__ out) {  // blockIdx.y = comb position: entries scaled by 2^(WC * position)
   __shared__ uint32_t s_gtab[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];
   __shared__ uint32_t s_rtab[64 * IBFT_RTAB_WORDS];
   for (uint32_t i = threadIdx.x; i < IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES; i += 64) s_gtab[i] = g_gtable[i];
@@ -418,7 +674,15 @@ k_build_ctable(uint32_t* __restrict__ out) {
   sc t = sc_mul(b, l);
   if (d2 < 0) t = sc_neg(t);
   sc k = sc_add(a, t);
-  uint32_t* o = out + IBFT_GTAB_ENTRY_WORDS * e;
+  const uint32_t pos = blockIdx.y;
+  if (pos) {
+    sc m;
+#pragma unroll
+    for (int i = 0; i < 8; i++) m.v[i] = 0;
+    m.v[(pos * IBFT_WC) / 32] = 1u << ((pos * IBFT_WC) % 32);
+    k = sc_mul(k, m);
+  }
+  uint32_t* o = out + IBFT_GTAB_ENTRY_WORDS * ((size_t)pos * IBFT_CTAB_ENTRIES + e);
   gtab_view G{s_gtab};
   rtab_view T{s_rtab + threadIdx.x, 64u};
   aff g1;
@@ -720,6 +984,9 @@ static int engine_alloc(ibft_engine* e) {
   CU(cudaMemcpyToSymbol(g_gtable, IBFT_GTABLE, sizeof(uint32_t) * IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES));
   CU(cudaFuncSetAttribute(k_recover<IBFT_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, IBFT_BLOCK * IBFT_RTAB_WORDS * 4));
   CU(cudaFuncSetAttribute(k_recover<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * IBFT_RTAB_WORDS * 4));
+#if IBFT_WC > 0
+  CU(cudaFuncSetAttribute(k_recover_split, cudaFuncAttributeMaxDynamicSharedMemorySize, IBFT_SPLIT_SMEM));
+#endif
   CU(cudaFuncGetAttributes(&e->recover_attr, k_recover<IBFT_BLOCK>));
   {
     cudaDeviceProp prop;
@@ -728,9 +995,11 @@ static int engine_alloc(ibft_engine* e) {
   }
 #if IBFT_WC > 0
   {
+    // position 0 is the combined table of the interleaved window loop; positions 1.. are the comb tables of the split
+    // latency kernel's helper warps (36 MB in all, L2-resident while a round is being verified)
     size_t entries = (size_t)IBFT_CTAB_ENTRIES;
-    CU(cudaMalloc(&e->d_ctable, entries * IBFT_GTAB_ENTRY_WORDS * 4));
-    k_build_ctable<<<(unsigned)((entries + 63) / 64), 64, 0, e->stream>>>(e->d_ctable);
+    CU(cudaMalloc(&e->d_ctable, (size_t)IBFT_CTAB_POSITIONS * entries * IBFT_GTAB_ENTRY_WORDS * 4));
+    k_build_ctable<<<dim3((unsigned)((entries + 63) / 64), IBFT_CTAB_POSITIONS), 64, 0, e->stream>>>(e->d_ctable);
     e->launches++;
     CU(cudaGetLastError());
   }
@@ -933,13 +1202,29 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
                           uint32_t lo, uint32_t hi, const ibft_group_desc* d_groups, uint32_t n_groups, uint32_t* d_bitmap,
                           uint8_t* d_recovered, cudaStream_t st, uint8_t* d_status = nullptr) {
   if (hi <= lo) return IBFT_OK;
-  // path selection (ibft_set_recover_path).  AUTO: a batch that fits ONE four-lane CTA per SM (<= SMs x 32 signatures, one warp
-  // per scheduler: 0.55 ms instead of 0.86 ms on a B200) takes the latency kernel; with more warps per scheduler the
-  // redundant work of the quads costs more than the shorter chain saves (10,000 signatures: 0.99 ms vs 0.86 ms), so larger
-  // batches stay on the one-thread-per-signature kernel -- one-warp CTAs while a single wave covers them, 128-thread CTAs beyond.
+  // path selection (ibft_set_recover_path).  AUTO picks by how many warps each of the SM's four schedulers would hold
+  // (B200, kernel time of one batch: profiles/latency_r01_v8.md):
+  //   <= SMs x 32 signatures   four lanes per signature, one CTA (4 warps) per SM                            0.55 ms
+  //   <= SMs x 96              chain warps + helper warp, one CTA (3 + 1 warps) per SM (10k-validator round)   0.7 ms
+  //   beyond                   one thread per signature: one-warp CTAs while one wave covers them (0.86 ms), then the
+  //                            128-thread throughput kernel
   const uint32_t cnt = hi - lo;
   int path = e->recover_path;
-  if (path == IBFT_PATH_AUTO) path = cnt <= (uint32_t)e->sm_count * IBFT_QUAD_SIGS ? IBFT_PATH_QUAD : IBFT_PATH_THREAD;
+  if (path == IBFT_PATH_AUTO) {
+    if (cnt <= (uint32_t)e->sm_count * IBFT_QUAD_SIGS) path = IBFT_PATH_QUAD;
+#if IBFT_WC > 0
+    else if (cnt <= (uint32_t)e->sm_count * IBFT_SPLIT_SIGS) path = IBFT_PATH_SPLIT;
+#endif
+    else path = IBFT_PATH_THREAD;
+  }
+#if IBFT_WC > 0
+  if (path == IBFT_PATH_SPLIT) {
+    uint32_t blocks = (cnt + IBFT_SPLIT_SIGS - 1) / IBFT_SPLIT_SIGS;
+    k_recover_split<<<blocks, 32 * (IBFT_SPLIT_CHAINS + 1), IBFT_SPLIT_SMEM, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
+                                                                              e->d_slots, e->p.max_table_slots, d_bitmap, d_recovered,
+                                                                              d_status, e->d_ctable);
+  } else
+#endif
   if (path == IBFT_PATH_QUAD) {
     uint32_t blocks = (cnt + IBFT_QUAD_SIGS - 1) / IBFT_QUAD_SIGS;
     k_recover_quad<<<blocks, 4 * IBFT_QUAD_SIGS, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
@@ -1320,7 +1605,7 @@ done:
 }
 
 extern "C" int ibft_set_recover_path(ibft_engine* e, int path) {
-  if (e == nullptr || path < IBFT_PATH_AUTO || path > IBFT_PATH_QUAD) { set_err("bad recover path"); return IBFT_ERR_INVALID_ARG; }
+  if (e == nullptr || path < IBFT_PATH_AUTO || path > IBFT_PATH_SPLIT) { set_err("bad recover path"); return IBFT_ERR_INVALID_ARG; }
   std::lock_guard<std::mutex> g(e->mu);
   e->recover_path = path;
   return IBFT_OK;

@@ -293,6 +293,7 @@ static_assert(IBFT_WG % IBFT_WR == 0, "generator window must be a multiple of th
 #endif
 #define IBFT_CTAB_D2 ((1 << IBFT_WC) + 1)
 #define IBFT_CTAB_ENTRIES (((1 << (IBFT_WC - 1)) + 1) * IBFT_CTAB_D2)
+#define IBFT_CTAB_POSITIONS ((IBFT_NWIN_R * IBFT_WR + IBFT_WC - 1) / IBFT_WC)  // comb positions covering the 132 window bits
 
 // Generator table accessor: entry i (0-based) = (i+1)*G as 16 words x[8] y[8] (shared memory on the device).
 #define IBFT_GTAB_ENTRY_WORDS 16
@@ -307,6 +308,22 @@ struct gtab_view {
     x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w; x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
     y.v[0] = c.x; y.v[1] = c.y; y.v[2] = c.z; y.v[3] = c.w; y.v[4] = d.x; y.v[5] = d.y; y.v[6] = d.z; y.v[7] = d.w;
 #else
+    for (int i = 0; i < 8; i++) { x.v[i] = e[i]; y.v[i] = e[8 + i]; }
+#endif
+  }
+  // entry (d1, d2) of POSITION pos of the per-position comb tables: device = the table itself (positions are contiguous after
+  // the combined table); the host emulation computes the entry through `host_pos` (a 36 MB table is not built there)
+#if !defined(__CUDA_ARCH__)
+  void (*host_pos)(int pos, int d1, int d2, uint32_t* xy16) = nullptr;
+#endif
+  IBFT_HD void load_comb_pos(int pos, int d1, int d2, fe& x, fe& y) const {
+#if defined(__CUDA_ARCH__)
+    gtab_view P = *this;
+    P.comb = comb + (size_t)pos * IBFT_GTAB_ENTRY_WORDS * (size_t)IBFT_CTAB_ENTRIES;
+    P.load_comb(d1, d2, x, y);
+#else
+    uint32_t e[16];
+    host_pos(pos, d1, d2, e);
     for (int i = 0; i < 8; i++) { x.v[i] = e[i]; y.v[i] = e[8 + i]; }
 #endif
   }
@@ -354,66 +371,63 @@ IBFT_HD fe fe_inv_for_table(const fe& a);
 #define IBFT_ROLLED
 #endif
 
-// Returns u1*G + u2*R (R affine, on the curve) as a Jacobian point.  u1, u2 in [0, n).
+// {1..8} * R into T: entry m holds (m+1)R; even multiples by doubling, odd ones by adding R.  The table is then made
+// AFFINE with one shared inversion (Montgomery's trick over the seven Z's), so that every addition of the main loop
+// is a mixed addition (8M+3S instead of 12M+4S) and the loop holds a single adder.
 // Every loop below is deliberately ROLLED and each group-law routine appears exactly once in the instruction stream:
 // the kernel is instruction-cache bound otherwise (see secp_fe.cuh, IBFT_FN).
-IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_view& G, const rtab_view& T) {
-  // digit streams: 0 = u2 half 1 (R), 1 = u2 half 2 (lambda R), 2 = u1 half 1 (G), 3 = u1 half 2 (lambda G)
+IBFT_HD void ecmult_build_rtable(const aff& R, const rtab_view& T) {
+  fe zs[8];  // Z of entry m
+  T.store(0, R.x, R.y);
+  zs[0] = fe_from_u32(1);
+  IBFT_ROLLED
+  for (int m = 1; m < 8; m++) {
+    jac p, t;
+    int src = (m & 1) ? ((m + 1) >> 1) - 1 : m - 1;
+    T.load(src, p.x, p.y);
+    p.z = zs[src]; p.inf = false;
+    if (m & 1) t = jac_double(p);
+    else t = jac_add_affine(p, R.x, R.y);
+    T.store(m, t.x, t.y);
+    zs[m] = t.z;
+  }
+  // prefix products pre[m] = Z_1 * ... * Z_m (Z_0 = 1), one inversion, then peel the inverses off backwards
+  IBFT_STAGE(5);
+  fe pre[8];
+  pre[1] = zs[1];
+  IBFT_ROLLED
+  for (int m = 2; m < 8; m++) pre[m] = fe_mul(pre[m - 1], zs[m]);
+  fe acc_inv = fe_inv_for_table(pre[7]);
+  IBFT_STAGE(6);
+  IBFT_ROLLED
+  for (int m = 7; m >= 1; m--) {
+    fe zi = m > 1 ? fe_mul(acc_inv, pre[m - 1]) : acc_inv;  // 1 / Z_m
+    if (m > 1) acc_inv = fe_mul(acc_inv, zs[m]);
+    fe zi2 = fe_sqr(zi);
+    fe x, y;
+    T.load(m, x, y);
+    T.store(m, fe_mul(x, zi2), fe_mul(y, fe_mul(zi2, zi)));
+  }
+}
+
+// digit streams of one double-scalar multiplication: 0 = u2 half 1 (R), 1 = u2 half 2 (lambda R), 2 = u1 half 1 (G),
+// 3 = u1 half 2 (lambda G); magnitudes < 2^129 in five limbs (+ one zero limb for the Booth window reads), signs apart
+struct ecmult_digits {
   uint32_t ks[4][6];
   bool kneg[4];
-  {
-    glv_half h1, h2;
-    glv_split(u2, h1, h2);
+};
+IBFT_HD void ecmult_split_into(const sc& k, ecmult_digits& d, int first) {
+  glv_half h1, h2;
+  glv_split(k, h1, h2);
 #pragma unroll
-    for (int i = 0; i < 5; i++) { ks[0][i] = h1.k[i]; ks[1][i] = h2.k[i]; }
-    kneg[0] = h1.neg; kneg[1] = h2.neg;
-    glv_split(u1, h1, h2);
-#pragma unroll
-    for (int i = 0; i < 5; i++) { ks[2][i] = h1.k[i]; ks[3][i] = h2.k[i]; }
-    kneg[2] = h1.neg; kneg[3] = h2.neg;
-    ks[0][5] = ks[1][5] = ks[2][5] = ks[3][5] = 0;
-  }
+  for (int i = 0; i < 5; i++) { d.ks[first][i] = h1.k[i]; d.ks[first + 1][i] = h2.k[i]; }
+  d.ks[first][5] = d.ks[first + 1][5] = 0;
+  d.kneg[first] = h1.neg; d.kneg[first + 1] = h2.neg;
+}
 
-  // {1..8} * R: entry m holds (m+1)R; even multiples by doubling, odd ones by adding R.  The table is then made
-  // AFFINE with one shared inversion (Montgomery's trick over the seven Z's), so that every addition of the main loop
-  // is a mixed addition (8M+3S instead of 12M+4S) and the loop holds a single adder.
+// The interleaved window loop over the affine table T (streams 0, 1) and -- when with_g -- the generator table(s).
+IBFT_HD jac ecmult_streams(const ecmult_digits& dg, const gtab_view& G, const rtab_view& T, bool with_g) {
   const fe beta = fe_beta();
-  IBFT_STAGE(4);
-  {
-    fe zs[8];  // Z of entry m
-    T.store(0, R.x, R.y);
-    zs[0] = fe_from_u32(1);
-    IBFT_ROLLED
-    for (int m = 1; m < 8; m++) {
-      jac p, t;
-      int src = (m & 1) ? ((m + 1) >> 1) - 1 : m - 1;
-      T.load(src, p.x, p.y);
-      p.z = zs[src]; p.inf = false;
-      if (m & 1) t = jac_double(p);
-      else t = jac_add_affine(p, R.x, R.y);
-      T.store(m, t.x, t.y);
-      zs[m] = t.z;
-    }
-    // prefix products pre[m] = Z_1 * ... * Z_m (Z_0 = 1), one inversion, then peel the inverses off backwards
-    IBFT_STAGE(5);
-    fe pre[8];
-    pre[1] = zs[1];
-    IBFT_ROLLED
-    for (int m = 2; m < 8; m++) pre[m] = fe_mul(pre[m - 1], zs[m]);
-    fe acc_inv = fe_inv_for_table(pre[7]);
-    IBFT_STAGE(6);
-    IBFT_ROLLED
-    for (int m = 7; m >= 1; m--) {
-      fe zi = m > 1 ? fe_mul(acc_inv, pre[m - 1]) : acc_inv;  // 1 / Z_m
-      if (m > 1) acc_inv = fe_mul(acc_inv, zs[m]);
-      fe zi2 = fe_sqr(zi);
-      fe x, y;
-      T.load(m, x, y);
-      T.store(m, fe_mul(x, zi2), fe_mul(y, fe_mul(zi2, zi)));
-    }
-  }
-
-  IBFT_STAGE(7);
   jac acc;
   acc.x = fe_zero(); acc.y = fe_zero(); acc.z = fe_zero();
   acc.inf = true;
@@ -427,9 +441,9 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
     // table, ONE stream for both generator halves every (WC/WR)-th window
 #if IBFT_WC > 0
     const bool comb = G.comb != nullptr;
-    const int ns = comb ? ((j % (IBFT_WC / IBFT_WR) == 0) ? 3 : 2) : ((j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2);
+    const int ns = !with_g ? 2 : comb ? ((j % (IBFT_WC / IBFT_WR) == 0) ? 3 : 2) : ((j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2);
 #else
-    const int ns = (j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2;
+    const int ns = !with_g ? 2 : (j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2;
 #endif
     IBFT_ROLLED
     for (int s = 0; s < ns; s++) {
@@ -438,9 +452,9 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
 #if IBFT_WC > 0
       if (comb && s == 2) {
         int jg = j / (IBFT_WC / IBFT_WR);
-        int d1 = booth_digit<IBFT_WC>(ks[2], jg), d2 = booth_digit<IBFT_WC>(ks[3], jg);
-        if (kneg[2]) d1 = -d1;
-        if (kneg[3]) d2 = -d2;
+        int d1 = booth_digit<IBFT_WC>(dg.ks[2], jg), d2 = booth_digit<IBFT_WC>(dg.ks[3], jg);
+        if (dg.kneg[2]) d1 = -d1;
+        if (dg.kneg[3]) d2 = -d2;
         if ((d1 | d2) == 0) continue;
         neg = d1 < 0 || (d1 == 0 && d2 < 0);
         if (neg) { d1 = -d1; d2 = -d2; }
@@ -448,13 +462,13 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
       } else
 #endif
       {
-        int d = s < 2 ? booth_digit<IBFT_WR>(ks[s], j) : booth_digit<IBFT_WG>(ks[s], j / (IBFT_WG / IBFT_WR));
+        int d = s < 2 ? booth_digit<IBFT_WR>(dg.ks[s], j) : booth_digit<IBFT_WG>(dg.ks[s], j / (IBFT_WG / IBFT_WR));
         if (d == 0) continue;
         int idx = (d < 0 ? -d : d) - 1;
         if (s < 2) T.load(idx, x, y);
         else G.load(idx, x, y);
         use_beta = (s & 1) != 0;
-        neg = (d < 0) != kneg[s];
+        neg = (d < 0) != dg.kneg[s];
       }
       if (use_beta) x = fe_mul(x, beta);  // lambda * (x, y) = (beta x, y)
       if (neg) y = fe_neg(y);
@@ -463,6 +477,43 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
   }
   return acc;
 }
+
+// Returns u1*G + u2*R (R affine, on the curve) as a Jacobian point.  u1, u2 in [0, n).
+IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_view& G, const rtab_view& T) {
+  ecmult_digits dg;
+  ecmult_split_into(u2, dg, 0);
+  ecmult_split_into(u1, dg, 2);
+  IBFT_STAGE(4);
+  ecmult_build_rtable(R, T);
+  IBFT_STAGE(7);
+  return ecmult_streams(dg, G, T, true);
+}
+
+#if IBFT_WC > 0
+// u1*G alone as a fixed-base COMB over per-position tables (no doublings): position j of the table holds
+// d1 * 2^(WC j) * G + d2 * 2^(WC j) * lambda G for the same (d1, d2) index space as the combined table (position 0 IS the
+// combined table).  Used by the helper warp of the split latency kernel, which adds the result to the chain warp's u2*R.
+// dg.ks[2], dg.ks[3] / kneg[2], kneg[3] must hold the split of u1.
+IBFT_HD jac ecmult_gen_comb(const ecmult_digits& dg, const gtab_view& G) {
+  jac acc;
+  acc.x = fe_zero(); acc.y = fe_zero(); acc.z = fe_zero();
+  acc.inf = true;
+  IBFT_ROLLED
+  for (int jg = IBFT_CTAB_POSITIONS - 1; jg >= 0; jg--) {
+    int d1 = booth_digit<IBFT_WC>(dg.ks[2], jg), d2 = booth_digit<IBFT_WC>(dg.ks[3], jg);
+    if (dg.kneg[2]) d1 = -d1;
+    if (dg.kneg[3]) d2 = -d2;
+    if ((d1 | d2) == 0) continue;
+    bool neg = d1 < 0 || (d1 == 0 && d2 < 0);
+    if (neg) { d1 = -d1; d2 = -d2; }
+    fe x, y;
+    G.load_comb_pos(jg, d1, d2, x, y);
+    if (neg) y = fe_neg(y);
+    acc = jac_add_affine(acc, x, y);
+  }
+  return acc;
+}
+#endif
 
 // The same double-scalar multiplication on the latency path: level-structured XYZZ group law driven by a lane executor
 // (exec_quad on the device; the serial executor in the host emulation).  Same digit streams as ecmult_double; the

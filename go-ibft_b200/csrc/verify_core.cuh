@@ -24,7 +24,8 @@ namespace ibft {
 IBFT_HD fe fe_inv_for_table(const fe& a) { return IBFT_FE_INV(a); }
 
 // digest of one item (kinds of include/ibft_verify.h).  Returns false for an unknown kind / out-of-range payload.
-IBFT_HD bool item_digest(const ibft_sig_item& it, const uint8_t* arena, size_t arena_len, uint8_t* z) {
+// want = false: only the structural checks (the chain warps of the split kernel never need z).
+IBFT_HD bool item_digest(const ibft_sig_item& it, const uint8_t* arena, size_t arena_len, uint8_t* z, bool want = true) {
   switch (it.kind) {
     case IBFT_KIND_DIGEST:
 #pragma unroll
@@ -32,9 +33,10 @@ IBFT_HD bool item_digest(const ibft_sig_item& it, const uint8_t* arena, size_t a
       return true;
     case IBFT_KIND_PAYLOAD:
       if ((size_t)it.payload_off + it.payload_len > arena_len) return false;
-      keccak256_bytes(arena + it.payload_off, it.payload_len, z);
+      if (want) keccak256_bytes(arena + it.payload_off, it.payload_len, z);
       return true;
     case IBFT_KIND_SEAL: {
+      if (!want) return true;
       uint8_t buf[33];
 #pragma unroll
       for (int i = 0; i < 32; i++) buf[i] = it.digest[i];
@@ -168,7 +170,8 @@ struct resolved_item {
   uint8_t r[32], s[32], z[32], signer[20];
   uint8_t v;
 };
-IBFT_HD int resolve_item(const ibft_sig_item& it, const uint8_t* arena, size_t arena_len, resolved_item& o, bool* valid) {
+IBFT_HD int resolve_item(const ibft_sig_item& it, const uint8_t* arena, size_t arena_len, resolved_item& o, bool* valid,
+                         bool want_digest = true) {
   *valid = false;
   if (it.kind == IBFT_KIND_WIRE || it.kind == IBFT_KIND_WIRE_SEAL) {
     if ((size_t)it.payload_off + it.payload_len > arena_len) return IBFT_ITEM_OK;
@@ -184,16 +187,18 @@ IBFT_HD int resolve_item(const ibft_sig_item& it, const uint8_t* arena, size_t a
 #pragma unroll
       for (int i = 0; i < 32; i++) { o.r[i] = w[f.sig_off + i]; o.s[i] = w[f.sig_off + 32 + i]; }
       o.v = w[f.sig_off + 64];
-      keccak256_two_spans(w, f.sig_tag_off, w + f.sig_end, it.payload_len - f.sig_end, o.z);
+      if (want_digest) keccak256_two_spans(w, f.sig_tag_off, w + f.sig_end, it.payload_len - f.sig_end, o.z);
     } else {
       // IsValidCommittedSeal on the frame: ExtractCommitHash needs type == COMMIT and commitData (messages/helpers.go:51-62),
       // the seal is commitData.committedSeal with Signer = From (:38-48)
       if (f.type != 2 || f.payload_field != 7 || f.hash_len != 32 || f.seal_len != 65) return IBFT_ITEM_OK;
-      uint8_t buf[33];
+      if (want_digest) {
+        uint8_t buf[33];
 #pragma unroll
-      for (int i = 0; i < 32; i++) buf[i] = w[f.hash_off + i];
-      buf[32] = 0x02;
-      keccak256_bytes(buf, 33, o.z);
+        for (int i = 0; i < 32; i++) buf[i] = w[f.hash_off + i];
+        buf[32] = 0x02;
+        keccak256_bytes(buf, 33, o.z);
+      }
 #pragma unroll
       for (int i = 0; i < 32; i++) { o.r[i] = w[f.seal_off + i]; o.s[i] = w[f.seal_off + 32 + i]; }
       o.v = w[f.seal_off + 64];
@@ -206,7 +211,7 @@ IBFT_HD int resolve_item(const ibft_sig_item& it, const uint8_t* arena, size_t a
 #pragma unroll
   for (int i = 0; i < 20; i++) o.signer[i] = it.signer[i];
   o.v = it.v;
-  *valid = item_digest(it, arena, arena_len, o.z);
+  *valid = item_digest(it, arena, arena_len, o.z, want_digest);
   return IBFT_ITEM_OK;
 }
 
@@ -305,6 +310,89 @@ IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t
                                const gtab_view& G, const rtab_view& T, uint8_t* addr20) {
   return ecrecover_address_x(exec_serial{}, r_be, s_be, v, z_be, G, T, addr20);
 }
+
+#if IBFT_WC > 0
+// ------------------------------------------------------------------------------------------------------------
+// Split pipeline of the mid-size latency kernel (k_recover_split): one signature's serial chain is cut between a CHAIN warp
+// and a HELPER warp that run on different schedulers of the SM.
+//   helper, phase 1: digest, range checks, r^-1 mod n, u1 = -z/r, u2 = s/r, GLV split of both          -> digits of u2
+//   helper, phase 2: y = sqrt(r^3 + 7) with the parity of v, u1*G as a comb over per-position tables     -> y, affine u1*G
+//   chain:           u2*R WITHOUT knowing y: it works on the isomorphic curve E': Y^2 = X^3 + 7 y^6, where
+//                    phi(R) = (x y^2, y^4) = (x c, c^2) with c = x^3 + 7 needs no square root (the a = 0 group law never
+//                    uses b, and (X, Y) -> (beta X, Y) is the same endomorphism on E'), then maps the Jacobian result
+//                    back with ONE multiplication, (X', Y', Z') -> (X', Y', Z' y), adds u1*G, converts, hashes.
+// The chain warp's critical path loses sqrt, the scalar inversion, the GLV split, the digest and the generator stream.
+// ------------------------------------------------------------------------------------------------------------
+// helper phase 1, in three steps so that the r^-1 of several signatures can share ONE inversion (Montgomery's trick across
+// the helper's passes): range check -> [batched inversion by the caller] -> digits of u2 = s/r -> digits of u1 = -z/r.
+IBFT_HD bool split_sig_in_range(const resolved_item& ri) {
+  sc r = sc_from_be(ri.r), s = sc_from_be(ri.s);
+  if (ri.v > 1) return false;
+  return !(sc_is_zero(r) || sc_is_zero(s) || sc_ge_n(r) || sc_ge_n(s));
+}
+IBFT_HD void split_helper_u2(const resolved_item& ri, const sc& rinv, ecmult_digits& dg) {
+  ecmult_split_into(sc_mul(sc_from_be(ri.s), rinv), dg, 0);
+}
+IBFT_HD void split_helper_u1(const resolved_item& ri, const sc& rinv, ecmult_digits& dg) {
+  sc z = sc_reduce_once(sc_from_be(ri.z));
+  ecmult_split_into(sc_neg(sc_mul(z, rinv)), dg, 2);
+}
+// all of phase 1 for one signature (host emulation).  Returns false when (r, s, v) is out of range (verdict 0).
+IBFT_HD bool split_helper_scalars(const resolved_item& ri, ecmult_digits& dg) {
+  if (!split_sig_in_range(ri)) return false;
+  sc rinv = IBFT_SC_INV(sc_from_be(ri.r));
+  split_helper_u2(ri, rinv, dg);
+  split_helper_u1(ri, rinv, dg);
+  return true;
+}
+// helper phase 2.  Returns false when r is not an abscissa of the curve.  g_inf: u1*G is the point at infinity (u1 = 0).
+IBFT_HD bool split_helper_point(const resolved_item& ri, const ecmult_digits& dg, const gtab_view& G, fe& y, bool& g_inf, fe& gx,
+                                fe& gy) {
+  sc r = sc_from_be(ri.r);
+  fe x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x.v[i] = r.v[i];
+  fe y2 = fe_add(fe_mul(fe_sqr(x), x), fe_from_u32(7));
+  y = fe_sqrt_candidate(y2);
+  if (!fe_equal(fe_sqr(y), y2)) return false;
+  y = fe_normalize(y);
+  if ((y.v[0] & 1u) != (uint32_t)ri.v) y = fe_normalize(fe_neg(y));
+  jac P = ecmult_gen_comb(dg, G);
+  g_inf = P.inf || fe_is_zero(P.z);
+  if (!g_inf) {
+    fe zi = IBFT_FE_INV(P.z), zi2 = fe_sqr(zi);
+    gx = fe_mul(P.x, zi2);
+    gy = fe_mul(P.y, fe_mul(zi2, zi));
+  }
+  return true;
+}
+// chain: phi(R) on E' from the abscissa alone
+IBFT_HD aff split_chain_point(const uint8_t* r_be) {
+  sc r = sc_from_be(r_be);
+  fe x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x.v[i] = r.v[i];
+  fe c = fe_add(fe_mul(fe_sqr(x), x), fe_from_u32(7));
+  aff Rp;
+  Rp.x = fe_mul(x, c);
+  Rp.y = fe_sqr(c);
+  return Rp;
+}
+// chain: map acc (= u2 * phi(R) on E') back, add u1*G, derive the address.  false = point at infinity.
+IBFT_HD bool split_chain_finish(jac acc, const fe& y, bool g_inf, const fe& gx, const fe& gy, uint8_t* addr20) {
+#pragma unroll
+  for (int i = 0; i < 20; i++) addr20[i] = 0;
+  if (!acc.inf) acc.z = fe_mul(acc.z, y);
+  if (!g_inf) acc = jac_add_affine(acc, gx, gy);
+  if (acc.inf || fe_is_zero(acc.z)) return false;
+  fe zi = IBFT_FE_INV(acc.z);
+  fe zi2 = fe_sqr(zi);
+  fe qx = fe_normalize(fe_mul(acc.x, zi2));
+  fe qy = fe_normalize(fe_mul(acc.y, fe_mul(zi2, zi)));
+  keccak256_xy_address(qx, qy, addr20);
+  return true;
+}
+#endif
 
 // ECDSA signing with a given nonce (the MessageConstructor side: reference core/backend.go:12-34 requires every built
 // message to be signed and BuildCommitMessage to create a committed seal).  sig65 = R||S||V, s normalised to the low half.

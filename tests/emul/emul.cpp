@@ -11,6 +11,9 @@
 #include "../../go-ibft_b200/csrc/secp_gtable.inc"
 
 #include <cstdio>
+#include <array>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -120,6 +123,70 @@ int emul_ecmult_levels(const uint8_t* a, const uint8_t* b, const uint8_t* c, uin
   fe_to_be(qy, out + 32);
   return 0;
 }
+
+#if IBFT_WC > 0
+// per-position comb entries computed on demand (the device holds a 36 MB table): (d1 + d2 lambda) 2^(WC pos) G
+static void emul_pos_entry(int pos, int d1, int d2, uint32_t* xy16) {
+  static std::mutex mu;
+  static std::map<uint64_t, std::array<uint32_t, 16>> cache;
+  uint64_t key = ((uint64_t)pos << 40) | ((uint64_t)d1 << 20) | (uint64_t)(d2 + 4096);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { memcpy(xy16, it->second.data(), 64); return; }
+  }
+  const uint32_t lam[8] = {0x1B23BD72u, 0xDF02967Cu, 0x20816678u, 0x122E22EAu, 0x8812645Au, 0xA5261C02u, 0xC05C30E0u, 0x5363AD4Cu};
+  sc a, b, l, m, zero;
+  for (int i = 0; i < 8; i++) { a.v[i] = 0; b.v[i] = 0; l.v[i] = lam[i]; m.v[i] = 0; zero.v[i] = 0; }
+  a.v[0] = (uint32_t)d1;
+  b.v[0] = (uint32_t)(d2 < 0 ? -d2 : d2);
+  m.v[(pos * IBFT_WC) / 32] = 1u << ((pos * IBFT_WC) % 32);
+  sc t = sc_mul(b, l);
+  if (d2 < 0) t = sc_neg(t);
+  sc k = sc_mul(sc_add(a, t), m);
+  gtab_view G = emul_gview();
+  uint32_t rtab[IBFT_RTAB_WORDS];
+  rtab_view T{rtab, 1};
+  aff g1;
+  G.load(0, g1.x, g1.y);
+  jac P = ecmult_double(k, zero, g1, G, T);
+  std::array<uint32_t, 16> e{};
+  if (!(P.inf || fe_is_zero(P.z))) {
+    fe zi = IBFT_FE_INV(P.z), zi2 = fe_sqr(zi);
+    fe x = fe_normalize(fe_mul(P.x, zi2)), y = fe_normalize(fe_mul(P.y, fe_mul(zi2, zi)));
+    for (int i = 0; i < 8; i++) { e[i] = x.v[i]; e[8 + i] = y.v[i]; }
+  }
+  memcpy(xy16, e.data(), 64);
+  std::lock_guard<std::mutex> g(mu);
+  cache[key] = e;
+}
+
+// the same item through the SPLIT pipeline of k_recover_split (helper / chain phases run one after the other)
+int emul_verify_item_split(const ibft_sig_item* it, const uint8_t* arena, size_t arena_len, uint8_t* recovered20) {
+  uint8_t addr[20];
+  memset(recovered20, 0, 20);
+  resolved_item ri;
+  bool valid = false;
+  int st = resolve_item(*it, arena, arena_len, ri, &valid);
+  if (st != IBFT_ITEM_OK) return -1;
+  if (!valid) return 0;
+  gtab_view G = emul_gview();
+  G.host_pos = emul_pos_entry;
+  uint32_t rtab[IBFT_RTAB_WORDS];
+  rtab_view T{rtab, 1};
+  ecmult_digits dg;
+  if (!split_helper_scalars(ri, dg)) return 0;             // helper phase 1
+  aff Rp = split_chain_point(ri.r);                        // chain: table + R streams on E'
+  ecmult_build_rtable(Rp, T);
+  jac acc = ecmult_streams(dg, G, T, false);
+  fe y, gx, gy;
+  bool g_inf = false;
+  if (!split_helper_point(ri, dg, G, y, g_inf, gx, gy)) return 0;  // helper phase 2
+  if (!split_chain_finish(acc, y, g_inf, gx, gy, addr)) return 0;   // chain: map back, + u1 G, address
+  memcpy(recovered20, addr, 20);
+  return memcmp(addr, ri.signer, 20) == 0;
+}
+#endif
 
 void emul_keccak256(const uint8_t* d, uint32_t n, uint8_t* out) { keccak256_bytes(d, n, out); }
 

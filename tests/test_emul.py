@@ -248,3 +248,51 @@ def test_level_structured_recover_config2(emul):
         r1 = emul.emul_verify_item(it.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(arena)), o1)
         r2 = emul.emul_verify_item_levels(it.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(arena)), o2)
         assert (r1, bytes(o1)) == (r2, bytes(o2)), i
+
+
+# ------------------------------------------------------------------ split pipeline (helper / chain warps of k_recover_split)
+def both_paths(E, it, arena_np, arena_len):
+    o1, o2 = (ctypes.c_uint8 * 20)(), (ctypes.c_uint8 * 20)()
+    r1 = E.emul_verify_item(it.ctypes.data_as(ctypes.c_void_p), arena_np.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arena_len), o1)
+    r2 = E.emul_verify_item_split(it.ctypes.data_as(ctypes.c_void_p), arena_np.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arena_len), o2)
+    return (r1, bytes(o1)), (r2, bytes(o2))
+
+
+def test_split_pipeline_isomorphic_curve_and_comb(emul):
+    """k_recover_split's arithmetic: u2*R on the isomorphic curve E' (no square root on the chain), u1*G as a per-position comb,
+    map back with Z' * y.  Must give the very same verdict and recovered address as the one-thread pipeline."""
+    import workloads as wl
+    rnd = random.Random(21)
+    zero = np.zeros(1, np.uint8)
+    for i in range(40):
+        d = rnd.getrandbits(256) % (N - 1) + 1
+        dig = keccak256(bytes([i, 7]))
+        sig = wl.sign(d, dig, low_s=bool(i & 1))
+        addr = co.ecrecover_address(dig, sig)
+        a, b = both_paths(emul, wl.make_item(sig, addr, 0, dig), zero, 0)
+        assert a == b == (1, addr)
+        bad = bytearray(sig)
+        bad[rnd.randrange(65)] ^= 1 << rnd.randrange(8)
+        a, b = both_paths(emul, wl.make_item(bytes(bad), addr, 0, dig), zero, 0)
+        assert a == b
+    # z = 0 (u1 = 0: the generator part is the point at infinity) and high-s / v = 1 variants
+    d = 0xC0FFEE
+    sig = wl.sign(d, bytes(32))
+    addr = co.ecrecover_address(bytes(32), sig)
+    a, b = both_paths(emul, wl.make_item(sig, addr, 0, bytes(32)), zero, 0)
+    assert a == b == (1, addr)
+    # r that is not an abscissa, r = 0, s = 0, r >= n, v = 2
+    for r, s, v in [(5, 1, 0), (0, 1, 0), (1, 0, 0), (N, 1, 0), (1, N, 1), (ec.G[0], 1, 2), (ec.G[0], 1, 0), (ec.G[0], N - 1, 1)]:
+        sg = r.to_bytes(32, "big") + s.to_bytes(32, "big") + bytes([v])
+        a, b = both_paths(emul, wl.make_item(sg, bytes(20), 0, keccak256(b"x")), zero, 0)
+        assert a == b, (r, s, v)
+
+
+def test_split_pipeline_config2_fixture(emul):
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "config2.npz"))
+    items = np.ascontiguousarray(d["items"]).view(co.ITEM_DTYPE).reshape(-1)
+    arena = d["arena"].tobytes()
+    a_np = np.frombuffer(arena, np.uint8)
+    for i in range(0, len(items), 5):
+        a, b = both_paths(emul, items[i:i + 1], a_np, len(arena))
+        assert a == b, i

@@ -25,7 +25,7 @@ int main(int argc, char** argv) {
   uint8_t dummy = 0;
   static const char* names[] = {"digest(keccak)+checks", "sqrt / lift_x", "r^-1, u1, u2", "glv split", "table build (7 group ops)",
                                 "table inversion", "table normalise", "main loop", "final inversion + affine", "keccak(address)"};
-  for (int path = IBFT_PATH_THREAD; path <= IBFT_PATH_QUAD; path++) {
+  for (int path = IBFT_PATH_THREAD; path <= IBFT_PATH_QUAD; path++) {  // (the split kernel has no single-thread chain to stamp)
     ibft_set_recover_path(e, path);
     for (int rep = 0; rep < 3; rep++)
       if (ibft_verify_batch(e, items.data(), n, &dummy, 0, nullptr, 0, bm.data(), nullptr, nullptr) != IBFT_OK) {
