@@ -354,8 +354,8 @@ def main():
         if i >= 5:
             lat_dev.append(a.elapsed_time(b) * 1e3)
     lat_dev.sort()
-    # the same measurement for a 4,096-seal round: small enough for the four-lanes-per-signature kernel (AUTO path selection)
-    small = np.ascontiguousarray(seals[:4096])
+    # the same measurement for a 1,000-seal round (AUTO path selection: four-lane chain warps + helper warp, k_recover_qsplit)
+    small = np.ascontiguousarray(seals[:1000])
     lat_small, lat_small_dev = [], []
     for i in range(args.latency_reps + 5):
         t0 = time.perf_counter()
@@ -424,7 +424,8 @@ def main():
         "quorum_latency_us": {"config": "10k-validator COMMIT round, 10,000 committed seals, host tuples -> bitmap+quorum on host",
                               "reps": len(lat), "p50": lat[len(lat) // 2], "p95": lat[int(len(lat) * 0.95)],
                               "device_only_p50": lat_dev[len(lat_dev) // 2], "device_only_p95": lat_dev[int(len(lat_dev) * 0.95)],
-                              "round_4096_seals": {"kernel": "k_recover_quad (four lanes per signature)", "p50": lat_small[len(lat_small) // 2],
+                              "kernel": "k_recover_split (chain warps + helper warp; AUTO path for 7,105..14,208 signatures)",
+                              "round_1000_seals": {"kernel": "k_recover_qsplit (four-lane chain warps + helper warp; AUTO path up to 7,104 signatures)", "p50": lat_small[len(lat_small) // 2],
                                                    "p95": lat_small[int(len(lat_small) * 0.95)],
                                                    "device_only_p50": lat_small_dev[len(lat_small_dev) // 2]}},
     }

@@ -514,6 +514,190 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
 }
 #endif
 
+#if IBFT_WC > 0
+// ------------------------------------------------------------------------------------------------------------
+// K1 + K2, small-round latency variant: the two ideas above combined.  CTA = 3 four-lane CHAIN warps (8 signatures each)
+// + 1 HELPER warp (one lane per signature, a single pass over the CTA's 24), one CTA per SM, one warp per scheduler.
+// The quads walk only u2*phi(R) (XYZZ levels, projective table, no square root, no inversion before the final one);
+// the helper supplies the digits of u2 early and y, u1*G later.  Verdict bits are OR-ed into a pre-zeroed bitmap
+// (24 signatures per CTA do not align with the 32-bit words).  Capacity of one wave: SMs x 24 signatures.
+// ------------------------------------------------------------------------------------------------------------
+#define IBFT_QSPLIT_SIGS 24
+__global__ void __launch_bounds__(128, 1)
+k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
+                 uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
+                 const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
+                 uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable) {
+  __shared__ uint32_t s_items[IBFT_QSPLIT_SIGS * IBFT_ITEM_ROW_WORDS];
+  __shared__ uint32_t s_qtab[IBFT_QSPLIT_SIGS * IBFT_QTAB_WORDS];
+  __shared__ uint32_t s_slot[IBFT_QSPLIT_SIGS * IBFT_SLOT_WORDS];
+  __shared__ uint32_t s_y[IBFT_QSPLIT_SIGS * 8];
+  __shared__ uint4 s_xb[4 * 128];
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint32_t base = shard_lo + blockIdx.x * IBFT_QSPLIT_SIGS;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(items + base);
+    uint32_t avail = base < shard_hi ? min((uint32_t)IBFT_QSPLIT_SIGS, shard_hi - base) : 0u;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      uint32_t u = tid + k * 128;
+      uint32_t row = u >> 3, col = u & 7;
+      if (row < avail) {
+        uint4 v = __ldg(src + u);
+        uint32_t* d = s_items + row * IBFT_ITEM_ROW_WORDS + col * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+  }
+  __syncthreads();
+  gtab_view G{g_gtable};
+  G.comb = ctable;
+  const uint32_t S = IBFT_QSPLIT_SIGS;
+  if (warp == 3) {
+    // ---------------------------------------------------------------- helper warp: lane l serves signature l (l < 24)
+    const uint32_t i = lane, idx = base + i;
+    const bool mine = lane < S && idx < shard_hi;
+    ibft_sig_item it;
+    resolved_item ri;
+    sc rinv;
+    uint32_t flags = 0;
+    if (mine) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+      const uint32_t* src = s_items + i * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+      for (int k = 0; k < 32; k++) w[k] = src[k];
+      bool have = false;
+      resolve_item(it, arena, arena_len, ri, &have, false);
+      if (have && split_sig_in_range(ri)) {
+        rinv = IBFT_SC_INV(sc_from_be(ri.r));
+        ecmult_digits dg;
+        split_helper_u2(ri, rinv, dg);
+        flags = IBFT_SF_VALID | (dg.kneg[0] ? IBFT_SF_NEG0 : 0u) | (dg.kneg[1] ? IBFT_SF_NEG1 : 0u);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          s_slot[k * S + i] = dg.ks[0][k];
+          s_slot[(5 + k) * S + i] = dg.ks[1][k];
+        }
+      }
+    }
+    if (lane < S) s_slot[10 * S + i] = flags;
+    __threadfence_block();
+    named_bar_arrive(1, 64); named_bar_arrive(2, 64); named_bar_arrive(3, 64);
+    if (flags & IBFT_SF_VALID) {
+      bool have = false;
+      resolve_item(it, arena, arena_len, ri, &have, true);  // with the digest
+      ecmult_digits dg;
+#pragma unroll
+      for (int k = 0; k < 6; k++) dg.ks[0][k] = dg.ks[1][k] = 0;
+      dg.kneg[0] = dg.kneg[1] = false;
+      split_helper_u1(ri, rinv, dg);
+      fe y, gx, gy;
+      bool g_inf = false;
+      if (split_helper_point(ri, dg, G, y, g_inf, gx, gy)) {
+        flags |= IBFT_SF_ROOT | (g_inf ? IBFT_SF_GINF : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          s_y[k * S + i] = y.v[k];
+          if (!g_inf) {
+            s_slot[(11 + k) * S + i] = gx.v[k];
+            s_slot[(19 + k) * S + i] = gy.v[k];
+          }
+        }
+      }
+      s_slot[10 * S + i] = flags;
+    }
+    __threadfence_block();
+    named_bar_arrive(4, 64); named_bar_arrive(5, 64); named_bar_arrive(6, 64);
+    return;
+  }
+  // ------------------------------------------------------------------ chain warps: four lanes per signature
+  const uint32_t q = tid >> 2, idx = base + q;
+  const bool active = idx < shard_hi;
+  exec_quad ex;
+  ex.role = (int)(tid & 3u);
+  ex.mask = 0xFu << (tid & 28u);
+  ex.xb = s_xb;
+  ex.par = 0;
+  ibft_sig_item it;
+  resolved_item ri;
+  bool have = false;
+  int st = IBFT_ITEM_OK;
+  fe c = fe_zero();
+  qtab_view T{s_qtab + q, S};
+  if (active) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+    const uint32_t* src = s_items + q * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+    for (int k = 0; k < 32; k++) w[k] = src[k];
+    st = resolve_item(it, arena, arena_len, ri, &have, false);
+    if (have) ecmult_build_qtable(ex, split_chain_point(ri.r, &c), T);
+  }
+  named_bar_sync(1 + warp, 64);
+  xyzz acc;
+  acc.x = fe_zero(); acc.y = fe_zero(); acc.zz = fe_zero(); acc.zzz = fe_zero();
+  acc.inf = true;
+  bool go = false;
+  if (active && have) {
+    uint32_t flags = s_slot[10 * S + q];
+    if (flags & IBFT_SF_VALID) {
+      ecmult_digits dg;
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        dg.ks[0][k] = s_slot[k * S + q];
+        dg.ks[1][k] = s_slot[(5 + k) * S + q];
+        dg.ks[2][k] = dg.ks[3][k] = 0;
+      }
+      dg.ks[0][5] = dg.ks[1][5] = dg.ks[2][5] = dg.ks[3][5] = 0;
+      dg.kneg[0] = flags & IBFT_SF_NEG0; dg.kneg[1] = flags & IBFT_SF_NEG1;
+      dg.kneg[2] = dg.kneg[3] = false;
+      acc = ecmult_streams_x(ex, dg, G, T, false);
+      go = true;
+    }
+  }
+  named_bar_sync(4 + warp, 64);
+  uint8_t addr[20];
+#pragma unroll
+  for (int k = 0; k < 20; k++) addr[k] = 0;
+  bool ok = false;
+  if (go) {
+    uint32_t flags = s_slot[10 * S + q];
+    if (flags & IBFT_SF_ROOT) {
+      fe y, gx, gy;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        y.v[k] = s_y[k * S + q];
+        gx.v[k] = s_slot[(11 + k) * S + q];
+        gy.v[k] = s_slot[(19 + k) * S + q];
+      }
+      ok = split_chain_finish_x(ex, acc, c, y, (flags & IBFT_SF_GINF) != 0, gx, gy, addr);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 20; k++) ok = ok && (addr[k] == ri.signer[k]);
+    if (ok && groups != nullptr) {
+      if (it.group >= n_groups) {
+        ok = false;
+      } else {
+        uint32_t slot = groups[it.group].table_slot;
+        if (slot != IBFT_NO_TABLE) {
+          if (slot >= n_slots || !slots[slot].valid) ok = false;
+          else ok = lookup_validator(slots[slot], ri.signer) >= 0;
+        }
+      }
+    }
+    if (ex.leader()) {
+      if (status != nullptr) status[idx] = (uint8_t)st;
+      if (recovered != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 20; k++) recovered[(size_t)idx * 20 + k] = addr[k];
+      }
+      if (ok) atomicOr(&bitmap[idx >> 5], 1u << (idx & 31u));
+    }
+  }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------------------
 // K3: quorum
 // ------------------------------------------------------------------------------------------------------------
@@ -1203,22 +1387,30 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
                           uint8_t* d_recovered, cudaStream_t st, uint8_t* d_status = nullptr) {
   if (hi <= lo) return IBFT_OK;
   // path selection (ibft_set_recover_path).  AUTO picks by how many warps each of the SM's four schedulers would hold
-  // (B200, kernel time of one batch: profiles/latency_r01_v8.md):
-  //   <= SMs x 32 signatures   four lanes per signature, one CTA (4 warps) per SM                            0.55 ms
-  //   <= SMs x 96              chain warps + helper warp, one CTA (3 + 1 warps) per SM (10k-validator round)   0.7 ms
+  // (B200, kernel time of one batch: profiles/latency_r01_v9.md):
+  //   <= SMs x 24 signatures   four-lane chain warps + helper warp, one CTA (3 + 1 warps) per SM                   0.41 ms
+  //   <= SMs x 48              the same, two CTAs per SM (two warps per scheduler)                                  0.51 ms
+  //   <= SMs x 96              chain warps + helper warp, one CTA (3 + 1 warps) per SM (a 10k-validator round)      0.68 ms
   //   beyond                   one thread per signature: one-warp CTAs while one wave covers them (0.86 ms), then the
   //                            128-thread throughput kernel
   const uint32_t cnt = hi - lo;
   int path = e->recover_path;
   if (path == IBFT_PATH_AUTO) {
-    if (cnt <= (uint32_t)e->sm_count * IBFT_QUAD_SIGS) path = IBFT_PATH_QUAD;
 #if IBFT_WC > 0
+    if (cnt <= (uint32_t)e->sm_count * 2u * IBFT_QSPLIT_SIGS) path = IBFT_PATH_QSPLIT;
     else if (cnt <= (uint32_t)e->sm_count * IBFT_SPLIT_SIGS) path = IBFT_PATH_SPLIT;
-#endif
     else path = IBFT_PATH_THREAD;
+#else
+    path = cnt <= (uint32_t)e->sm_count * IBFT_QUAD_SIGS ? IBFT_PATH_QUAD : IBFT_PATH_THREAD;
+#endif
   }
 #if IBFT_WC > 0
-  if (path == IBFT_PATH_SPLIT) {
+  if (path == IBFT_PATH_QSPLIT) {
+    uint32_t blocks = (cnt + IBFT_QSPLIT_SIGS - 1) / IBFT_QSPLIT_SIGS;
+    CU(cudaMemsetAsync(d_bitmap + (lo >> 5), 0, (size_t)((hi + 31) / 32 - (lo >> 5)) * 4, st));  // verdict bits are OR-ed in
+    k_recover_qsplit<<<blocks, 128, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+                                             e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
+  } else if (path == IBFT_PATH_SPLIT) {
     uint32_t blocks = (cnt + IBFT_SPLIT_SIGS - 1) / IBFT_SPLIT_SIGS;
     k_recover_split<<<blocks, 32 * (IBFT_SPLIT_CHAINS + 1), IBFT_SPLIT_SMEM, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
                                                                               e->d_slots, e->p.max_table_slots, d_bitmap, d_recovered,
@@ -1605,7 +1797,7 @@ done:
 }
 
 extern "C" int ibft_set_recover_path(ibft_engine* e, int path) {
-  if (e == nullptr || path < IBFT_PATH_AUTO || path > IBFT_PATH_SPLIT) { set_err("bad recover path"); return IBFT_ERR_INVALID_ARG; }
+  if (e == nullptr || path < IBFT_PATH_AUTO || path > IBFT_PATH_QSPLIT) { set_err("bad recover path"); return IBFT_ERR_INVALID_ARG; }
   std::lock_guard<std::mutex> g(e->mu);
   e->recover_path = path;
   return IBFT_OK;

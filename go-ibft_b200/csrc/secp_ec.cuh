@@ -519,41 +519,26 @@ IBFT_HD jac ecmult_gen_comb(const ecmult_digits& dg, const gtab_view& G) {
 // (exec_quad on the device; the serial executor in the host emulation).  Same digit streams as ecmult_double; the
 // per-signature table stays projective.  Table writes are done by the quad's leader lane, with a quad-level sync around them.
 template <class EX>
-IBFT_HD xyzz ecmult_double_x(const EX& ex, const sc& u1, const sc& u2, const aff& R, const gtab_view& G, const qtab_view& T) {
-  uint32_t ks[4][6];
-  bool kneg[4];
-  {
-    glv_half h1, h2;
-    glv_split(u2, h1, h2);
-#pragma unroll
-    for (int i = 0; i < 5; i++) { ks[0][i] = h1.k[i]; ks[1][i] = h2.k[i]; }
-    kneg[0] = h1.neg; kneg[1] = h2.neg;
-    glv_split(u1, h1, h2);
-#pragma unroll
-    for (int i = 0; i < 5; i++) { ks[2][i] = h1.k[i]; ks[3][i] = h2.k[i]; }
-    kneg[2] = h1.neg; kneg[3] = h2.neg;
-    ks[0][5] = ks[1][5] = ks[2][5] = ks[3][5] = 0;
+IBFT_HD void ecmult_build_qtable(const EX& ex, const aff& R, const qtab_view& T) {
+  const fe one = fe_from_u32(1);
+  xyzz e0;
+  e0.x = R.x; e0.y = R.y; e0.zz = one; e0.zzz = one; e0.inf = false;
+  if (ex.leader()) T.store(0, e0);
+  ex.sync();
+  IBFT_ROLLED
+  for (int m = 1; m < 8; m++) {
+    int src = (m & 1) ? ((m + 1) >> 1) - 1 : m - 1;
+    xyzz p = T.load(src);
+    xyzz t = (m & 1) ? xyzz_double_x(ex, p) : xyzz_add_x(ex, p, e0);
+    if (ex.leader()) T.store(m, t);
+    ex.sync();
   }
+}
+
+template <class EX>
+IBFT_HD xyzz ecmult_streams_x(const EX& ex, const ecmult_digits& dg, const gtab_view& G, const qtab_view& T, bool with_g) {
   const fe beta = fe_beta();
   const fe one = fe_from_u32(1);
-  IBFT_STAGE(4);
-  {
-    xyzz e0;
-    e0.x = R.x; e0.y = R.y; e0.zz = one; e0.zzz = one; e0.inf = false;
-    if (ex.leader()) T.store(0, e0);
-    ex.sync();
-    IBFT_ROLLED
-    for (int m = 1; m < 8; m++) {
-      int src = (m & 1) ? ((m + 1) >> 1) - 1 : m - 1;
-      xyzz p = T.load(src);
-      xyzz t = (m & 1) ? xyzz_double_x(ex, p) : xyzz_add_x(ex, p, e0);
-      if (ex.leader()) T.store(m, t);
-      ex.sync();
-    }
-  }
-  IBFT_STAGE(5);
-  IBFT_STAGE(6);
-  IBFT_STAGE(7);
   xyzz acc;
   acc.x = fe_zero(); acc.y = fe_zero(); acc.zz = fe_zero(); acc.zzz = fe_zero();
   acc.inf = true;
@@ -565,9 +550,9 @@ IBFT_HD xyzz ecmult_double_x(const EX& ex, const sc& u1, const sc& u2, const aff
     }
 #if IBFT_WC > 0
     const bool comb = G.comb != nullptr;
-    const int ns = comb ? ((j % (IBFT_WC / IBFT_WR) == 0) ? 3 : 2) : ((j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2);
+    const int ns = !with_g ? 2 : comb ? ((j % (IBFT_WC / IBFT_WR) == 0) ? 3 : 2) : ((j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2);
 #else
-    const int ns = (j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2;
+    const int ns = !with_g ? 2 : (j % (IBFT_WG / IBFT_WR) == 0) ? 4 : 2;
 #endif
     IBFT_ROLLED
     for (int s = 0; s < ns; s++) {
@@ -576,9 +561,9 @@ IBFT_HD xyzz ecmult_double_x(const EX& ex, const sc& u1, const sc& u2, const aff
 #if IBFT_WC > 0
       if (comb && s == 2) {
         int jg = j / (IBFT_WC / IBFT_WR);
-        int d1 = booth_digit<IBFT_WC>(ks[2], jg), d2 = booth_digit<IBFT_WC>(ks[3], jg);
-        if (kneg[2]) d1 = -d1;
-        if (kneg[3]) d2 = -d2;
+        int d1 = booth_digit<IBFT_WC>(dg.ks[2], jg), d2 = booth_digit<IBFT_WC>(dg.ks[3], jg);
+        if (dg.kneg[2]) d1 = -d1;
+        if (dg.kneg[3]) d2 = -d2;
         if ((d1 | d2) == 0) continue;
         neg = d1 < 0 || (d1 == 0 && d2 < 0);
         if (neg) { d1 = -d1; d2 = -d2; }
@@ -587,7 +572,7 @@ IBFT_HD xyzz ecmult_double_x(const EX& ex, const sc& u1, const sc& u2, const aff
       } else
 #endif
       {
-        int d = s < 2 ? booth_digit<IBFT_WR>(ks[s], j) : booth_digit<IBFT_WG>(ks[s], j / (IBFT_WG / IBFT_WR));
+        int d = s < 2 ? booth_digit<IBFT_WR>(dg.ks[s], j) : booth_digit<IBFT_WG>(dg.ks[s], j / (IBFT_WG / IBFT_WR));
         if (d == 0) continue;
         int idx = (d < 0 ? -d : d) - 1;
         if (s < 2) {
@@ -597,7 +582,7 @@ IBFT_HD xyzz ecmult_double_x(const EX& ex, const sc& u1, const sc& u2, const aff
           q.zz = one; q.zzz = one; q.inf = false;
         }
         use_beta = (s & 1) != 0;
-        neg = (d < 0) != kneg[s];
+        neg = (d < 0) != dg.kneg[s];
       }
       if (use_beta) q.x = fe_mul(q.x, beta);  // lambda * (x, y) = (beta x, y)
       if (neg) q.y = fe_neg(q.y);
@@ -605,6 +590,19 @@ IBFT_HD xyzz ecmult_double_x(const EX& ex, const sc& u1, const sc& u2, const aff
     }
   }
   return acc;
+}
+
+template <class EX>
+IBFT_HD xyzz ecmult_double_x(const EX& ex, const sc& u1, const sc& u2, const aff& R, const gtab_view& G, const qtab_view& T) {
+  ecmult_digits dg;
+  ecmult_split_into(u2, dg, 0);
+  ecmult_split_into(u1, dg, 2);
+  IBFT_STAGE(4);
+  ecmult_build_qtable(ex, R, T);
+  IBFT_STAGE(5);
+  IBFT_STAGE(6);
+  IBFT_STAGE(7);
+  return ecmult_streams_x(ex, dg, G, T, true);
 }
 
 }  // namespace ibft

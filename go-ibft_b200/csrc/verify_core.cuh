@@ -366,8 +366,8 @@ IBFT_HD bool split_helper_point(const resolved_item& ri, const ecmult_digits& dg
   }
   return true;
 }
-// chain: phi(R) on E' from the abscissa alone
-IBFT_HD aff split_chain_point(const uint8_t* r_be) {
+// chain: phi(R) on E' from the abscissa alone; c = x^3 + 7 = y^2
+IBFT_HD aff split_chain_point(const uint8_t* r_be, fe* c_out = nullptr) {
   sc r = sc_from_be(r_be);
   fe x;
 #pragma unroll
@@ -376,6 +376,7 @@ IBFT_HD aff split_chain_point(const uint8_t* r_be) {
   aff Rp;
   Rp.x = fe_mul(x, c);
   Rp.y = fe_sqr(c);
+  if (c_out) *c_out = c;
   return Rp;
 }
 // chain: map acc (= u2 * phi(R) on E') back, add u1*G, derive the address.  false = point at infinity.
@@ -389,6 +390,34 @@ IBFT_HD bool split_chain_finish(jac acc, const fe& y, bool g_inf, const fe& gx, 
   fe zi2 = fe_sqr(zi);
   fe qx = fe_normalize(fe_mul(acc.x, zi2));
   fe qy = fe_normalize(fe_mul(acc.y, fe_mul(zi2, zi)));
+  keccak256_xy_address(qx, qy, addr20);
+  return true;
+}
+// the same for the four-lane chain (XYZZ accumulator): Z -> Z y means ZZ -> ZZ c, ZZZ -> ZZZ c y
+template <class EX>
+IBFT_HD bool split_chain_finish_x(const EX& ex, xyzz acc, const fe& c, const fe& y, bool g_inf, const fe& gx, const fe& gy,
+                                  uint8_t* addr20) {
+#pragma unroll
+  for (int i = 0; i < 20; i++) addr20[i] = 0;
+  if (!acc.inf) {
+    fe a[4], b[4], o[4];
+    a[0] = acc.zz; b[0] = c; a[1] = c; b[1] = y;
+    ex.mul4(a, b, 2, o);
+    acc.zz = o[0];
+    a[0] = acc.zzz; b[0] = o[1];
+    ex.mul4(a, b, 1, o);
+    acc.zzz = o[0];
+  }
+  if (!g_inf) {
+    xyzz q;
+    q.x = gx; q.y = gy; q.zz = fe_from_u32(1); q.zzz = q.zz; q.inf = false;
+    acc = xyzz_add_x(ex, acc, q);
+  }
+  if (acc.inf || fe_is_zero(acc.zzz)) return false;
+  fe i3 = IBFT_FE_INV(acc.zzz);
+  fe zi = fe_mul(acc.zz, i3);
+  fe qx = fe_normalize(fe_mul(acc.x, fe_sqr(zi)));
+  fe qy = fe_normalize(fe_mul(acc.y, i3));
   keccak256_xy_address(qx, qy, addr20);
   return true;
 }

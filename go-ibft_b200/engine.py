@@ -134,7 +134,7 @@ class Engine:
         self._check(self.lib.ibft_engine_device_info(self.handle, ctypes.byref(di)))
         return {f: (getattr(di, f).decode() if f == "name" else getattr(di, f)) for f, _ in DeviceInfo._fields_}
 
-    PATH_AUTO, PATH_THREAD, PATH_QUAD, PATH_SPLIT = 0, 1, 2, 3
+    PATH_AUTO, PATH_THREAD, PATH_QUAD, PATH_SPLIT, PATH_QSPLIT = 0, 1, 2, 3, 4
 
     def set_recover_path(self, path: int) -> None:
         """Kernel selection of the recover step (include/ibft_verify.h IBFT_PATH_*): verdicts are identical on every path."""

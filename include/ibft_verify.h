@@ -208,17 +208,18 @@ int ibft_sign_batch(ibft_engine* e, const uint8_t* privkeys, const uint8_t* dige
 
 /* measurement / test hooks ------------------------------------------------------------------------- */
 /* Kernel selection of the recover step (the verdicts are identical on every path; only latency / throughput differ):
- *   AUTO    batches of at most SMs x 32 signatures (4,736 on a B200: one four-lane CTA per SM) take the
- *           four-lanes-per-signature latency kernel, up to SMs x 96 (14,208) the chain + helper kernel, everything larger
- *           the one-thread-per-signature throughput kernel;
+ *   AUTO    by batch size: up to SMs x 48 signatures (7,104 on a B200) QSPLIT, up to SMs x 96 (14,208) SPLIT, beyond
+ *           that THREAD (the throughput kernel);
  *   THREAD  always one thread per signature;  QUAD  always four lanes per signature;
  *   SPLIT   chain warps (one lane per signature) + a helper warp per CTA that takes the digest, r^-1, sqrt and u1*G off the
- *           chain (mid-size batches: up to SMs x 96 signatures in one wave, e.g. a 10k-validator COMMIT round).
+ *           chain (mid-size batches: up to SMs x 96 signatures in one wave, e.g. a 10k-validator COMMIT round);
+ *   QSPLIT  both: four-lane chain warps + a helper warp (small rounds: up to SMs x 24 signatures in one wave).
  * North star: "one CUDA thread (or several lanes) per signature".  Returns IBFT_ERR_INVALID_ARG for an unknown path. */
 #define IBFT_PATH_AUTO 0
 #define IBFT_PATH_THREAD 1
 #define IBFT_PATH_QUAD 2
 #define IBFT_PATH_SPLIT 3
+#define IBFT_PATH_QSPLIT 4
 int ibft_set_recover_path(ibft_engine* e, int path);
 
 /* Number of kernel launches issued by this engine since creation (bench.py reports gpu_launches from it). */

@@ -31,15 +31,15 @@ def emul():
     return ctypes.CDLL(os.path.join(d, "libibft_emul.so"))
 
 
-@pytest.fixture(scope="session", params=["thread", "quad", "split"])
+@pytest.fixture(scope="session", params=["thread", "quad", "split", "qsplit"])
 def engine(request):
-    """Every parity test that takes `engine` runs on ALL THREE recover kernels: one thread per signature (throughput), four
-    lanes per signature (small-batch latency) and chain + helper warps (mid-size latency).  Tests that build their own engine
+    """Every parity test that takes `engine` runs on ALL FOUR recover kernels: one thread per signature (throughput), four
+    lanes per signature, chain + helper warps (mid-size latency) and four-lane chains + helper (small-round latency).  Tests that build their own engine
     exercise the AUTO selection."""
     if not has_gpu():
         pytest.skip("no CUDA device")
     import ibft_b200 as ib
     e = ib.Engine(device=0, max_items=1 << 16, max_payload_bytes=1 << 24, max_groups=64, max_table_slots=16, max_validators=16384)
-    e.set_recover_path({"thread": ib.Engine.PATH_THREAD, "quad": ib.Engine.PATH_QUAD, "split": ib.Engine.PATH_SPLIT}[request.param])
+    e.set_recover_path({"thread": ib.Engine.PATH_THREAD, "quad": ib.Engine.PATH_QUAD, "split": ib.Engine.PATH_SPLIT, "qsplit": ib.Engine.PATH_QSPLIT}[request.param])
     yield e
     e.close()

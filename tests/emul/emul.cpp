@@ -186,6 +186,34 @@ int emul_verify_item_split(const ibft_sig_item* it, const uint8_t* arena, size_t
   memcpy(recovered20, addr, 20);
   return memcmp(addr, ri.signer, 20) == 0;
 }
+
+// split pipeline with the level-structured (four-lane) chain
+int emul_verify_item_qsplit(const ibft_sig_item* it, const uint8_t* arena, size_t arena_len, uint8_t* recovered20) {
+  uint8_t addr[20];
+  memset(recovered20, 0, 20);
+  resolved_item ri;
+  bool valid = false;
+  int st = resolve_item(*it, arena, arena_len, ri, &valid);
+  if (st != IBFT_ITEM_OK) return -1;
+  if (!valid) return 0;
+  gtab_view G = emul_gview();
+  G.host_pos = emul_pos_entry;
+  uint32_t qtab[IBFT_QTAB_WORDS];
+  qtab_view T{qtab, 1};
+  exec_levels ex;
+  ecmult_digits dg;
+  if (!split_helper_scalars(ri, dg)) return 0;
+  fe c;
+  aff Rp = split_chain_point(ri.r, &c);
+  ecmult_build_qtable(ex, Rp, T);
+  xyzz acc = ecmult_streams_x(ex, dg, G, T, false);
+  fe y, gx, gy;
+  bool g_inf = false;
+  if (!split_helper_point(ri, dg, G, y, g_inf, gx, gy)) return 0;
+  if (!split_chain_finish_x(ex, acc, c, y, g_inf, gx, gy, addr)) return 0;
+  memcpy(recovered20, addr, 20);
+  return memcmp(addr, ri.signer, 20) == 0;
+}
 #endif
 
 void emul_keccak256(const uint8_t* d, uint32_t n, uint8_t* out) { keccak256_bytes(d, n, out); }

@@ -255,6 +255,10 @@ def both_paths(E, it, arena_np, arena_len):
     o1, o2 = (ctypes.c_uint8 * 20)(), (ctypes.c_uint8 * 20)()
     r1 = E.emul_verify_item(it.ctypes.data_as(ctypes.c_void_p), arena_np.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arena_len), o1)
     r2 = E.emul_verify_item_split(it.ctypes.data_as(ctypes.c_void_p), arena_np.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arena_len), o2)
+    # ... and through the split pipeline with the level-structured (four-lane) chain: must agree with the one-lane chain
+    o3 = (ctypes.c_uint8 * 20)()
+    r3 = E.emul_verify_item_qsplit(it.ctypes.data_as(ctypes.c_void_p), arena_np.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(arena_len), o3)
+    assert (r3, bytes(o3)) == (r2, bytes(o2))
     return (r1, bytes(o1)), (r2, bytes(o2))
 
 

@@ -28,7 +28,7 @@ torch.cuda.set_stream(st)
 for n in sizes:
     words = (n + 31) // 32
     row = {"items": n}
-    for name, path in (("thread", ib.Engine.PATH_THREAD), ("quad", ib.Engine.PATH_QUAD), ("split", ib.Engine.PATH_SPLIT)):
+    for name, path in (("thread", ib.Engine.PATH_THREAD), ("quad", ib.Engine.PATH_QUAD), ("split", ib.Engine.PATH_SPLIT), ("qsplit", ib.Engine.PATH_QSPLIT)):
         eng.set_recover_path(path)
         t_bm = torch.zeros(words, dtype=torch.int32, device="cuda")
         for _ in range(3):
