@@ -47,6 +47,23 @@ func NewEngine(p Params) (*Engine, error) {
 	return e, nil
 }
 
+// RecoverPath values for SetRecoverPath (include/ibft_verify.h IBFT_PATH_*).  The verdicts are identical on every path.
+const (
+	PathAuto   = 0 // by batch size (default): small rounds take the latency kernels, large backlogs the throughput kernel
+	PathThread = 1
+	PathQuad   = 2
+	PathSplit  = 3
+	PathQSplit = 4
+)
+
+// SetRecoverPath pins the recover kernel (diagnostics / benchmarks); production code leaves it on PathAuto.
+func (e *Engine) SetRecoverPath(path int) error {
+	if rc := C.ibft_set_recover_path(e.h, C.int(path)); rc != C.IBFT_OK {
+		return lastError()
+	}
+	return nil
+}
+
 func (e *Engine) Close() {
 	if e.h != nil {
 		C.ibft_engine_destroy(e.h)
