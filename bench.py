@@ -332,6 +332,16 @@ def main():
     # ---- quorum latency of ONE 10k-validator COMMIT round (10,000 committed seals), host buffers in / bitmap + quorum out
     seal_group = list(d["groups"]).index("COMMIT_SEAL")
     seals = np.ascontiguousarray(base_items[base_items["group"] == seal_group])
+    # measured twice: tuples in pageable memory (what a cgo caller hands over: the engine stages them into its pinned buffer)
+    # and in pinned memory (as the e2e leg above: DMA straight from the caller's buffer)
+    seals_pinned = torch.from_numpy(seals.view(np.uint8)).pin_memory().numpy().view(ib.ITEM_DTYPE).reshape(-1)
+    lat_pin = []
+    for i in range(args.latency_reps + 5):
+        t0 = time.perf_counter()
+        eng.verify_batch(seals_pinned, b"", groups)
+        if i >= 5:
+            lat_pin.append((time.perf_counter() - t0) * 1e6)
+    lat_pin.sort()
     lat = []
     for i in range(args.latency_reps + 5):
         t0 = time.perf_counter()
@@ -423,6 +433,7 @@ def main():
                      "kernel_regs": info["kernel_regs"], "kernel_smem_bytes": info["kernel_smem_bytes"]},
         "quorum_latency_us": {"config": "10k-validator COMMIT round, 10,000 committed seals, host tuples -> bitmap+quorum on host",
                               "reps": len(lat), "p50": lat[len(lat) // 2], "p95": lat[int(len(lat) * 0.95)],
+                              "pinned_input_p50": lat_pin[len(lat_pin) // 2], "pinned_input_p95": lat_pin[int(len(lat_pin) * 0.95)],
                               "device_only_p50": lat_dev[len(lat_dev) // 2], "device_only_p95": lat_dev[int(len(lat_dev) * 0.95)],
                               "kernel": "k_recover_split (chain warps + helper warp; AUTO path for 7,105..14,208 signatures)",
                               "round_1000_seals": {"kernel": "k_recover_qsplit (four-lane chain warps + helper warp; AUTO path up to 7,104 signatures)", "p50": lat_small[len(lat_small) // 2],

@@ -71,6 +71,40 @@ __device__ int lookup_validator(const slot_dev& s, const uint8_t* addr) {
   return -1;
 }
 
+struct group_dev {
+  uint32_t voted_off;  // word offset of the group's voted set
+  uint32_t n_words;
+};
+
+// Where a recover kernel may record a VALID item's vote right away (K2 + the marking half of K3 fused): the group's voted
+// set and valid count.  voted == nullptr: no fused marking (device-resident / sharded callers run k_quorum_mark themselves).
+struct vote_sink {
+  uint32_t* voted;
+  uint32_t* n_valid;
+  const group_dev* gdev;
+};
+
+// validator-set membership at the message's height (reference core/backend.go:44) for an item whose signature verified,
+// plus -- when a sink is given -- the vote itself: same effect as k_quorum_mark on this item.
+__device__ __forceinline__ bool member_and_vote(const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
+                                                const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t group,
+                                                const uint8_t* signer, const vote_sink& sink, bool record) {
+  if (groups == nullptr) return true;
+  if (group >= n_groups) return false;
+  uint32_t slot = groups[group].table_slot;
+  int v = -1;
+  if (slot != IBFT_NO_TABLE) {
+    if (slot >= n_slots || !slots[slot].valid) return false;
+    v = lookup_validator(slots[slot], signer);
+    if (v < 0) return false;
+  }
+  if (record && sink.voted != nullptr) {
+    atomicAdd(&sink.n_valid[group], 1u);
+    if (v >= 0) atomicOr(&sink.voted[sink.gdev[group].voted_off + ((uint32_t)v >> 5)], 1u << (v & 31));
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K1 + K2: recover kernel.  One thread per signature; a warp's 32 verdicts become one bitmap word.
 // ------------------------------------------------------------------------------------------------------------
@@ -84,7 +118,7 @@ __global__ void __launch_bounds__(BLOCK, (IBFT_MIN_BLOCKS * IBFT_BLOCK) / BLOCK)
 k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
           uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
           const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
-          uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable) {
+          uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink) {
 #if IBFT_GTAB_SMEM
   __shared__ uint32_t s_gtab[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];
 #else
@@ -145,17 +179,7 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
 #pragma unroll
     for (int i = 0; i < 20; i++) ok = ok && (addr[i] == ri.signer[i]);
     // validator-set membership at the message's height (reference core/backend.go:44)
-    if (ok && groups != nullptr) {
-      if (it.group >= n_groups) {
-        ok = false;
-      } else {
-        uint32_t slot = groups[it.group].table_slot;
-        if (slot != IBFT_NO_TABLE) {
-          if (slot >= n_slots || !slots[slot].valid) ok = false;
-          else ok = lookup_validator(slots[slot], ri.signer) >= 0;
-        }
-      }
-    }
+    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, true);
     if (recovered != nullptr) {
 #pragma unroll
       for (int i = 0; i < 20; i++) recovered[(size_t)idx * 20 + i] = addr[i];
@@ -179,7 +203,7 @@ __global__ void __launch_bounds__(4 * IBFT_QUAD_SIGS, 2)
 k_recover_quad(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
                uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
                const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
-               uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable) {
+               uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink) {
   __shared__ uint32_t s_items[IBFT_QUAD_SIGS * IBFT_ITEM_ROW_WORDS];
   __shared__ uint32_t s_rtab[IBFT_QUAD_SIGS * IBFT_QTAB_WORDS];  // projective (XYZZ) tables {1..8}*R
   __shared__ uint4 s_xb[4 * 4 * IBFT_QUAD_SIGS];  // exec_quad's product exchange buffer (2 parities x 2 halves per thread)
@@ -234,17 +258,7 @@ k_recover_quad(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
     ok = rec;
 #pragma unroll
     for (int i = 0; i < 20; i++) ok = ok && (addr[i] == ri.signer[i]);
-    if (ok && groups != nullptr) {
-      if (it.group >= n_groups) {
-        ok = false;
-      } else {
-        uint32_t slot = groups[it.group].table_slot;
-        if (slot != IBFT_NO_TABLE) {
-          if (slot >= n_slots || !slots[slot].valid) ok = false;
-          else ok = lookup_validator(slots[slot], ri.signer) >= 0;
-        }
-      }
-    }
+    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, ex.leader());
     if (ex.leader()) {
       if (status != nullptr) status[idx] = (uint8_t)st;
       if (recovered != nullptr) {
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(32 * (IBFT_SPLIT_CHAINS + 1), 1)
 k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
                 uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
                 const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
-                uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable) {
+                uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink) {
   extern __shared__ uint32_t s_dyn[];
   uint32_t* s_items = s_dyn;                                              // 96 packed tuples, 33-word rows
   uint32_t* s_rtab = s_items + IBFT_SPLIT_SIGS * IBFT_ITEM_ROW_WORDS;     // 96 tables {1..8}*phi(R), signature-interleaved
@@ -490,17 +504,7 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
   if (active) {
 #pragma unroll
     for (int k = 0; k < 20; k++) ok = ok && (addr[k] == ri.signer[k]);
-    if (ok && groups != nullptr) {
-      if (it.group >= n_groups) {
-        ok = false;
-      } else {
-        uint32_t slot = groups[it.group].table_slot;
-        if (slot != IBFT_NO_TABLE) {
-          if (slot >= n_slots || !slots[slot].valid) ok = false;
-          else ok = lookup_validator(slots[slot], ri.signer) >= 0;
-        }
-      }
-    }
+    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, true);
     if (status != nullptr) status[idx] = (uint8_t)st;
     if (recovered != nullptr) {
 #pragma unroll
@@ -527,7 +531,7 @@ __global__ void __launch_bounds__(128, 1)
 k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
                  uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
                  const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
-                 uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable) {
+                 uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink) {
   __shared__ uint32_t s_items[IBFT_QSPLIT_SIGS * IBFT_ITEM_ROW_WORDS];
   __shared__ uint32_t s_qtab[IBFT_QSPLIT_SIGS * IBFT_QTAB_WORDS];
   __shared__ uint32_t s_slot[IBFT_QSPLIT_SIGS * IBFT_SLOT_WORDS];
@@ -675,17 +679,7 @@ k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint
   if (active) {
 #pragma unroll
     for (int k = 0; k < 20; k++) ok = ok && (addr[k] == ri.signer[k]);
-    if (ok && groups != nullptr) {
-      if (it.group >= n_groups) {
-        ok = false;
-      } else {
-        uint32_t slot = groups[it.group].table_slot;
-        if (slot != IBFT_NO_TABLE) {
-          if (slot >= n_slots || !slots[slot].valid) ok = false;
-          else ok = lookup_validator(slots[slot], ri.signer) >= 0;
-        }
-      }
-    }
+    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, ex.leader());
     if (ex.leader()) {
       if (status != nullptr) status[idx] = (uint8_t)st;
       if (recovered != nullptr) {
@@ -701,10 +695,6 @@ k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint
 // ------------------------------------------------------------------------------------------------------------
 // K3: quorum
 // ------------------------------------------------------------------------------------------------------------
-struct group_dev {
-  uint32_t voted_off;  // word offset of the group's voted set
-  uint32_t n_words;
-};
 
 __global__ void k_quorum_mark(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
                               const uint32_t* __restrict__ bitmap,
@@ -742,12 +732,13 @@ __global__ void k_quorum_merge(const uint32_t* __restrict__ parts, uint32_t n_pa
 }
 
 // one CTA per group: 320-bit sum of the voting power of the voted validators, compared with the threshold
-__global__ void __launch_bounds__(256)
+#define IBFT_REDUCE_THREADS 1024  // one CTA per group; a 10k-validator set is 10 strided passes instead of 40
+__global__ void __launch_bounds__(IBFT_REDUCE_THREADS)
 k_quorum_reduce(const ibft_group_desc* __restrict__ groups, const group_dev* __restrict__ gdev, uint32_t n_groups,
                 const slot_dev* __restrict__ slots, uint32_t n_slots, const uint32_t* __restrict__ voted,
                 const uint32_t* __restrict__ n_valid, ibft_group_result* __restrict__ results) {
-  __shared__ uint64_t s_sum[256][5];
-  __shared__ uint32_t s_cnt[256];
+  __shared__ uint64_t s_sum[IBFT_REDUCE_THREADS][5];
+  __shared__ uint32_t s_cnt[IBFT_REDUCE_THREADS];
   uint32_t g = blockIdx.x;
   if (g >= n_groups) return;
   uint32_t slot = groups[g].table_slot;
@@ -1074,6 +1065,8 @@ struct ibft_engine {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;       // H2D of chunk k+1 overlaps the recover kernel of chunk k
   std::vector<cudaEvent_t> chunk_ev;
+  cudaStream_t lat_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // one round in four pieces: copy + kernel of piece k
+  cudaEvent_t lat_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // overlap the staging of piece k+1 (latency path)
   cudaEvent_t done_ev = nullptr;
   // device
   ibft_sig_item* d_items = nullptr;
@@ -1131,6 +1124,8 @@ static void engine_free(ibft_engine* e) {
   if (e->done_ev) cudaEventDestroy(e->done_ev);
   for (auto ev : e->chunk_ev) cudaEventDestroy(ev);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  for (auto ls : e->lat_stream) if (ls) cudaStreamDestroy(ls);
+  for (auto ev : e->lat_ev) if (ev) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1140,6 +1135,8 @@ static int engine_alloc(ibft_engine* e) {
   CU(cudaSetDevice(p.device));
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (auto& ls : e->lat_stream) CU(cudaStreamCreateWithFlags(&ls, cudaStreamNonBlocking));
+  for (auto& ev : e->lat_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->done_ev, cudaEventDisableTiming));
   size_t n = p.max_items, words = (n + 31) / 32;
   CU(cudaMalloc(&e->d_items, n * sizeof(ibft_sig_item)));
@@ -1384,21 +1381,23 @@ static int plan_groups(ibft_engine* e, const ibft_group_desc* groups, uint32_t n
 
 static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len,
                           uint32_t lo, uint32_t hi, const ibft_group_desc* d_groups, uint32_t n_groups, uint32_t* d_bitmap,
-                          uint8_t* d_recovered, cudaStream_t st, uint8_t* d_status = nullptr) {
+                          uint8_t* d_recovered, cudaStream_t st, uint8_t* d_status = nullptr, int forced_path = IBFT_PATH_AUTO,
+                          vote_sink sink = vote_sink{nullptr, nullptr, nullptr}) {
   if (hi <= lo) return IBFT_OK;
   // path selection (ibft_set_recover_path).  AUTO picks by how many warps each of the SM's four schedulers would hold
   // (B200, kernel time of one batch: profiles/latency_r01_v9.md):
   //   <= SMs x 24 signatures   four-lane chain warps + helper warp, one CTA (3 + 1 warps) per SM                   0.41 ms
   //   <= SMs x 48              the same, two CTAs per SM (two warps per scheduler)                                  0.51 ms
   //   <= SMs x 96              chain warps + helper warp, one CTA (3 + 1 warps) per SM (a 10k-validator round)      0.68 ms
-  //   beyond                   one thread per signature: one-warp CTAs while one wave covers them (0.86 ms), then the
-  //                            128-thread throughput kernel
+  //   <= SMs x 192             the same, two CTAs per SM (one-thread kernel: 1.16 ms)                               0.90 ms
+  //   beyond                   one thread per signature: one-warp CTAs while one wave covers them, then the 128-thread
+  //                            throughput kernel
   const uint32_t cnt = hi - lo;
-  int path = e->recover_path;
+  int path = forced_path != IBFT_PATH_AUTO ? forced_path : e->recover_path;
   if (path == IBFT_PATH_AUTO) {
 #if IBFT_WC > 0
     if (cnt <= (uint32_t)e->sm_count * 2u * IBFT_QSPLIT_SIGS) path = IBFT_PATH_QSPLIT;
-    else if (cnt <= (uint32_t)e->sm_count * IBFT_SPLIT_SIGS) path = IBFT_PATH_SPLIT;
+    else if (cnt <= (uint32_t)e->sm_count * 2u * IBFT_SPLIT_SIGS) path = IBFT_PATH_SPLIT;
     else path = IBFT_PATH_THREAD;
 #else
     path = cnt <= (uint32_t)e->sm_count * IBFT_QUAD_SIGS ? IBFT_PATH_QUAD : IBFT_PATH_THREAD;
@@ -1409,26 +1408,26 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
     uint32_t blocks = (cnt + IBFT_QSPLIT_SIGS - 1) / IBFT_QSPLIT_SIGS;
     CU(cudaMemsetAsync(d_bitmap + (lo >> 5), 0, (size_t)((hi + 31) / 32 - (lo >> 5)) * 4, st));  // verdict bits are OR-ed in
     k_recover_qsplit<<<blocks, 128, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                             e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
+                                             e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
   } else if (path == IBFT_PATH_SPLIT) {
     uint32_t blocks = (cnt + IBFT_SPLIT_SIGS - 1) / IBFT_SPLIT_SIGS;
     k_recover_split<<<blocks, 32 * (IBFT_SPLIT_CHAINS + 1), IBFT_SPLIT_SMEM, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
                                                                               e->d_slots, e->p.max_table_slots, d_bitmap, d_recovered,
-                                                                              d_status, e->d_ctable);
+                                                                              d_status, e->d_ctable, sink);
   } else
 #endif
   if (path == IBFT_PATH_QUAD) {
     uint32_t blocks = (cnt + IBFT_QUAD_SIGS - 1) / IBFT_QUAD_SIGS;
     k_recover_quad<<<blocks, 4 * IBFT_QUAD_SIGS, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
+                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
   } else if (cnt <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs
     uint32_t blocks = (cnt + 31) / 32;
     k_recover<32><<<blocks, 32, 32 * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
+                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
   } else {
     uint32_t blocks = (cnt + IBFT_BLOCK - 1) / IBFT_BLOCK;
     k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable);
+                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
   }
   e->launches++;
   CU(cudaGetLastError());
@@ -1437,17 +1436,19 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
 
 static int launch_quorum(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len, const uint32_t* d_bitmap,
                          const ibft_group_desc* d_groups, const group_dev* d_gdev, uint32_t n_groups, size_t voted_words,
-                         ibft_group_result* d_results, cudaStream_t st) {
+                         ibft_group_result* d_results, cudaStream_t st, bool already_marked = false) {
   if (n_groups == 0) return IBFT_OK;
-  CU(cudaMemsetAsync(e->d_voted, 0, std::max<size_t>(voted_words, 1) * 4, st));
-  CU(cudaMemsetAsync(e->d_nvalid, 0, (size_t)n_groups * 4, st));
-  if (n) {
+  if (!already_marked) {
+    CU(cudaMemsetAsync(e->d_voted, 0, std::max<size_t>(voted_words, 1) * 4, st));
+    CU(cudaMemsetAsync(e->d_nvalid, 0, (size_t)n_groups * 4, st));
+  }
+  if (n && !already_marked) {
     k_quorum_mark<<<(n + 255) / 256, 256, 0, st>>>(d_items, n, d_arena, arena_len, d_bitmap, d_groups, d_gdev, n_groups, e->d_slots,
                                                     e->p.max_table_slots, e->d_voted, e->d_nvalid, 0u, n);
     e->launches++;
     CU(cudaGetLastError());
   }
-  k_quorum_reduce<<<n_groups, 256, 0, st>>>(d_groups, d_gdev, n_groups, e->d_slots, e->p.max_table_slots, e->d_voted,
+  k_quorum_reduce<<<n_groups, IBFT_REDUCE_THREADS, 0, st>>>(d_groups, d_gdev, n_groups, e->d_slots, e->p.max_table_slots, e->d_voted,
                                             e->d_nvalid, d_results);
   e->launches++;
   CU(cudaGetLastError());
@@ -1485,10 +1486,17 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
     CU(cudaMemcpyAsync(e->d_groups, e->h_groups, (size_t)n_groups * sizeof(ibft_group_desc), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(e->d_gdev, e->h_gdev, (size_t)n_groups * sizeof(group_dev), cudaMemcpyHostToDevice, st));
   }
+  // quorum requested: the recover kernels record the votes themselves (no k_quorum_mark pass over the tuples afterwards)
+  vote_sink sink{nullptr, nullptr, nullptr};
+  if (n_groups && results_out) {
+    CU(cudaMemsetAsync(e->d_voted, 0, std::max<size_t>(voted_words, 1) * 4, st));
+    CU(cudaMemsetAsync(e->d_nvalid, 0, (size_t)n_groups * 4, st));
+    sink = vote_sink{e->d_voted, e->d_nvalid, e->d_gdev};
+  }
   // Tuples go up in chunks: while the recover kernel works on chunk k, the host stages chunk k+1 into pinned memory and the
   // copy engine moves it (two streams + events).  Small batches are a single chunk.
   const uint32_t CHUNK = 1u << 17;
-  uint32_t n_chunks = n ? (n + CHUNK - 1) / CHUNK : 0;
+  uint32_t n_chunks = n ? (n + CHUNK - 1) / CHUNK : 0;  // (not const: the latency path below takes the round over)
   while (e->chunk_ev.size() < n_chunks + 1) {
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1499,6 +1507,40 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
     CU(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[n_chunks], 0));
   }
   int rc = IBFT_OK;
+#if IBFT_WC > 0
+  // One mid-size round (the chain + helper kernel's range, e.g. 10,000 seals = 1.28 MB of tuples): the staging copy and the
+  // H2D transfer would sit in front of a kernel that cannot start before its last tuple has arrived.  Cut the round into four
+  // pieces, each with its own stream -- stage, copy and launch piece k while piece k+1 is being staged; the four kernels
+  // (<= 37 CTAs each) run side by side on different SMs and the main stream joins them before the quorum kernels.
+  const bool lat_pieces = e->recover_path == IBFT_PATH_AUTO && n > (uint32_t)e->sm_count * 2u * IBFT_QSPLIT_SIGS &&
+                          n <= (uint32_t)e->sm_count * IBFT_SPLIT_SIGS;
+  if (lat_pieces) {
+    bool pinned = false;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, items) == cudaSuccess) pinned = pa.type == cudaMemoryTypeHost;
+    else (void)cudaGetLastError();
+    CU(cudaEventRecord(e->lat_ev[4], st));  // arena / groups uploads of this call
+    const uint32_t per = ((n + 3) / 4 + IBFT_SPLIT_SIGS - 1) / IBFT_SPLIT_SIGS * IBFT_SPLIT_SIGS;
+    for (uint32_t c = 0; c < 4; c++) {
+      uint32_t lo = std::min(n, c * per), hi = std::min(n, lo + per);
+      if (hi <= lo) break;
+      cudaStream_t ls = e->lat_stream[c];
+      const ibft_sig_item* src = items + lo;
+      if (!pinned) {
+        memcpy(e->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
+        src = e->h_items + lo;
+      }
+      CU(cudaStreamWaitEvent(ls, e->lat_ev[4], 0));
+      CU(cudaMemcpyAsync(e->d_items + lo, src, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, ls));
+      rc = launch_recover(e, e->d_items, n, e->d_arena, arena_len, lo, hi, n_groups ? e->d_groups : nullptr, n_groups, e->d_bitmap,
+                          recovered_out ? e->d_recovered : nullptr, ls, e->d_status, IBFT_PATH_SPLIT, sink);
+      if (rc != IBFT_OK) return rc;
+      CU(cudaEventRecord(e->lat_ev[c], ls));
+      CU(cudaStreamWaitEvent(st, e->lat_ev[c], 0));
+    }
+    n_chunks = 0;  // the generic chunk loop below has nothing left to do
+  }
+#endif
   // A caller that already holds the tuples in page-locked memory (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory)
   // is copied from directly; pageable memory (Go heap through cgo) goes through the engine's pinned staging first.
   bool caller_pinned = false;
@@ -1521,11 +1563,12 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
       CU(cudaStreamWaitEvent(st, e->chunk_ev[c], 0));
     }
     rc = launch_recover(e, e->d_items, n, e->d_arena, arena_len, lo, hi, n_groups ? e->d_groups : nullptr, n_groups, e->d_bitmap,
-                        recovered_out ? e->d_recovered : nullptr, st, e->d_status);
+                        recovered_out ? e->d_recovered : nullptr, st, e->d_status, IBFT_PATH_AUTO, sink);
     if (rc != IBFT_OK) return rc;
   }
   if (n_groups && results_out) {
-    rc = launch_quorum(e, e->d_items, n, e->d_arena, arena_len, e->d_bitmap, e->d_groups, e->d_gdev, n_groups, voted_words, e->d_results, st);
+    rc = launch_quorum(e, e->d_items, n, e->d_arena, arena_len, e->d_bitmap, e->d_groups, e->d_gdev, n_groups, voted_words, e->d_results, st,
+                       /*already_marked=*/true);
     if (rc != IBFT_OK) return rc;
     CU(cudaMemcpyAsync(e->h_results, e->d_results, (size_t)n_groups * sizeof(ibft_group_result), cudaMemcpyDeviceToHost, st));
   }
@@ -1713,7 +1756,7 @@ extern "C" int ibft_quorum_merge_device(ibft_engine* e, const void* d_partials, 
                                                       n_groups, e->d_voted, e->d_nvalid);
   e->launches++;
   CU(cudaGetLastError());
-  k_quorum_reduce<<<n_groups, 256, 0, st>>>(e->d_groups, e->d_gdev, n_groups, e->d_slots, e->p.max_table_slots, e->d_voted, e->d_nvalid,
+  k_quorum_reduce<<<n_groups, IBFT_REDUCE_THREADS, 0, st>>>(e->d_groups, e->d_gdev, n_groups, e->d_slots, e->p.max_table_slots, e->d_voted, e->d_nvalid,
                                             (ibft_group_result*)d_results);
   e->launches++;
   CU(cudaGetLastError());

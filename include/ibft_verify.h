@@ -208,7 +208,7 @@ int ibft_sign_batch(ibft_engine* e, const uint8_t* privkeys, const uint8_t* dige
 
 /* measurement / test hooks ------------------------------------------------------------------------- */
 /* Kernel selection of the recover step (the verdicts are identical on every path; only latency / throughput differ):
- *   AUTO    by batch size: up to SMs x 48 signatures (7,104 on a B200) QSPLIT, up to SMs x 96 (14,208) SPLIT, beyond
+ *   AUTO    by batch size: up to SMs x 48 signatures (7,104 on a B200) QSPLIT, up to SMs x 192 (28,416) SPLIT, beyond
  *           that THREAD (the throughput kernel);
  *   THREAD  always one thread per signature;  QUAD  always four lanes per signature;
  *   SPLIT   chain warps (one lane per signature) + a helper warp per CTA that takes the digest, r^-1, sqrt and u1*G off the
