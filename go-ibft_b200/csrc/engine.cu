@@ -527,7 +527,10 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
 // (24 signatures per CTA do not align with the 32-bit words).  Capacity of one wave: SMs x 24 signatures.
 // ------------------------------------------------------------------------------------------------------------
 #define IBFT_QSPLIT_SIGS 24
-__global__ void __launch_bounds__(128, 1)
+#ifndef IBFT_QSPLIT_MIN_CTAS
+#define IBFT_QSPLIT_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(128, IBFT_QSPLIT_MIN_CTAS)
 k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
                  uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
                  const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,

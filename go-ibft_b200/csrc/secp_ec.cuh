@@ -145,8 +145,7 @@ struct exec_quad {
     }
     return r;
   }
-  // exchange buffer in shared memory: two parities x two halves x one uint4 per thread of the CTA (conflict-free: lane t owns
-  // slot t; the four lanes of a quad read the same four consecutive slots).  A warp shuffle costs ~10 cycles of issue on this
+  // exchange buffer in shared memory: two parities x two halves x one uint4 per thread of the CTA.  A warp shuffle costs ~10 cycles of issue on this
   // part (330 cycles for the 32 shuffles of a four-product level); two STS.128 + 2k LDS.128 + one quad-level sync are cheaper.
   uint4* xb;            // CTA-wide buffer, 4 * blockDim.x uint4
   mutable uint32_t par; // level parity: double buffering, so one sync per level suffices
@@ -156,16 +155,21 @@ struct exec_quad {
     const uint32_t t = threadIdx.y * blockDim.x + threadIdx.x;
     uint4* buf = xb + par * 2u * nt;
     par ^= 1u;
+    // slot of (quad Q of the warp, product k) = 8k + ((Q + 2k) & 7): the eight quads reading product k hit eight different
+    // 16-byte bank groups, and so do the eight lanes of every quarter-warp when they write (ncu r01_v10: the plain layout
+    // "slot = lane" cost 1.06 M shared-memory bank conflicts per 1,000-signature launch on the reads)
+    const uint32_t wb = t & ~31u, Q = (t >> 2) & 7u;
     if (role < count) {
-      buf[t] = make_uint4(p.v[0], p.v[1], p.v[2], p.v[3]);
-      buf[nt + t] = make_uint4(p.v[4], p.v[5], p.v[6], p.v[7]);
+      const uint32_t sl = wb + 8u * (uint32_t)role + ((Q + 2u * (uint32_t)role) & 7u);
+      buf[sl] = make_uint4(p.v[0], p.v[1], p.v[2], p.v[3]);
+      buf[nt + sl] = make_uint4(p.v[4], p.v[5], p.v[6], p.v[7]);
     }
     __syncwarp(mask);
-    const uint32_t q0 = t & ~3u;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       if (k < count) {
-        uint4 lo = buf[q0 + k], hi = buf[nt + q0 + k];
+        const uint32_t sl = wb + 8u * k + ((Q + 2u * k) & 7u);
+        uint4 lo = buf[sl], hi = buf[nt + sl];
         out[k].v[0] = lo.x; out[k].v[1] = lo.y; out[k].v[2] = lo.z; out[k].v[3] = lo.w;
         out[k].v[4] = hi.x; out[k].v[5] = hi.y; out[k].v[6] = hi.z; out[k].v[7] = hi.w;
       }

@@ -328,3 +328,40 @@ def test_random_tuples_recovered_addresses_match_oracle(engine):
         n_rec += bool(ok)
         assert bytes(recovered[i]) == want, i
     assert 2000 < n_rec < 8000
+
+
+def test_auto_path_selection_boundaries():
+    """AUTO picks the recover kernel by batch size (qsplit <= SMs*48 < split <= SMs*192 < thread) and, for a mid-size host
+    batch with quorum results, uploads the round in four pieces on four streams with the votes recorded by the recover kernels.
+    Every boundary size must give the golden bitmap and the same quorum sums as the reference-order computation."""
+    d, items = load_fixture("config3.npz")
+    eng = ib.Engine(device=0, max_items=1 << 16, max_payload_bytes=1 << 22, max_groups=8, max_table_slots=2, max_validators=16384)
+    try:
+        sms = eng.device_info()["sm_count"]
+        eng.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+        groups = groups_for(len(d["groups"]))
+        gold = np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(items)]
+        big = np.tile(items, 3)
+        gold_big = np.tile(gold, 3)
+        sizes = sorted({1, 23, 24, 25, sms * 24, sms * 24 + 1, sms * 48, sms * 48 + 1, 10000, sms * 96 - 5, sms * 96, sms * 96 + 1,
+                        sms * 192, sms * 192 + 1, 40000})
+        for n in sizes:
+            sub = np.ascontiguousarray(big[:n])
+            bm, results, rec = eng.verify_batch(sub, d["arena"], groups, want_recovered=True)
+            bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[:n]
+            assert np.array_equal(bits, gold_big[:n]), n
+            exp, _ = expected_groups(sub, bm, d["addrs"], d["powers"])
+            for g in range(len(groups)):
+                nv, nd, power, hq = exp.get(g, (0, 0, 0, False))
+                r = results[g]
+                assert (int(r["n_valid"]), int(r["n_distinct"]), bool(r["has_quorum"])) == (nv, nd, hq), (n, g)
+                assert sum(int(r["power"][k]) << (64 * k) for k in range(5)) == power, (n, g)
+            # the same batch without quorum results and from pinned memory takes the other upload branches
+            import torch
+            pinned = torch.from_numpy(sub.view(np.uint8)).pin_memory().numpy().view(ib.ITEM_DTYPE).reshape(-1)
+            bm2, res2, _ = eng.verify_batch(pinned, d["arena"], None)
+            want2 = bits & np.array([1] * n, dtype=np.uint8)  # without groups there is no membership check: superset of `bits`
+            bits2 = np.unpackbits(bm2.view(np.uint8), bitorder="little")[:n]
+            assert res2 is None and np.all(bits2 >= want2), n
+    finally:
+        eng.close()
