@@ -453,13 +453,14 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
   bool have = false;
   int st = IBFT_ITEM_OK;
   rtab_view T{s_rtab + i, (uint32_t)IBFT_SPLIT_SIGS};
+  fe gz = fe_from_u32(1);  // global Z of the table (ecmult_build_rtable_globalz)
   if (active) {
     uint32_t* w = reinterpret_cast<uint32_t*>(&it);
     const uint32_t* src = s_items + i * IBFT_ITEM_ROW_WORDS;
 #pragma unroll
     for (int k = 0; k < 32; k++) w[k] = src[k];
     st = resolve_item(it, arena, arena_len, ri, &have, false);  // fields only: the chain never needs the digest
-    if (have) ecmult_build_rtable(split_chain_point(ri.r), T);
+    if (have) gz = ecmult_build_rtable_globalz(split_chain_point(ri.r), T);  // table on a second isomorphic curve: no inversion
   }
   named_bar_sync(1 + warp, 64);  // the helper has posted the digits of u2
   jac acc;
@@ -498,7 +499,7 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
         gx.v[k] = s_slot[(11 + k) * IBFT_SPLIT_SIGS + i];
         gy.v[k] = s_slot[(19 + k) * IBFT_SPLIT_SIGS + i];
       }
-      ok = split_chain_finish(acc, y, (flags & IBFT_SF_GINF) != 0, gx, gy, addr);
+      ok = split_chain_finish(acc, fe_mul(y, gz), (flags & IBFT_SF_GINF) != 0, gx, gy, addr);  // Z' -> Z' * Z_8 * y
     }
   }
   if (active) {

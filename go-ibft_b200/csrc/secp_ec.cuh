@@ -76,9 +76,10 @@ IBFT_PT jac jac_double(const jac& p) {
   return r;
 }
 
-// p + (qx, qy) with q affine (never infinity): 8M + 3S
-IBFT_PT jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
+// p + (qx, qy) with q affine (never infinity): 8M + 3S.  h_out (optional): Z3 / Z1 of the generic case (= H), 1 otherwise.
+IBFT_PT jac jac_add_affine(const jac& p, const fe& qx, const fe& qy, fe* h_out = nullptr) {
   jac r;
+  if (h_out) *h_out = fe_from_u32(1);
   if (p.inf) {
     r.x = qx;
     r.y = qy;
@@ -104,6 +105,7 @@ IBFT_PT jac jac_add_affine(const jac& p, const fe& qx, const fe& qy) {
   r.y = fe_sub(PMUL(rr, fe_sub(v, r.x)), PMUL(p.y, hhh));
   r.z = PMUL(p.z, h);
   r.inf = false;
+  if (h_out) *h_out = h;
   return r;
 }
 
@@ -412,6 +414,38 @@ IBFT_HD void ecmult_build_rtable(const aff& R, const rtab_view& T) {
     T.load(m, x, y);
     T.store(m, fe_mul(x, zi2), fe_mul(y, fe_mul(zi2, zi)));
   }
+}
+
+// The same table WITHOUT any inversion ("effective affine", as libsecp256k1's odd-multiples table does it): build
+// 2R = dbl(R), (m+1)R = mR + R, so that every new Z is the previous one times a known ratio (2y for the doubling, H for a mixed
+// addition); scale every entry up to the LAST entry's Z with those ratios -- (X f^2, Y f^3), f = Z_8 / Z_m -- and read the
+// table as AFFINE points of the isomorphic curve Y^2 = X^3 + 7 Z_8^6.  The caller runs the window loop on that curve (the a = 0
+// law never uses b) and multiplies the accumulator's Z by the returned Z_8 at the end.  Only usable when nothing else (no
+// generator point of the original curve) is added inside the loop: the chain warps of k_recover_split.
+// 1 dbl + 6 madd + 6 M + 7 (1S + 3M), against 4 dbl + 3 madd + inversion + 6 M + 7 (1S + 5M) for ecmult_build_rtable.
+IBFT_HD fe ecmult_build_rtable_globalz(const aff& R, const rtab_view& T) {
+  fe zr[8];  // zr[m] = Z of entry m / Z of entry m-1
+  jac t;
+  t.x = R.x; t.y = R.y; t.z = fe_from_u32(1); t.inf = false;
+  T.store(0, R.x, R.y);
+  IBFT_ROLLED
+  for (int m = 1; m < 8; m++) {
+    fe h;
+    if (m == 1) { t = jac_double(t); h = t.z; }  // Z of R is 1
+    else t = jac_add_affine(t, R.x, R.y, &h);
+    T.store(m, t.x, t.y);
+    zr[m] = h;
+  }
+  fe f = zr[7];
+  IBFT_ROLLED
+  for (int m = 6; m >= 0; m--) {
+    if (m < 6) f = fe_mul(f, zr[m + 1]);
+    fe f2 = fe_sqr(f);
+    fe x, y;
+    T.load(m, x, y);
+    T.store(m, fe_mul(x, f2), fe_mul(y, fe_mul(f2, f)));
+  }
+  return t.z;
 }
 
 // digit streams of one double-scalar multiplication: 0 = u2 half 1 (R), 1 = u2 half 2 (lambda R), 2 = u1 half 1 (G),

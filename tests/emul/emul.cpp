@@ -176,13 +176,13 @@ int emul_verify_item_split(const ibft_sig_item* it, const uint8_t* arena, size_t
   rtab_view T{rtab, 1};
   ecmult_digits dg;
   if (!split_helper_scalars(ri, dg)) return 0;             // helper phase 1
-  aff Rp = split_chain_point(ri.r);                        // chain: table + R streams on E'
-  ecmult_build_rtable(Rp, T);
+  aff Rp = split_chain_point(ri.r);                        // chain: inversion-free table + R streams on E' / E''
+  fe gz = ecmult_build_rtable_globalz(Rp, T);
   jac acc = ecmult_streams(dg, G, T, false);
   fe y, gx, gy;
   bool g_inf = false;
   if (!split_helper_point(ri, dg, G, y, g_inf, gx, gy)) return 0;  // helper phase 2
-  if (!split_chain_finish(acc, y, g_inf, gx, gy, addr)) return 0;   // chain: map back, + u1 G, address
+  if (!split_chain_finish(acc, fe_mul(y, gz), g_inf, gx, gy, addr)) return 0;   // chain: map back, + u1 G, address
   memcpy(recovered20, addr, 20);
   return memcmp(addr, ri.signer, 20) == 0;
 }
