@@ -45,7 +45,15 @@ struct slot_dev {
   uint64_t quorum[5];      // floor(2*total/3) + 1
   uint32_t n;
   uint32_t valid;
+  // key registry (engine flag IBFT_FLAG_KEY_CACHE; all nullptr otherwise), validator-index order:
+  uint32_t* key_state;     // 0 = unknown, 1 = key learned from a successful recovery, 2 = table of multiples built
+  uint32_t* key_xy;        // n x 16 words: affine public key
+  uint32_t* key_tab;       // n x 128 entries x 16 words: {1..128} * Q, affine (verify_core.cuh build_keytab)
+  uint32_t* learn_count;   // number of keys learned so far (the host compares it with the number of tables built)
 };
+#define IBFT_KEY_UNKNOWN 0u
+#define IBFT_KEY_LEARNED 1u
+#define IBFT_KEY_READY 2u
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
@@ -84,25 +92,57 @@ struct vote_sink {
   const group_dev* gdev;
 };
 
-// validator-set membership at the message's height (reference core/backend.go:44) for an item whose signature verified,
-// plus -- when a sink is given -- the vote itself: same effect as k_quorum_mark on this item.
-__device__ __forceinline__ bool member_and_vote(const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
-                                                const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t group,
-                                                const uint8_t* signer, const vote_sink& sink, bool record) {
+// validator-set membership at the message's height (reference core/backend.go:44).  Returns false when the item can never
+// get verdict 1 (unknown group, unset table, signer not in the set); *v_out = validator index, or -1 when the group has no
+// table (IBFT_NO_TABLE) or no groups were given.
+__device__ __forceinline__ bool group_member(const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
+                                             const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t group,
+                                             const uint8_t* signer, int* v_out, uint32_t* slot_out) {
+  *v_out = -1;
+  *slot_out = IBFT_NO_TABLE;
   if (groups == nullptr) return true;
   if (group >= n_groups) return false;
   uint32_t slot = groups[group].table_slot;
-  int v = -1;
-  if (slot != IBFT_NO_TABLE) {
-    if (slot >= n_slots || !slots[slot].valid) return false;
-    v = lookup_validator(slots[slot], signer);
-    if (v < 0) return false;
-  }
-  if (record && sink.voted != nullptr) {
-    atomicAdd(&sink.n_valid[group], 1u);
-    if (v >= 0) atomicOr(&sink.voted[sink.gdev[group].voted_off + ((uint32_t)v >> 5)], 1u << (v & 31));
-  }
+  if (slot == IBFT_NO_TABLE) return true;
+  if (slot >= n_slots || !slots[slot].valid) return false;
+  int v = lookup_validator(slots[slot], signer);
+  if (v < 0) return false;
+  *v_out = v;
+  *slot_out = slot;
   return true;
+}
+// the vote of a valid item: same effect as k_quorum_mark on this item
+__device__ __forceinline__ void record_vote(const vote_sink& sink, const ibft_group_desc* __restrict__ groups, uint32_t group, int v) {
+  if (groups == nullptr || sink.voted == nullptr) return;
+  atomicAdd(&sink.n_valid[group], 1u);
+  if (v >= 0) atomicOr(&sink.voted[sink.gdev[group].voted_off + ((uint32_t)v >> 5)], 1u << (v & 31));
+}
+// membership + vote for an item whose signature verified (the latency kernels look the signer up at the end)
+__device__ __forceinline__ bool member_and_vote(const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
+                                                const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t group,
+                                                const uint8_t* signer, const vote_sink& sink, bool record, int* v_out = nullptr,
+                                                uint32_t* slot_out = nullptr) {
+  int v;
+  uint32_t slot;
+  bool ok = group_member(groups, n_groups, slots, n_slots, group, signer, &v, &slot);
+  if (v_out) *v_out = v;
+  if (slot_out) *slot_out = slot;
+  if (ok && record) record_vote(sink, groups, group, v);
+  return ok;
+}
+// key registry: remember the public key a successful recovery produced for validator v (first writer wins; concurrent
+// writers store the same key)
+__device__ __forceinline__ void learn_key(const slot_dev* __restrict__ slots, uint32_t slot, int v, const aff& K) {
+  if (slot == IBFT_NO_TABLE || v < 0) return;
+  const slot_dev& s = slots[slot];
+  if (s.key_state == nullptr || s.key_state[v] != IBFT_KEY_UNKNOWN) return;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    s.key_xy[16 * (size_t)v + i] = K.x.v[i];
+    s.key_xy[16 * (size_t)v + 8 + i] = K.y.v[i];
+  }
+  __threadfence();
+  if (atomicCAS(&s.key_state[v], IBFT_KEY_UNKNOWN, IBFT_KEY_LEARNED) == IBFT_KEY_UNKNOWN) atomicAdd(s.learn_count, 1u);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -118,7 +158,10 @@ __global__ void __launch_bounds__(BLOCK, (IBFT_MIN_BLOCKS * IBFT_BLOCK) / BLOCK)
 k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
           uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
           const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
-          uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink) {
+          uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink,
+          const uint32_t* __restrict__ list) {
+  // list != nullptr: WORKLIST mode (second pass of the key-registry path): list[0] = count, list[1..] = item indices that the
+  // verify pass could not decide; the items are gathered, verdict bits are OR-ed into the bitmap the first pass wrote.
 #if IBFT_GTAB_SMEM
   __shared__ uint32_t s_gtab[IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES];
 #else
@@ -135,7 +178,7 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
 #endif
   // stage this CTA's 128 packed tuples with coalesced 16-byte loads
   const uint32_t base = shard_lo + blockIdx.x * BLOCK;
-  {
+  if (list == nullptr) {
     const uint4* src = reinterpret_cast<const uint4*>(items + base);
     uint32_t avail = base < shard_hi ? min((uint32_t)BLOCK, shard_hi - base) : 0u;
 #pragma unroll
@@ -150,45 +193,131 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
     }
   }
   __syncthreads();
-  const uint32_t idx = base + tid;
+  uint32_t idx = base + tid;
+  bool active = idx < shard_hi;
   bool ok = false;
   ibft_sig_item it;
-  {
+  if (list == nullptr) {
     uint32_t* w = reinterpret_cast<uint32_t*>(&it);
     const uint32_t* s = s_items + tid * IBFT_ITEM_ROW_WORDS;
 #pragma unroll
     for (int i = 0; i < 32; i++) w[i] = s[i];
+  } else {
+    const uint32_t t = blockIdx.x * BLOCK + tid;
+    active = t < list[0];
+    idx = active ? list[1 + t] : 0u;
+    const uint4* src = reinterpret_cast<const uint4*>(items + idx);
+    uint4* w = reinterpret_cast<uint4*>(&it);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = __ldg(src + i);
   }
   __syncthreads();  // the staging area becomes the R tables from here on
-  if (idx < shard_hi) {
+  if (active) {
     uint8_t addr[20];
+#pragma unroll
+    for (int i = 0; i < 20; i++) addr[i] = 0;
     resolved_item ri;
     bool have = false;
     IBFT_STAGE(0);
     int st = resolve_item(it, arena, arena_len, ri, &have);  // raw frames are parsed here (IBFT_KIND_WIRE*)
-    if (status != nullptr) status[idx] = (uint8_t)st;
+    if (status != nullptr && list == nullptr) status[idx] = (uint8_t)st;
     gtab_view G{s_gtab};
     G.comb = ctable;
     rtab_view T{s_rtab + tid, (uint32_t)BLOCK};
-    bool rec = have && ecrecover_address(ri.r, ri.s, ri.v, ri.z, G, T, addr);
-    if (!rec) {
+    // the signer is looked up FIRST: an item of an unknown group / a non-member can never get verdict 1 (its signature is
+    // still recovered when the caller asked for the recovered addresses)
+    int v = -1;
+    uint32_t slot = IBFT_NO_TABLE;
+    const bool member = have && group_member(groups, n_groups, slots, n_slots, it.group, ri.signer, &v, &slot);
+    if (have && (member || recovered != nullptr)) {
+      aff K;
+      bool rec = ecrecover_address(ri.r, ri.s, ri.v, ri.z, G, T, addr, &K);
+      if (!rec) {
 #pragma unroll
-      for (int i = 0; i < 20; i++) addr[i] = 0;
+        for (int i = 0; i < 20; i++) addr[i] = 0;
+      }
+      ok = rec && member;
+#pragma unroll
+      for (int i = 0; i < 20; i++) ok = ok && (addr[i] == ri.signer[i]);
+      if (ok) learn_key(slots, slot, v, K);
     }
-    ok = rec;
-#pragma unroll
-    for (int i = 0; i < 20; i++) ok = ok && (addr[i] == ri.signer[i]);
-    // validator-set membership at the message's height (reference core/backend.go:44)
-    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, true);
+    if (ok) record_vote(sink, groups, it.group, v);
     if (recovered != nullptr) {
 #pragma unroll
       for (int i = 0; i < 20; i++) recovered[(size_t)idx * 20 + i] = addr[i];
     }
+    if (list != nullptr && ok) atomicOr(&bitmap[idx >> 5], 1u << (idx & 31u));
   }
+  if (list != nullptr) return;
   // warp-ballot reduction of the 32 verdicts into one bitmap word (shard bounds are multiples of 32)
   uint32_t word = __ballot_sync(0xFFFFFFFFu, ok);
   if ((tid & 31) == 0 && idx < shard_hi) bitmap[idx >> 5] = word;
 }
+
+#if IBFT_WC > 0
+// ------------------------------------------------------------------------------------------------------------
+// Key-registry path, first pass (engine flag IBFT_FLAG_KEY_CACHE, throughput regime): one thread per signature; a signature
+// whose signer's key table is ready is VERIFIED against the key (verify_core.cuh ecdsa_verify_known).  Whatever this pass
+// cannot accept -- key not known yet, or the verification rejected -- goes to the worklist and is decided by the recover
+// path in a second, dense launch of k_recover (so a warp never walks both window loops, and every verdict is the recover
+// path's verdict).  Items that can never be valid (malformed, unknown group, signer not in the set) are settled here.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(IBFT_BLOCK, IBFT_MIN_BLOCKS)
+k_verify_known(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
+               uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
+               const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
+               uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink, uint32_t* __restrict__ worklist) {
+  __shared__ uint32_t s_items[IBFT_BLOCK * IBFT_ITEM_ROW_WORDS];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t base = shard_lo + blockIdx.x * IBFT_BLOCK;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(items + base);
+    uint32_t avail = base < shard_hi ? min((uint32_t)IBFT_BLOCK, shard_hi - base) : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint32_t q = tid + k * IBFT_BLOCK;
+      uint32_t row = q >> 3, col = q & 7;
+      if (row < avail) {
+        uint4 v = __ldg(src + q);
+        uint32_t* d = s_items + row * IBFT_ITEM_ROW_WORDS + col * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t idx = base + tid;
+  bool ok = false;
+  if (idx < shard_hi) {
+    ibft_sig_item it;
+    {
+      uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+      const uint32_t* s = s_items + tid * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+      for (int i = 0; i < 32; i++) w[i] = s[i];
+    }
+    resolved_item ri;
+    bool have = false;
+    int st = resolve_item(it, arena, arena_len, ri, &have);
+    if (status != nullptr) status[idx] = (uint8_t)st;
+    int v = -1;
+    uint32_t slot = IBFT_NO_TABLE;
+    const bool member = have && group_member(groups, n_groups, slots, n_slots, it.group, ri.signer, &v, &slot);
+    if (member) {
+      bool ready = v >= 0 && slots[slot].key_state != nullptr && slots[slot].key_state[v] == IBFT_KEY_READY;
+      if (ready) {
+        gtab_view G{g_gtable};
+        G.comb = ctable;
+        gtab_view Qt{slots[slot].key_tab + (size_t)v * IBFT_KEYTAB_ENTRIES * IBFT_GTAB_ENTRY_WORDS};
+        ok = ecdsa_verify_known(ri, G, Qt);
+      }
+      if (ok) record_vote(sink, groups, it.group, v);
+      else worklist[1 + atomicAdd(&worklist[0], 1u)] = idx;  // key unknown, or rejected: the recover pass decides
+    }
+  }
+  uint32_t word = __ballot_sync(0xFFFFFFFFu, ok);
+  if ((tid & 31) == 0 && idx < shard_hi) bitmap[idx >> 5] = word;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------------------
 // K1 + K2, latency variant: FOUR LANES PER SIGNATURE.  A 10k-validator COMMIT round is one wave of independent serial
@@ -250,7 +379,8 @@ k_recover_quad(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
     gtab_view G{g_gtable};
     G.comb = ctable;
     rtab_view T{s_rtab + q, (uint32_t)IBFT_QUAD_SIGS};
-    bool rec = have && ecrecover_address_x(ex, ri.r, ri.s, ri.v, ri.z, G, T, addr);
+    aff K;
+    bool rec = have && ecrecover_address_x(ex, ri.r, ri.s, ri.v, ri.z, G, T, addr, &K);
     if (!rec) {
 #pragma unroll
       for (int i = 0; i < 20; i++) addr[i] = 0;
@@ -258,7 +388,10 @@ k_recover_quad(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
     ok = rec;
 #pragma unroll
     for (int i = 0; i < 20; i++) ok = ok && (addr[i] == ri.signer[i]);
-    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, ex.leader());
+    int vi = -1;
+    uint32_t vslot = IBFT_NO_TABLE;
+    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, ex.leader(), &vi, &vslot);
+    if (ok && ex.leader()) learn_key(slots, vslot, vi, K);
     if (ex.leader()) {
       if (status != nullptr) status[idx] = (uint8_t)st;
       if (recovered != nullptr) {
@@ -485,6 +618,8 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
     }
   }
   named_bar_sync(1 + IBFT_SPLIT_CHAINS + warp, 64);  // the helper has posted y and u1*G
+  aff K;
+  K.x = fe_zero(); K.y = fe_zero();
   uint8_t addr[20];
 #pragma unroll
   for (int k = 0; k < 20; k++) addr[k] = 0;
@@ -499,13 +634,16 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
         gx.v[k] = s_slot[(11 + k) * IBFT_SPLIT_SIGS + i];
         gy.v[k] = s_slot[(19 + k) * IBFT_SPLIT_SIGS + i];
       }
-      ok = split_chain_finish(acc, fe_mul(y, gz), (flags & IBFT_SF_GINF) != 0, gx, gy, addr);  // Z' -> Z' * Z_8 * y
+      ok = split_chain_finish(acc, fe_mul(y, gz), (flags & IBFT_SF_GINF) != 0, gx, gy, addr, &K);  // Z' -> Z' * Z_8 * y
     }
   }
   if (active) {
 #pragma unroll
     for (int k = 0; k < 20; k++) ok = ok && (addr[k] == ri.signer[k]);
-    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, true);
+    int vi = -1;
+    uint32_t vslot = IBFT_NO_TABLE;
+    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, true, &vi, &vslot);
+    if (ok) learn_key(slots, vslot, vi, K);
     if (status != nullptr) status[idx] = (uint8_t)st;
     if (recovered != nullptr) {
 #pragma unroll
@@ -663,6 +801,8 @@ k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint
     }
   }
   named_bar_sync(4 + warp, 64);
+  aff K;
+  K.x = fe_zero(); K.y = fe_zero();
   uint8_t addr[20];
 #pragma unroll
   for (int k = 0; k < 20; k++) addr[k] = 0;
@@ -677,13 +817,16 @@ k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint
         gx.v[k] = s_slot[(11 + k) * S + q];
         gy.v[k] = s_slot[(19 + k) * S + q];
       }
-      ok = split_chain_finish_x(ex, acc, c, y, (flags & IBFT_SF_GINF) != 0, gx, gy, addr);
+      ok = split_chain_finish_x(ex, acc, c, y, (flags & IBFT_SF_GINF) != 0, gx, gy, addr, &K);
     }
   }
   if (active) {
 #pragma unroll
     for (int k = 0; k < 20; k++) ok = ok && (addr[k] == ri.signer[k]);
-    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, ex.leader());
+    int vi = -1;
+    uint32_t vslot = IBFT_NO_TABLE;
+    if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, ex.leader(), &vi, &vslot);
+    if (ok && ex.leader()) learn_key(slots, vslot, vi, K);
     if (ex.leader()) {
       if (status != nullptr) status[idx] = (uint8_t)st;
       if (recovered != nullptr) {
@@ -882,6 +1025,26 @@ k_build_ctable(uint32_t* __restrict__ out) {  // blockIdx.y = comb position: ent
 }
 #endif
 
+#if IBFT_WC > 0
+// key registry: tables of multiples for every validator of `slot` whose key has been learned but whose table is missing.
+// One thread per validator (128 additions + 128 inversions each: ~3 ms for a whole 10k-validator set, once per validator).
+__global__ void __launch_bounds__(64)
+k_build_keytabs(const slot_dev* __restrict__ slots, uint32_t slot) {
+  const slot_dev& s = slots[slot];
+  uint32_t v = blockIdx.x * 64 + threadIdx.x;
+  if (s.key_state == nullptr || v >= s.n || s.key_state[v] != IBFT_KEY_LEARNED) return;
+  aff Q;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    Q.x.v[i] = s.key_xy[16 * (size_t)v + i];
+    Q.y.v[i] = s.key_xy[16 * (size_t)v + 8 + i];
+  }
+  build_keytab(Q, s.key_tab + (size_t)v * IBFT_KEYTAB_ENTRIES * IBFT_GTAB_ENTRY_WORDS);
+  __threadfence();
+  s.key_state[v] = IBFT_KEY_READY;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------------------
 // batched signing (MessageConstructor side)
 // ------------------------------------------------------------------------------------------------------------
@@ -1053,6 +1216,12 @@ struct slot_host {
   uint32_t* d_keys = nullptr;
   uint64_t* d_powers = nullptr;
   uint64_t quorum[5] = {0, 0, 0, 0, 0};
+  // key registry (IBFT_FLAG_KEY_CACHE)
+  uint32_t* d_key_state = nullptr;
+  uint32_t* d_key_xy = nullptr;
+  uint32_t* d_key_tab = nullptr;
+  uint32_t* d_learn_count = nullptr;
+  uint32_t built_count = 0;  // value of *d_learn_count when the tables were last brought up to date
 };
 
 struct pending_call {
@@ -1102,6 +1271,7 @@ struct ibft_engine {
   pending_call pending;
   uint64_t launches = 0;
   int recover_path = IBFT_PATH_AUTO;
+  uint32_t* d_worklist = nullptr;  // key-registry path: [0] = count, [1..] = indices left to the recover pass
   int sm_count = 148;
   const uint8_t* dev_arena = nullptr;
   size_t dev_arena_len = 0;
@@ -1118,9 +1288,11 @@ static void engine_free(ibft_engine* e) {
   for (auto& s : e->slots) {
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_powers) cudaFree(s.d_powers);
+    cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab); cudaFree(s.d_learn_count);
   }
   cudaFree(e->d_status); cudaFreeHost(e->h_status);
   cudaFree(e->d_ctable);
+  cudaFree(e->d_worklist);
   cudaFree(e->d_items); cudaFree(e->d_arena); cudaFree(e->d_bitmap); cudaFree(e->d_recovered); cudaFree(e->d_groups);
   cudaFree(e->d_gdev); cudaFree(e->d_results); cudaFree(e->d_voted); cudaFree(e->d_nvalid); cudaFree(e->d_slots);
   cudaFreeHost(e->h_items); cudaFreeHost(e->h_arena); cudaFreeHost(e->h_bitmap); cudaFreeHost(e->h_recovered);
@@ -1144,6 +1316,7 @@ static int engine_alloc(ibft_engine* e) {
   CU(cudaEventCreateWithFlags(&e->done_ev, cudaEventDisableTiming));
   size_t n = p.max_items, words = (n + 31) / 32;
   CU(cudaMalloc(&e->d_items, n * sizeof(ibft_sig_item)));
+  if (p.flags & IBFT_FLAG_KEY_CACHE) CU(cudaMalloc(&e->d_worklist, (n + 1) * 4));
   CU(cudaMalloc(&e->d_arena, std::max<size_t>(p.max_payload_bytes, 16)));
   CU(cudaMalloc(&e->d_bitmap, std::max<size_t>(words, 1) * 4));
   CU(cudaMalloc(&e->d_recovered, n * 20));
@@ -1327,6 +1500,9 @@ extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t
   CU(cudaStreamSynchronize(e->stream));
   if (s.d_keys) { cudaFree(s.d_keys); s.d_keys = nullptr; }
   if (s.d_powers) { cudaFree(s.d_powers); s.d_powers = nullptr; }
+  cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab); cudaFree(s.d_learn_count);
+  s.d_key_state = s.d_key_xy = s.d_key_tab = s.d_learn_count = nullptr;
+  s.built_count = 0;
   s.valid = false;
   CU(cudaMalloc(&s.d_keys, std::max<size_t>(keys.size(), 6) * 4));
   CU(cudaMalloc(&s.d_powers, std::max<size_t>(powers.size(), 4) * 8));
@@ -1338,15 +1514,63 @@ extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t
   s.height = height;
   memcpy(s.quorum, q, sizeof s.quorum);
   s.valid = true;
+#if IBFT_WC > 0
+  if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && n) {  // a new validator set starts with an empty key registry
+    CU(cudaMalloc(&s.d_key_state, (size_t)n * 4));
+    CU(cudaMalloc(&s.d_key_xy, (size_t)n * 64));
+    CU(cudaMalloc(&s.d_key_tab, (size_t)n * IBFT_KEYTAB_ENTRIES * 64));
+    CU(cudaMalloc(&s.d_learn_count, 4));
+    CU(cudaMemset(s.d_key_state, 0, (size_t)n * 4));
+    CU(cudaMemset(s.d_learn_count, 0, 4));
+  }
+#endif
   slot_dev sd{};
   sd.keys = s.d_keys;
   sd.powers = s.d_powers;
+  sd.key_state = s.d_key_state;
+  sd.key_xy = s.d_key_xy;
+  sd.key_tab = s.d_key_tab;
+  sd.learn_count = s.d_learn_count;
   memcpy(sd.quorum, q, sizeof sd.quorum);
   sd.n = n;
   sd.valid = 1;
   e->slots_shadow[table_slot] = sd;
   CU(cudaMemcpy(e->d_slots + table_slot, &sd, sizeof sd, cudaMemcpyHostToDevice));
   return IBFT_OK;
+}
+
+// Key registry upkeep: for every resident validator table, build the tables of multiples of the keys learned since the last
+// call.  Cheap when nothing is new (one 4-byte read per slot).  ibft_verify_batch / ibft_verify_wait call it on their way out;
+// callers of the device-resident entry points call it between rounds.
+static int refresh_key_tables_locked(ibft_engine* e, uint32_t* n_ready_out) {
+  uint32_t total = 0;
+#if IBFT_WC > 0
+  if (e->p.flags & IBFT_FLAG_KEY_CACHE) {
+    CU(cudaSetDevice(e->p.device));
+    for (uint32_t slot = 0; slot < e->p.max_table_slots; slot++) {
+      slot_host& s = e->slots[slot];
+      if (!s.valid || !s.d_learn_count) continue;
+      uint32_t learned = 0;
+      CU(cudaMemcpyAsync(&learned, s.d_learn_count, 4, cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+      if (learned > s.built_count) {
+        k_build_keytabs<<<(s.n + 63) / 64, 64, 0, e->stream>>>(e->d_slots, slot);
+        e->launches++;
+        CU(cudaGetLastError());
+        s.built_count = learned;
+      }
+      total += learned;
+    }
+  }
+#endif
+  if (n_ready_out) *n_ready_out = total;
+  return IBFT_OK;
+}
+extern "C" int ibft_refresh_key_tables(ibft_engine* e, uint32_t* n_keys_out) {
+  if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (e->pending.active) { set_err("a submitted call is still pending"); return IBFT_ERR_INVALID_ARG; }
+  return refresh_key_tables_locked(e, n_keys_out);
 }
 
 extern "C" int ibft_get_quorum(ibft_engine* e, uint32_t table_slot, uint64_t quorum_out[5], uint64_t* height_out,
@@ -1427,11 +1651,25 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
   } else if (cnt <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs
     uint32_t blocks = (cnt + 31) / 32;
     k_recover<32><<<blocks, 32, 32 * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
+                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink, nullptr);
   } else {
     uint32_t blocks = (cnt + IBFT_BLOCK - 1) / IBFT_BLOCK;
+#if IBFT_WC > 0
+    if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && d_recovered == nullptr && d_groups != nullptr && e->d_worklist != nullptr) {
+      // key-registry path: verify what can be verified, then recover the rest from the worklist (dense second launch; the
+      // threads beyond the worklist's length leave at once)
+      CU(cudaMemsetAsync(e->d_worklist, 0, 4, st));
+      k_verify_known<<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+                                                    e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink, e->d_worklist);
+      e->launches++;
+      CU(cudaGetLastError());
+      k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
+                                                           e->d_slots, e->p.max_table_slots, d_bitmap, nullptr, nullptr, e->d_ctable, sink,
+                                                           e->d_worklist);
+    } else
+#endif
     k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
+                                                         e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink, nullptr);
   }
   e->launches++;
   CU(cudaGetLastError());
@@ -1610,6 +1848,7 @@ static int wait_locked(ibft_engine* e) {
     if (pc.recovered_out) memcpy(pc.recovered_out, e->h_recovered, (size_t)pc.n * 20);
   }
   if (pc.n_groups) memcpy(pc.results_out, e->h_results, (size_t)pc.n_groups * sizeof(ibft_group_result));
+  if (e->p.flags & IBFT_FLAG_KEY_CACHE) return refresh_key_tables_locked(e, nullptr);  // new keys -> tables, for the next call
   return IBFT_OK;
 }
 

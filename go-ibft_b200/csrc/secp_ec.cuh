@@ -528,6 +528,51 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
 }
 
 #if IBFT_WC > 0
+// u1*G + u2*Q for a KNOWN point Q with a precomputed table {1..2^(WQ-1)}*Q (affine, same entry format as the generator table;
+// global memory): every stream advances in 8-bit windows, so there are 17 rounds of 8 doublings + at most three mixed
+// additions (Q, lambda Q, combined generator entry) -- no per-signature table at all.  dg: streams 0,1 = split of u2,
+// streams 2,3 = split of u1.
+#define IBFT_WQ 8
+#define IBFT_KEYTAB_ENTRIES (1 << (IBFT_WQ - 1))
+IBFT_HD jac ecmult_streams_known(const ecmult_digits& dg, const gtab_view& G, const gtab_view& Qt) {
+  const fe beta = fe_beta();
+  jac acc;
+  acc.x = fe_zero(); acc.y = fe_zero(); acc.z = fe_zero();
+  acc.inf = true;
+  IBFT_ROLLED
+  for (int jg = IBFT_CTAB_POSITIONS - 1; jg >= 0; jg--) {
+    if (!acc.inf) {
+      IBFT_ROLLED
+      for (int t = 0; t < IBFT_WQ; t++) acc = jac_double(acc);
+    }
+    IBFT_ROLLED
+    for (int s = 0; s < 3; s++) {
+      fe x, y;
+      bool neg;
+      if (s == 2) {
+        int d1 = booth_digit<IBFT_WC>(dg.ks[2], jg), d2 = booth_digit<IBFT_WC>(dg.ks[3], jg);
+        if (dg.kneg[2]) d1 = -d1;
+        if (dg.kneg[3]) d2 = -d2;
+        if ((d1 | d2) == 0) continue;
+        neg = d1 < 0 || (d1 == 0 && d2 < 0);
+        if (neg) { d1 = -d1; d2 = -d2; }
+        G.load_comb(d1, d2, x, y);
+      } else {
+        int d = booth_digit<IBFT_WQ>(dg.ks[s], jg);
+        if (d == 0) continue;
+        Qt.load((d < 0 ? -d : d) - 1, x, y);
+        if (s == 1) x = fe_mul(x, beta);
+        neg = (d < 0) != dg.kneg[s];
+      }
+      if (neg) y = fe_neg(y);
+      acc = jac_add_affine(acc, x, y);
+    }
+  }
+  return acc;
+}
+#endif
+
+#if IBFT_WC > 0
 // u1*G alone as a fixed-base COMB over per-position tables (no doublings): position j of the table holds
 // d1 * 2^(WC j) * G + d2 * 2^(WC j) * lambda G for the same (d1, d2) index space as the combined table (position 0 IS the
 // combined table).  Used by the helper warp of the split latency kernel, which adds the result to the chain warp's u2*R.

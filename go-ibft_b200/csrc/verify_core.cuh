@@ -273,7 +273,7 @@ __device__ __forceinline__ bool ecmult_affine(const exec_quad& ex, const sc& u1,
 // Recover the signer of (r, s, v) over digest z.  Returns false when the signature is invalid; addr20 then zero.
 template <class EX>
 IBFT_HD bool ecrecover_address_x(const EX& ex, const uint8_t* r_be, const uint8_t* s_be, uint8_t v, const uint8_t* z_be,
-                                 const gtab_view& G, const rtab_view& T, uint8_t* addr20) {
+                                 const gtab_view& G, const rtab_view& T, uint8_t* addr20, aff* key_out = nullptr) {
 #pragma unroll
   for (int i = 0; i < 20; i++) addr20[i] = 0;
   sc r = sc_from_be(r_be), s = sc_from_be(s_be);
@@ -301,14 +301,15 @@ IBFT_HD bool ecrecover_address_x(const EX& ex, const uint8_t* r_be, const uint8_
   IBFT_STAGE(3);
   fe qx, qy;
   if (!ecmult_affine(ex, u1, u2, R, G, T, qx, qy)) return false;
+  if (key_out) { key_out->x = qx; key_out->y = qy; }
   IBFT_STAGE(9);
   keccak256_xy_address(qx, qy, addr20);
   IBFT_STAGE(10);
   return true;
 }
 IBFT_HD bool ecrecover_address(const uint8_t* r_be, const uint8_t* s_be, uint8_t v, const uint8_t* z_be,
-                               const gtab_view& G, const rtab_view& T, uint8_t* addr20) {
-  return ecrecover_address_x(exec_serial{}, r_be, s_be, v, z_be, G, T, addr20);
+                               const gtab_view& G, const rtab_view& T, uint8_t* addr20, aff* key_out = nullptr) {
+  return ecrecover_address_x(exec_serial{}, r_be, s_be, v, z_be, G, T, addr20, key_out);
 }
 
 #if IBFT_WC > 0
@@ -380,7 +381,8 @@ IBFT_HD aff split_chain_point(const uint8_t* r_be, fe* c_out = nullptr) {
   return Rp;
 }
 // chain: map acc (= u2 * phi(R) on E') back, add u1*G, derive the address.  false = point at infinity.
-IBFT_HD bool split_chain_finish(jac acc, const fe& y, bool g_inf, const fe& gx, const fe& gy, uint8_t* addr20) {
+IBFT_HD bool split_chain_finish(jac acc, const fe& y, bool g_inf, const fe& gx, const fe& gy, uint8_t* addr20,
+                                aff* key_out = nullptr) {
 #pragma unroll
   for (int i = 0; i < 20; i++) addr20[i] = 0;
   if (!acc.inf) acc.z = fe_mul(acc.z, y);
@@ -390,13 +392,14 @@ IBFT_HD bool split_chain_finish(jac acc, const fe& y, bool g_inf, const fe& gx, 
   fe zi2 = fe_sqr(zi);
   fe qx = fe_normalize(fe_mul(acc.x, zi2));
   fe qy = fe_normalize(fe_mul(acc.y, fe_mul(zi2, zi)));
+  if (key_out) { key_out->x = qx; key_out->y = qy; }
   keccak256_xy_address(qx, qy, addr20);
   return true;
 }
 // the same for the four-lane chain (XYZZ accumulator): Z -> Z y means ZZ -> ZZ c, ZZZ -> ZZZ c y
 template <class EX>
 IBFT_HD bool split_chain_finish_x(const EX& ex, xyzz acc, const fe& c, const fe& y, bool g_inf, const fe& gx, const fe& gy,
-                                  uint8_t* addr20) {
+                                  uint8_t* addr20, aff* key_out = nullptr) {
 #pragma unroll
   for (int i = 0; i < 20; i++) addr20[i] = 0;
   if (!acc.inf) {
@@ -418,8 +421,60 @@ IBFT_HD bool split_chain_finish_x(const EX& ex, xyzz acc, const fe& c, const fe&
   fe zi = fe_mul(acc.zz, i3);
   fe qx = fe_normalize(fe_mul(acc.x, fe_sqr(zi)));
   fe qy = fe_normalize(fe_mul(acc.y, i3));
+  if (key_out) { key_out->x = qx; key_out->y = qy; }
   keccak256_xy_address(qx, qy, addr20);
   return true;
+}
+#endif
+
+#if IBFT_WC > 0
+// ------------------------------------------------------------------------------------------------------------
+// Verification against a KNOWN public key.  Once a validator's signature has been recovered successfully its key Q is known
+// (addr(Q) = the validator's address); later signatures of that validator are checked as u1*G + u2*Q == R with u1 = z/s,
+// u2 = r/s, against a per-validator table of multiples of Q: no square root, no per-signature table, no address hash.
+//   accept  <=>  the point equals R = (r, y) with the parity of y equal to v  <=>  recovery from (r, s, v, z) yields exactly Q
+// (zG + rQ = sR  <=>  Q = r^-1 (sR - zG); x = r only, as in the recovery convention of this engine), hence accept implies the
+// recover path's verdict 1.  A reject says "recovery would NOT yield Q" -- the caller then runs the recover path, so the
+// final verdict is the recover path's in every case (also when the signature was made by another key with the same address).
+// ------------------------------------------------------------------------------------------------------------
+IBFT_HD bool ecdsa_verify_known(const resolved_item& ri, const gtab_view& G, const gtab_view& Qt) {
+  sc r = sc_from_be(ri.r), s = sc_from_be(ri.s);
+  if (ri.v > 1) return false;
+  if (sc_is_zero(r) || sc_is_zero(s) || sc_ge_n(r) || sc_ge_n(s)) return false;
+  sc z = sc_reduce_once(sc_from_be(ri.z));
+  sc w = IBFT_SC_INV(s);
+  ecmult_digits dg;
+  ecmult_split_into(sc_mul(r, w), dg, 0);
+  ecmult_split_into(sc_mul(z, w), dg, 2);
+  jac P = ecmult_streams_known(dg, G, Qt);
+  if (P.inf || fe_is_zero(P.z)) return false;
+  fe zi = IBFT_FE_INV(P.z);
+  fe zi2 = fe_sqr(zi);
+  fe px = fe_normalize(fe_mul(P.x, zi2));
+  fe py = fe_normalize(fe_mul(P.y, fe_mul(zi2, zi)));
+  bool same = true;
+#pragma unroll
+  for (int i = 0; i < 8; i++) same = same && (px.v[i] == r.v[i]);  // r < n < p: canonical
+  return same && ((py.v[0] & 1u) == (uint32_t)ri.v);
+}
+
+// the table {1..128}*Q of one validator (affine, 16 words per entry), by repeated addition; each entry normalised with its own
+// inversion (built once per validator, off the hot path)
+IBFT_HD void build_keytab(const aff& Q, uint32_t* out) {
+  jac P;
+  P.x = Q.x; P.y = Q.y; P.z = fe_from_u32(1); P.inf = false;
+  IBFT_ROLLED
+  for (int m = 0; m < IBFT_KEYTAB_ENTRIES; m++) {
+    if (m) P = jac_add_affine(P, Q.x, Q.y);  // the first addition is a doubling (handled by the adder)
+    fe x = fe_zero(), y = fe_zero();
+    if (!P.inf && !fe_is_zero(P.z)) {
+      fe zi = IBFT_FE_INV(P.z), zi2 = fe_sqr(zi);
+      x = fe_normalize(fe_mul(P.x, zi2));
+      y = fe_normalize(fe_mul(P.y, fe_mul(zi2, zi)));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { out[16 * m + i] = x.v[i]; out[16 * m + 8 + i] = y.v[i]; }
+  }
 }
 #endif
 

@@ -32,7 +32,7 @@ EXPORTS = [
     "ibft_abi_version", "ibft_last_error", "ibft_engine_create", "ibft_engine_destroy", "ibft_engine_device_info",
     "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_last_item_status", "ibft_verify_submit", "ibft_verify_poll",
     "ibft_verify_wait", "ibft_bind_groups", "ibft_verify_batch_device", "ibft_quorum_reduce_device", "ibft_quorum_partial_words", "ibft_quorum_mark_device", "ibft_quorum_merge_device",
-    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_set_recover_path", "ibft_probe_int_peak", "ibft_debug_op", "ibft_debug_ctable",
+    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_set_recover_path", "ibft_refresh_key_tables", "ibft_probe_int_peak", "ibft_debug_op", "ibft_debug_ctable",
 ]
 
 
@@ -64,6 +64,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     so = path or os.environ.get("IBFT_LIB") or _build.build()  # IBFT_LIB: kernel-variant experiments (tools/quick_bench.py)
     lib = ctypes.CDLL(so)
     lib.ibft_last_error.restype = c_char_p
+    lib.ibft_refresh_key_tables.restype = c_int
+    lib.ibft_refresh_key_tables.argtypes = [c_void_p, POINTER(c_uint32)]
     lib.ibft_set_recover_path.restype = c_int
     lib.ibft_set_recover_path.argtypes = [c_void_p, c_int]
     lib.ibft_engine_launch_count.restype = c_uint64
@@ -104,9 +106,10 @@ class Engine:
     """One engine per process per GPU (one process per GPU is the deployment model)."""
 
     def __init__(self, device: int = 0, max_items: int = 1 << 16, max_payload_bytes: int = 1 << 24, max_groups: int = 64,
-                 max_table_slots: int = 16, max_validators: int = 16384):
+                 max_table_slots: int = 16, max_validators: int = 16384, key_cache: bool = False):
+        """key_cache: IBFT_FLAG_KEY_CACHE -- verify (instead of recover) signatures of validators whose key is already known."""
         self.lib = load_library()
-        self.params = EngineParams(device, max_items, max_payload_bytes, max_groups, max_table_slots, max_validators, 0)
+        self.params = EngineParams(device, max_items, max_payload_bytes, max_groups, max_table_slots, max_validators, 1 if key_cache else 0)
         self.handle = c_void_p()
         rc = self.lib.ibft_engine_create(ctypes.byref(self.params), ctypes.byref(self.handle))
         if rc != IBFT_OK:
@@ -139,6 +142,12 @@ class Engine:
     def set_recover_path(self, path: int) -> None:
         """Kernel selection of the recover step (include/ibft_verify.h IBFT_PATH_*): verdicts are identical on every path."""
         self._check(self.lib.ibft_set_recover_path(self.handle, int(path)))
+
+    def refresh_key_tables(self) -> int:
+        """Key registry upkeep (engine flag key_cache): returns the number of validator keys known so far."""
+        n = c_uint32(0)
+        self._check(self.lib.ibft_refresh_key_tables(self.handle, ctypes.byref(n)))
+        return int(n.value)
 
     def launch_count(self) -> int:
         return int(self.lib.ibft_engine_launch_count(self.handle))

@@ -99,8 +99,15 @@ typedef struct ibft_engine_params {
   uint32_t max_groups;        /* capacity of the groups array of one call */
   uint32_t max_table_slots;   /* number of validator-table slots (heights kept resident) */
   uint32_t max_validators;    /* capacity of one validator table */
-  uint32_t flags;             /* reserved, 0 */
+  uint32_t flags;             /* IBFT_FLAG_* */
 } ibft_engine_params;
+
+/* Engine flag: keep a registry of the validators' public keys.  A key is learned from the first successful recovery of a
+ * signature by that validator; once its table of multiples is built, later signatures by the same validator are VERIFIED
+ * against the key (no square root, no per-signature table, no address hash) instead of recovered.  A signature the
+ * verification rejects is re-checked by the recover path, so every verdict is the recover path's verdict.  Costs 8 KiB of
+ * device memory per validator and table slot; the registry of a slot is emptied by ibft_set_validators. */
+#define IBFT_FLAG_KEY_CACHE 1u
 
 typedef struct ibft_device_info {
   char name[64];
@@ -221,6 +228,11 @@ int ibft_sign_batch(ibft_engine* e, const uint8_t* privkeys, const uint8_t* dige
 #define IBFT_PATH_SPLIT 3
 #define IBFT_PATH_QSPLIT 4
 int ibft_set_recover_path(ibft_engine* e, int path);
+
+/* Key registry (IBFT_FLAG_KEY_CACHE): build the tables of the keys learned since the last call; *n_keys_out = keys known
+ * over all resident tables.  ibft_verify_batch / ibft_verify_wait do this on their way out; users of the device-resident
+ * entry points call it between rounds.  No-op (0 keys) when the flag is off. */
+int ibft_refresh_key_tables(ibft_engine* e, uint32_t* n_keys_out);
 
 /* Number of kernel launches issued by this engine since creation (bench.py reports gpu_launches from it). */
 uint64_t ibft_engine_launch_count(ibft_engine* e);

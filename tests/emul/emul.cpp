@@ -214,6 +214,35 @@ int emul_verify_item_qsplit(const ibft_sig_item* it, const uint8_t* arena, size_
   memcpy(recovered20, addr, 20);
   return memcmp(addr, ri.signer, 20) == 0;
 }
+
+// verification against a known public key: key64 = X || Y big-endian; the table is built here for every call (test only).
+// Returns the verdict of ecdsa_verify_known; *recovers_key = 1 when the recover path yields exactly that key.
+int emul_verify_item_known(const ibft_sig_item* it, const uint8_t* arena, size_t arena_len, const uint8_t* key64, int* recovers_key) {
+  resolved_item ri;
+  bool valid = false;
+  *recovers_key = 0;
+  int st = resolve_item(*it, arena, arena_len, ri, &valid);
+  if (st != IBFT_ITEM_OK) return -1;
+  if (!valid) return 0;
+  gtab_view G = emul_gview();
+  aff Q;
+  Q.x = fe_from_be(key64);
+  Q.y = fe_from_be(key64 + 32);
+  std::vector<uint32_t> kt((size_t)IBFT_KEYTAB_ENTRIES * 16);
+  build_keytab(Q, kt.data());
+  gtab_view Qt{kt.data()};
+  uint32_t rtab[IBFT_RTAB_WORDS];
+  rtab_view T{rtab, 1};
+  uint8_t addr[20];
+  aff K;
+  if (ecrecover_address(ri.r, ri.s, ri.v, ri.z, G, T, addr, &K)) {
+    fe qx = fe_normalize(Q.x), qy = fe_normalize(Q.y);
+    bool same = true;
+    for (int i = 0; i < 8; i++) same = same && K.x.v[i] == qx.v[i] && K.y.v[i] == qy.v[i];
+    *recovers_key = same ? 1 : 0;
+  }
+  return ecdsa_verify_known(ri, G, Qt) ? 1 : 0;
+}
 #endif
 
 void emul_keccak256(const uint8_t* d, uint32_t n, uint8_t* out) { keccak256_bytes(d, n, out); }

@@ -300,3 +300,53 @@ def test_split_pipeline_config2_fixture(emul):
     for i in range(0, len(items), 5):
         a, b = both_paths(emul, items[i:i + 1], a_np, len(arena))
         assert a == b, i
+
+
+# --------------------------------------------------------------- verification against a known (previously recovered) key
+def test_verify_known_key_is_equivalent_to_recovering_that_key(emul):
+    """ecdsa_verify_known(Q) accepts exactly when the recover path yields the key Q (not merely the same address): valid
+    signatures (low and high s, both recovery ids), corrupted ones, a flipped recovery id, another signer's key."""
+    import workloads as wl
+    rnd = random.Random(31)
+    zero = np.zeros(1, np.uint8)
+
+    def run(item, key):
+        rk = ctypes.c_int(0)
+        key64 = key[0].to_bytes(32, "big") + key[1].to_bytes(32, "big")
+        ok = emul.emul_verify_item_known(item.ctypes.data_as(ctypes.c_void_p), zero.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(0), B(key64),
+                                         ctypes.byref(rk))
+        return ok, rk.value
+
+    accepted = 0
+    for i in range(24):
+        d = rnd.getrandbits(256) % (N - 1) + 1
+        Q = ec.point_mul(d, ec.G)
+        dig = keccak256(bytes([i, 9]))
+        sig = wl.sign(d, dig, low_s=bool(i & 1))
+        if i % 3 == 0:  # the high-s twin with the other recovery id is the same signature of the same key
+            s = int.from_bytes(sig[32:64], "big")
+            sig = sig[:32] + (N - s).to_bytes(32, "big") + bytes([sig[64] ^ 1])
+        addr = co.ecrecover_address(dig, sig)
+        assert run(wl.make_item(sig, addr, 0, dig), Q) == (1, 1)
+        accepted += 1
+        # committed-seal kind goes through the same digest resolution
+        ph = keccak256(bytes([i, 3]))
+        sg = wl.sign(d, wl.seal_digest(ph))
+        assert run(wl.make_item(sg, addr, 2, ph), Q) == (1, 1)
+        # flipped recovery id: recovery yields ANOTHER key -> reject
+        flipped = sig[:64] + bytes([sig[64] ^ 1])
+        ok, rk = run(wl.make_item(flipped, addr, 0, dig), Q)
+        assert (ok, rk) == (0, 0)
+        # random corruption: accept <=> recover yields Q
+        bad = bytearray(sig)
+        bad[rnd.randrange(64)] ^= 1 << rnd.randrange(8)
+        ok, rk = run(wl.make_item(bytes(bad), addr, 0, dig), Q)
+        assert ok == rk
+        # somebody else's key
+        Q2 = ec.point_mul(d + 1, ec.G)
+        assert run(wl.make_item(sig, addr, 0, dig), Q2) == (0, 0)
+    assert accepted == 24
+    # out-of-range scalars
+    for r, s, v in [(0, 1, 0), (1, 0, 0), (N, 1, 0), (1, N, 1), (ec.G[0], 1, 2)]:
+        sg = r.to_bytes(32, "big") + s.to_bytes(32, "big") + bytes([v])
+        assert run(wl.make_item(sg, bytes(20), 0, keccak256(b"x")), ec.G)[0] == 0

@@ -1,0 +1,100 @@
+"""Key registry (IBFT_FLAG_KEY_CACHE): signatures of validators whose public key was learned from an earlier successful
+recovery are VERIFIED against that key; every verdict must still be the recover path's verdict (include/ibft_verify.h)."""
+import random
+
+import numpy as np
+import pytest
+
+import ibft_b200 as ib
+import workloads as wl
+from oracle import coracle as co
+from oracle import secp256k1 as ec
+from test_gpu_verify import expected_groups, groups_for, load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(**kw):
+    return ib.Engine(device=0, max_items=1 << 16, max_payload_bytes=1 << 22, max_groups=8, max_table_slots=2, max_validators=16384, **kw)
+
+
+@pytest.mark.parametrize("name", ["config2.npz", "config3.npz"])
+def test_learn_then_verify_gives_the_golden_bitmap(name):
+    d, items = load_fixture(name)
+    eng = make_engine(key_cache=True)
+    try:
+        eng.set_recover_path(ib.Engine.PATH_THREAD)  # the kernel that holds the verify path
+        eng.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+        groups = groups_for(len(d["groups"]))
+        assert eng.refresh_key_tables() == 0
+        bm1, res1, _ = eng.verify_batch(items, d["arena"], groups)          # recover path, keys learned, tables built on the way out
+        assert np.array_equal(bm1, d["bitmap"])
+        known = eng.refresh_key_tables()
+        signers_ok = {bytes(items[i]["signer"]) for i in range(len(items)) if (int(bm1[i >> 5]) >> (i & 31)) & 1}
+        assert known == len(signers_ok) > 0
+        launches = eng.launch_count()
+        bm2, res2, _ = eng.verify_batch(items, d["arena"], groups)          # verify path for every known signer
+        assert np.array_equal(bm2, d["bitmap"])
+        assert res1.tobytes() == res2.tobytes()
+        assert eng.launch_count() - launches <= 3                           # no table rebuild: nothing new was learned
+        # recovered addresses requested: the recover path must be taken (and give the same answers as a plain engine)
+        bm3, _, rec3 = eng.verify_batch(items[:500], d["arena"], groups, want_recovered=True)
+        plain = make_engine()
+        plain.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+        bm4, _, rec4 = plain.verify_batch(items[:500], d["arena"], groups, want_recovered=True)
+        plain.close()
+        assert np.array_equal(bm3, bm4) and np.array_equal(rec3, rec4)
+        # a new validator set empties the registry
+        eng.set_validators(0, int(d["meta"][2]) + 1, d["addrs"], d["powers"])
+        assert eng.refresh_key_tables() == 0
+        bm5, _, _ = eng.verify_batch(items, d["arena"], groups)
+        assert np.array_equal(bm5, d["bitmap"])
+    finally:
+        eng.close()
+
+
+def test_rejected_verifications_fall_back_to_recovery_exactly():
+    """Known validators, then a batch of valid / corrupted / recovery-id-flipped / misattributed signatures: bit-exact with the
+    oracle (which always recovers)."""
+    rnd = random.Random(77)
+    vs = wl.ValidatorSet(11, 64, weighted=True)
+    eng = make_engine(key_cache=True)
+    try:
+        eng.set_recover_path(ib.Engine.PATH_THREAD)
+        eng.set_validators(0, 9, vs.addr_array(), vs.power_array())
+        groups = groups_for(1)
+        # round 1: everybody signs once -> all keys learned
+        dig0 = co.keccak256(b"round-1")
+        warm = np.concatenate([wl.make_item(wl.sign(vs.keys[i], dig0), vs.addrs[i], 0, dig0) for i in range(48)])  # 16 stay unknown
+        bm, _, _ = eng.verify_batch(warm, b"", groups)
+        assert all((int(bm[i >> 5]) >> (i & 31)) & 1 for i in range(48))
+        assert eng.refresh_key_tables() == 48
+        # round 2: a mixed bag
+        rows = []
+        for i in range(64):
+            dig = co.keccak256(bytes([i]) + b"round-2")
+            sig = wl.sign(vs.keys[i], dig, low_s=bool(i & 1))
+            kind = i % 6
+            claimed = vs.addrs[i]
+            if kind == 1:      # corrupted r or s
+                b = bytearray(sig); b[rnd.randrange(64)] ^= 1 << rnd.randrange(8); sig = bytes(b)
+            elif kind == 2:    # flipped recovery id
+                sig = sig[:64] + bytes([sig[64] ^ 1])
+            elif kind == 3:    # signed by i, attributed to another (known) validator
+                claimed = vs.addrs[(i + 1) % 48]
+            elif kind == 4:    # high-s twin: same key, other recovery id -> still valid
+                s = int.from_bytes(sig[32:64], "big")
+                sig = sig[:32] + (ec.N - s).to_bytes(32, "big") + bytes([sig[64] ^ 1])
+            rows.append(wl.make_item(sig, claimed, 0, dig))
+            ph = co.keccak256(bytes([i]) + b"seal")
+            rows.append(wl.make_item(wl.sign(vs.keys[i], wl.seal_digest(ph)), vs.addrs[i], 2, ph))
+        batch = np.concatenate(rows)
+        bm2, res2, _ = eng.verify_batch(batch, b"", groups)
+        want = co.verify_batch(batch, b"", tables=[vs.addr_array()], group_table=[0], n_threads=4)
+        assert np.array_equal(bm2, want)
+        exp, _ = expected_groups(batch, bm2, vs.addr_array(), vs.power_array())
+        nv, nd, power, hq = exp.get(0, (0, 0, 0, False))
+        assert (int(res2[0]["n_valid"]), int(res2[0]["n_distinct"]), bool(res2[0]["has_quorum"])) == (nv, nd, hq)
+        assert eng.refresh_key_tables() == 64      # the 16 late validators were learned in round 2
+    finally:
+        eng.close()
