@@ -534,7 +534,7 @@ IBFT_HD jac ecmult_double(const sc& u1, const sc& u2, const aff& R, const gtab_v
 // streams 2,3 = split of u1.
 #define IBFT_WQ 8
 #define IBFT_KEYTAB_ENTRIES (1 << (IBFT_WQ - 1))
-IBFT_HD jac ecmult_streams_known(const ecmult_digits& dg, const gtab_view& G, const gtab_view& Qt) {
+IBFT_HD jac ecmult_streams_known(const ecmult_digits& dg, const gtab_view& G, const gtab_view& Qt, bool with_g = true) {
   const fe beta = fe_beta();
   jac acc;
   acc.x = fe_zero(); acc.y = fe_zero(); acc.z = fe_zero();
@@ -546,7 +546,7 @@ IBFT_HD jac ecmult_streams_known(const ecmult_digits& dg, const gtab_view& G, co
       for (int t = 0; t < IBFT_WQ; t++) acc = jac_double(acc);
     }
     IBFT_ROLLED
-    for (int s = 0; s < 3; s++) {
+    for (int s = 0; s < (with_g ? 3 : 2); s++) {
       fe x, y;
       bool neg;
       if (s == 2) {

@@ -458,6 +458,38 @@ IBFT_HD bool ecdsa_verify_known(const resolved_item& ri, const gtab_view& G, con
   return same && ((py.v[0] & 1u) == (uint32_t)ri.v);
 }
 
+// The same verification cut between a chain warp and a helper warp (k_verify_split): the helper supplies w = s^-1, the digits
+// of u2 = r w, and later the affine u1*G = (z w) G from the comb tables; the chain walks u2*Q and closes the check.
+IBFT_HD void known_helper_u2(const resolved_item& ri, const sc& w, ecmult_digits& dg) { ecmult_split_into(sc_mul(sc_from_be(ri.r), w), dg, 0); }
+IBFT_HD void known_helper_u1g(const resolved_item& ri, const sc& w, const gtab_view& G, bool& g_inf, fe& gx, fe& gy) {
+  ecmult_digits dg;
+#pragma unroll
+  for (int k = 0; k < 6; k++) dg.ks[0][k] = dg.ks[1][k] = 0;
+  dg.kneg[0] = dg.kneg[1] = false;
+  ecmult_split_into(sc_mul(sc_reduce_once(sc_from_be(ri.z)), w), dg, 2);
+  jac P = ecmult_gen_comb(dg, G);
+  g_inf = P.inf || fe_is_zero(P.z);
+  if (!g_inf) {
+    fe zi = IBFT_FE_INV(P.z), zi2 = fe_sqr(zi);
+    gx = fe_mul(P.x, zi2);
+    gy = fe_mul(P.y, fe_mul(zi2, zi));
+  }
+}
+// chain: acc = u2*Q (Jacobian); accept <=> acc + u1*G == (r, y) with parity(y) == v
+IBFT_HD bool known_chain_finish(jac acc, bool g_inf, const fe& gx, const fe& gy, const resolved_item& ri) {
+  if (!g_inf) acc = jac_add_affine(acc, gx, gy);
+  if (acc.inf || fe_is_zero(acc.z)) return false;
+  fe zi = IBFT_FE_INV(acc.z);
+  fe zi2 = fe_sqr(zi);
+  fe px = fe_normalize(fe_mul(acc.x, zi2));
+  fe py = fe_normalize(fe_mul(acc.y, fe_mul(zi2, zi)));
+  sc r = sc_from_be(ri.r);
+  bool same = true;
+#pragma unroll
+  for (int i = 0; i < 8; i++) same = same && (px.v[i] == r.v[i]);
+  return same && ((py.v[0] & 1u) == (uint32_t)ri.v);
+}
+
 // the table {1..128}*Q of one validator (affine, 16 words per entry), by repeated addition; each entry normalised with its own
 // inversion (built once per validator, off the hot path)
 IBFT_HD void build_keytab(const aff& Q, uint32_t* out) {

@@ -31,6 +31,9 @@ type Engine struct {
 
 type Params struct {
 	Device, MaxItems, MaxPayloadBytes, MaxGroups, MaxTableSlots, MaxValidators uint32
+	// KeyCache sets IBFT_FLAG_KEY_CACHE: the engine learns every validator's public key from its first valid signature and
+	// verifies (instead of recovering) that validator's later signatures; verdicts are identical.
+	KeyCache bool
 }
 
 func lastError() error { return errors.New(C.GoString(C.ibft_last_error())) }
@@ -41,6 +44,9 @@ func NewEngine(p Params) (*Engine, error) {
 	e.params = C.ibft_engine_params{device: C.int32_t(p.Device), max_items: C.uint32_t(p.MaxItems),
 		max_payload_bytes: C.uint32_t(p.MaxPayloadBytes), max_groups: C.uint32_t(p.MaxGroups),
 		max_table_slots: C.uint32_t(p.MaxTableSlots), max_validators: C.uint32_t(p.MaxValidators)}
+	if p.KeyCache {
+		e.params.flags = C.IBFT_FLAG_KEY_CACHE
+	}
 	if rc := C.ibft_engine_create(&e.params, &e.h); rc != C.IBFT_OK {
 		return nil, fmt.Errorf("ibft_engine_create: %w", lastError())
 	}

@@ -241,7 +241,24 @@ int emul_verify_item_known(const ibft_sig_item* it, const uint8_t* arena, size_t
     for (int i = 0; i < 8; i++) same = same && K.x.v[i] == qx.v[i] && K.y.v[i] == qy.v[i];
     *recovers_key = same ? 1 : 0;
   }
-  return ecdsa_verify_known(ri, G, Qt) ? 1 : 0;
+  int whole = ecdsa_verify_known(ri, G, Qt) ? 1 : 0;
+  // the chain / helper cut of k_verify_split must give the same answer
+  int cut = 0;
+  if (split_sig_in_range(ri)) {
+    G.host_pos = emul_pos_entry;
+    sc w = IBFT_SC_INV(sc_from_be(ri.s));
+    ecmult_digits dg;
+    for (int k = 0; k < 6; k++) dg.ks[2][k] = dg.ks[3][k] = 0;
+    dg.kneg[2] = dg.kneg[3] = false;
+    known_helper_u2(ri, w, dg);
+    jac acc = ecmult_streams_known(dg, G, Qt, false);
+    bool g_inf = false;
+    fe gx, gy;
+    known_helper_u1g(ri, w, G, g_inf, gx, gy);
+    cut = known_chain_finish(acc, g_inf, gx, gy, ri) ? 1 : 0;
+  }
+  if (cut != whole) return -2;
+  return whole;
 }
 #endif
 
