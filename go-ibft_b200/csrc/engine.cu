@@ -1272,6 +1272,8 @@ struct ibft_engine {
   uint64_t launches = 0;
   int recover_path = IBFT_PATH_AUTO;
   uint32_t* d_worklist = nullptr;  // key-registry path: [0] = count, [1..] = indices left to the recover pass
+  uint32_t* d_learn_counts = nullptr;  // key registry: one "keys learned" counter per table slot (read back in one copy)
+  uint32_t* h_learn_counts = nullptr;  // pinned
   int sm_count = 148;
   const uint8_t* dev_arena = nullptr;
   size_t dev_arena_len = 0;
@@ -1288,11 +1290,13 @@ static void engine_free(ibft_engine* e) {
   for (auto& s : e->slots) {
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_powers) cudaFree(s.d_powers);
-    cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab); cudaFree(s.d_learn_count);
+    cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab);
   }
   cudaFree(e->d_status); cudaFreeHost(e->h_status);
   cudaFree(e->d_ctable);
   cudaFree(e->d_worklist);
+  cudaFree(e->d_learn_counts);
+  cudaFreeHost(e->h_learn_counts);
   cudaFree(e->d_items); cudaFree(e->d_arena); cudaFree(e->d_bitmap); cudaFree(e->d_recovered); cudaFree(e->d_groups);
   cudaFree(e->d_gdev); cudaFree(e->d_results); cudaFree(e->d_voted); cudaFree(e->d_nvalid); cudaFree(e->d_slots);
   cudaFreeHost(e->h_items); cudaFreeHost(e->h_arena); cudaFreeHost(e->h_bitmap); cudaFreeHost(e->h_recovered);
@@ -1316,7 +1320,12 @@ static int engine_alloc(ibft_engine* e) {
   CU(cudaEventCreateWithFlags(&e->done_ev, cudaEventDisableTiming));
   size_t n = p.max_items, words = (n + 31) / 32;
   CU(cudaMalloc(&e->d_items, n * sizeof(ibft_sig_item)));
-  if (p.flags & IBFT_FLAG_KEY_CACHE) CU(cudaMalloc(&e->d_worklist, (n + 1) * 4));
+  if (p.flags & IBFT_FLAG_KEY_CACHE) {
+    CU(cudaMalloc(&e->d_worklist, (n + 1) * 4));
+    CU(cudaMalloc(&e->d_learn_counts, (size_t)p.max_table_slots * 4));
+    CU(cudaMemset(e->d_learn_counts, 0, (size_t)p.max_table_slots * 4));
+    CU(cudaHostAlloc(&e->h_learn_counts, (size_t)p.max_table_slots * 4, cudaHostAllocDefault));
+  }
   CU(cudaMalloc(&e->d_arena, std::max<size_t>(p.max_payload_bytes, 16)));
   CU(cudaMalloc(&e->d_bitmap, std::max<size_t>(words, 1) * 4));
   CU(cudaMalloc(&e->d_recovered, n * 20));
@@ -1500,7 +1509,7 @@ extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t
   CU(cudaStreamSynchronize(e->stream));
   if (s.d_keys) { cudaFree(s.d_keys); s.d_keys = nullptr; }
   if (s.d_powers) { cudaFree(s.d_powers); s.d_powers = nullptr; }
-  cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab); cudaFree(s.d_learn_count);
+  cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab);
   s.d_key_state = s.d_key_xy = s.d_key_tab = s.d_learn_count = nullptr;
   s.built_count = 0;
   s.valid = false;
@@ -1519,7 +1528,7 @@ extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t
     CU(cudaMalloc(&s.d_key_state, (size_t)n * 4));
     CU(cudaMalloc(&s.d_key_xy, (size_t)n * 64));
     CU(cudaMalloc(&s.d_key_tab, (size_t)n * IBFT_KEYTAB_ENTRIES * 64));
-    CU(cudaMalloc(&s.d_learn_count, 4));
+    s.d_learn_count = e->d_learn_counts + table_slot;
     CU(cudaMemset(s.d_key_state, 0, (size_t)n * 4));
     CU(cudaMemset(s.d_learn_count, 0, 4));
   }
@@ -1545,22 +1554,26 @@ extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t
 static int refresh_key_tables_locked(ibft_engine* e, uint32_t* n_ready_out) {
   uint32_t total = 0;
 #if IBFT_WC > 0
-  if (e->p.flags & IBFT_FLAG_KEY_CACHE) {
+  if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && e->d_learn_counts) {
     CU(cudaSetDevice(e->p.device));
+    CU(cudaMemcpyAsync(e->h_learn_counts, e->d_learn_counts, (size_t)e->p.max_table_slots * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    bool built = false;
     for (uint32_t slot = 0; slot < e->p.max_table_slots; slot++) {
       slot_host& s = e->slots[slot];
       if (!s.valid || !s.d_learn_count) continue;
-      uint32_t learned = 0;
-      CU(cudaMemcpyAsync(&learned, s.d_learn_count, 4, cudaMemcpyDeviceToHost, e->stream));
-      CU(cudaStreamSynchronize(e->stream));
+      uint32_t learned = e->h_learn_counts[slot];
       if (learned > s.built_count) {
         k_build_keytabs<<<(s.n + 63) / 64, 64, 0, e->stream>>>(e->d_slots, slot);
         e->launches++;
         CU(cudaGetLastError());
         s.built_count = learned;
+        built = true;
       }
       total += learned;
     }
+    // the tables are complete before anybody can launch the next round on another stream
+    if (built) CU(cudaStreamSynchronize(e->stream));
   }
 #endif
   if (n_ready_out) *n_ready_out = total;
@@ -1648,26 +1661,28 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
     uint32_t blocks = (cnt + IBFT_QUAD_SIGS - 1) / IBFT_QUAD_SIGS;
     k_recover_quad<<<blocks, 4 * IBFT_QUAD_SIGS, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                                          e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
-  } else if (cnt <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs
+  } else
+#if IBFT_WC > 0
+  if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && d_recovered == nullptr && d_groups != nullptr && e->d_worklist != nullptr) {
+    // key-registry path (one thread per signature, any batch size): verify what can be verified, then recover the rest from
+    // the worklist (dense second launch; the threads beyond the worklist's length leave at once)
+    uint32_t blocks = (cnt + IBFT_BLOCK - 1) / IBFT_BLOCK;
+    CU(cudaMemsetAsync(e->d_worklist, 0, 4, st));
+    k_verify_known<<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+                                                  e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink, e->d_worklist);
+    e->launches++;
+    CU(cudaGetLastError());
+    k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
+                                                         e->d_slots, e->p.max_table_slots, d_bitmap, nullptr, nullptr, e->d_ctable, sink,
+                                                         e->d_worklist);
+  } else
+#endif
+  if (cnt <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs
     uint32_t blocks = (cnt + 31) / 32;
     k_recover<32><<<blocks, 32, 32 * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                          e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink, nullptr);
   } else {
     uint32_t blocks = (cnt + IBFT_BLOCK - 1) / IBFT_BLOCK;
-#if IBFT_WC > 0
-    if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && d_recovered == nullptr && d_groups != nullptr && e->d_worklist != nullptr) {
-      // key-registry path: verify what can be verified, then recover the rest from the worklist (dense second launch; the
-      // threads beyond the worklist's length leave at once)
-      CU(cudaMemsetAsync(e->d_worklist, 0, 4, st));
-      k_verify_known<<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                                    e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink, e->d_worklist);
-      e->launches++;
-      CU(cudaGetLastError());
-      k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
-                                                           e->d_slots, e->p.max_table_slots, d_bitmap, nullptr, nullptr, e->d_ctable, sink,
-                                                           e->d_worklist);
-    } else
-#endif
     k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                                          e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink, nullptr);
   }
