@@ -321,6 +321,9 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = n_global * e2e_steps / float(e2e_dt[0])
+    e2e_bits_ok = bool(np.array_equal(np.unpackbits(bm_local.view(np.uint8), bitorder="little")[: hi - lo], np.tile(golden_bits, reps)[lo:hi]))
+    if not e2e_bits_ok:
+        raise SystemExit("bench: e2e leg: verdict bitmap differs from the golden bitmap -- refusing to report a number")
     h2d = host_local.nbytes + arena_host.nbytes + groups.nbytes
     d2h = (n_local // 8) + n_local + len(groups) * ib.RESULT_DTYPE.itemsize  # bitmap + per-item status bytes + quorum results
 

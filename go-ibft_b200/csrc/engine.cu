@@ -1321,7 +1321,7 @@ static int engine_alloc(ibft_engine* e) {
   size_t n = p.max_items, words = (n + 31) / 32;
   CU(cudaMalloc(&e->d_items, n * sizeof(ibft_sig_item)));
   if (p.flags & IBFT_FLAG_KEY_CACHE) {
-    CU(cudaMalloc(&e->d_worklist, (n + 1) * 4));
+    CU(cudaMalloc(&e->d_worklist, 2 * (n + 1) * 4));  // two lists: consecutive chunks of a large host batch run on two streams
     CU(cudaMalloc(&e->d_learn_counts, (size_t)p.max_table_slots * 4));
     CU(cudaMemset(e->d_learn_counts, 0, (size_t)p.max_table_slots * 4));
     CU(cudaHostAlloc(&e->h_learn_counts, (size_t)p.max_table_slots * 4, cudaHostAllocDefault));
@@ -1623,8 +1623,9 @@ static int plan_groups(ibft_engine* e, const ibft_group_desc* groups, uint32_t n
 static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len,
                           uint32_t lo, uint32_t hi, const ibft_group_desc* d_groups, uint32_t n_groups, uint32_t* d_bitmap,
                           uint8_t* d_recovered, cudaStream_t st, uint8_t* d_status = nullptr, int forced_path = IBFT_PATH_AUTO,
-                          vote_sink sink = vote_sink{nullptr, nullptr, nullptr}) {
+                          vote_sink sink = vote_sink{nullptr, nullptr, nullptr}, uint32_t worklist_index = 0) {
   if (hi <= lo) return IBFT_OK;
+  uint32_t* const worklist = e->d_worklist ? e->d_worklist + (size_t)worklist_index * ((size_t)e->p.max_items + 1) : nullptr;
   // path selection (ibft_set_recover_path).  AUTO picks by how many warps each of the SM's four schedulers would hold
   // (B200, kernel time of one batch: profiles/latency_r01_v9.md):
   //   <= SMs x 24 signatures   four-lane chain warps + helper warp, one CTA (3 + 1 warps) per SM                   0.41 ms
@@ -1667,14 +1668,14 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
     // key-registry path (one thread per signature, any batch size): verify what can be verified, then recover the rest from
     // the worklist (dense second launch; the threads beyond the worklist's length leave at once)
     uint32_t blocks = (cnt + IBFT_BLOCK - 1) / IBFT_BLOCK;
-    CU(cudaMemsetAsync(e->d_worklist, 0, 4, st));
+    CU(cudaMemsetAsync(worklist, 0, 4, st));
     k_verify_known<<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                                  e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink, e->d_worklist);
+                                                  e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink, worklist);
     e->launches++;
     CU(cudaGetLastError());
     k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
                                                          e->d_slots, e->p.max_table_slots, d_bitmap, nullptr, nullptr, e->d_ctable, sink,
-                                                         e->d_worklist);
+                                                         worklist);
   } else
 #endif
   if (cnt <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs
@@ -1806,6 +1807,13 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
     if (cudaPointerGetAttributes(&pa, items) == cudaSuccess) caller_pinned = pa.type == cudaMemoryTypeHost;
     else (void)cudaGetLastError();
   }
+  // Several chunks: chunk c's kernels run on one of two alternating streams, so that the tail of one chunk (the last CTAs of a
+  // 1,024-CTA launch on 444 resident slots) overlaps the head of the next instead of idling the SMs eight times per batch.
+  if (n_chunks > 1) {
+    CU(cudaEventRecord(e->lat_ev[4], st));  // arena / groups uploads and the vote-sink memsets of this call
+    CU(cudaStreamWaitEvent(e->lat_stream[0], e->lat_ev[4], 0));
+    CU(cudaStreamWaitEvent(e->lat_stream[1], e->lat_ev[4], 0));
+  }
   for (uint32_t c = 0; c < n_chunks; c++) {
     uint32_t lo = c * CHUNK, hi = std::min(n, lo + CHUNK);
     const ibft_sig_item* src = items + lo;
@@ -1814,14 +1822,21 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
       src = e->h_items + lo;
     }
     cudaStream_t cs = n_chunks > 1 ? e->copy_stream : st;
+    cudaStream_t ks = n_chunks > 1 ? e->lat_stream[c & 1u] : st;
     CU(cudaMemcpyAsync(e->d_items + lo, src, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, cs));
     if (n_chunks > 1) {
       CU(cudaEventRecord(e->chunk_ev[c], cs));
-      CU(cudaStreamWaitEvent(st, e->chunk_ev[c], 0));
+      CU(cudaStreamWaitEvent(ks, e->chunk_ev[c], 0));
     }
     rc = launch_recover(e, e->d_items, n, e->d_arena, arena_len, lo, hi, n_groups ? e->d_groups : nullptr, n_groups, e->d_bitmap,
-                        recovered_out ? e->d_recovered : nullptr, st, e->d_status, IBFT_PATH_AUTO, sink);
+                        recovered_out ? e->d_recovered : nullptr, ks, e->d_status, IBFT_PATH_AUTO, sink, c & 1u);
     if (rc != IBFT_OK) return rc;
+  }
+  if (n_chunks > 1) {
+    for (int k = 0; k < 2; k++) {
+      CU(cudaEventRecord(e->lat_ev[k], e->lat_stream[k]));
+      CU(cudaStreamWaitEvent(st, e->lat_ev[k], 0));
+    }
   }
   if (n_groups && results_out) {
     rc = launch_quorum(e, e->d_items, n, e->d_arena, arena_len, e->d_bitmap, e->d_groups, e->d_gdev, n_groups, voted_words, e->d_results, st,
