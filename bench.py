@@ -176,6 +176,11 @@ def workload_config(n_gpus):
             "l2": "inputs (128 MiB of tuples per GPU) exceed the 126 MB L2; no flush needed"}
 
 
+# rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on the GPU boxes) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
