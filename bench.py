@@ -218,7 +218,7 @@ def main():
     eng = ib.Engine(device=local_rank, max_items=n_local, max_payload_bytes=max(1 << 22, len(d["arena"])), max_groups=8,
                     max_table_slots=2, max_validators=16384)
     eng.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
-    groups = np.zeros(len(d["groups"]), dtype=ib.GROUP_DTYPE)
+    groups = eng.groups(len(d["groups"]))
     eng.bind_groups(groups)
 
     # ---- device-resident inputs (every rank holds the global tuple array: the quorum kernels read every signer)

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,7 @@
 using namespace ibft;
 
 static_assert(sizeof(ibft_sig_item) == 128, "packed item must be 128 bytes");
+static_assert(sizeof(ibft_group_desc) == 16, "group descriptor must be 16 bytes");
 static_assert(IBFT_GTABLE_WG == IBFT_WG, "regenerate secp_gtable.inc (tools/gen_tables.py) for this IBFT_WG");
 
 #define IBFT_BLOCK 128
@@ -311,7 +313,8 @@ k_verify_known(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
         ok = ecdsa_verify_known(ri, G, Qt);
       }
       if (ok) record_vote(sink, groups, it.group, v);
-      else worklist[1 + atomicAdd(&worklist[0], 1u)] = idx;  // key unknown, or rejected: the recover pass decides
+      else worklist[1 + atomicAdd(&worklist[0], 1u)] = idx;  // key unknown, or rejected: the recover pass decides (the host
+                                                             // only takes this path when the shard fits the worklist)
     }
   }
   uint32_t word = __ballot_sync(0xFFFFFFFFu, ok);
@@ -959,15 +962,28 @@ k_quorum_reduce(const ibft_group_desc* __restrict__ groups, const group_dev* __r
 // hash-only batch (IsValidProposalHash)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_keccak_batch(const uint8_t* __restrict__ arena, size_t arena_len, const uint32_t* __restrict__ offs,
-                               const uint32_t* __restrict__ lens, uint32_t n, uint8_t* __restrict__ out) {
+                               const uint32_t* __restrict__ lens, const uint64_t* __restrict__ rounds, uint32_t n,
+                               uint8_t* __restrict__ out) {
+  // rounds == nullptr: out[i] = Keccak-256(message i).
+  // rounds != nullptr: the proposal hash of this engine's synthetic convention, both sponges in ONE launch:
+  //                    out[i] = Keccak-256(Keccak-256(rawProposal_i) || u64_be(round_i))   (IsValidProposalHash)
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint8_t h[32];
+  uint8_t h[40];
   if ((size_t)offs[i] + lens[i] > arena_len) {
 #pragma unroll
     for (int k = 0; k < 32; k++) h[k] = 0;
   } else {
     keccak256_bytes(arena + offs[i], lens[i], h);
+    if (rounds != nullptr) {
+      uint64_t r = rounds[i];
+#pragma unroll
+      for (int k = 0; k < 8; k++) h[32 + k] = (uint8_t)(r >> (8 * (7 - k)));
+      uint8_t h2[32];
+      keccak256_bytes(h, 40, h2);
+#pragma unroll
+      for (int k = 0; k < 32; k++) h[k] = h2[k];
+    }
   }
 #pragma unroll
   for (int k = 0; k < 32; k++) out[(size_t)i * 32 + k] = h[k];
@@ -1232,9 +1248,19 @@ struct pending_call {
   uint8_t* recovered_out = nullptr;
 };
 
-struct ibft_engine {
-  ibft_engine_params p;
+// One LANE = everything a host-buffer verify call needs while it is in flight: streams, events, device buffers, pinned
+// staging.  The engine has two, so that two handlers do not serialise (the reference runs the COMMIT fan-in, a ROUND_CHANGE
+// watcher and the gossip ingress concurrently: core/ibft.go:335-347, :1128):
+//   lane 0  full capacity (max_items): bulk handler batches, the async submit/poll/wait API, the device-resident entry points;
+//   lane 1  a small lane (IBFT_LANE1_ITEMS) for the ingress coalescer's batches and other small concurrent calls.
+// A call holds its lane's mutex from staging to the copy-out; validator tables and the key registry are shared.
+#define IBFT_LANES 2
+#define IBFT_LANE1_ITEMS 16384u
+#define IBFT_LANE1_ARENA (4u << 20)
+struct lane {
   std::mutex mu;
+  uint32_t cap_items = 0;
+  size_t cap_arena = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;       // H2D of chunk k+1 overlaps the recover kernel of chunk k
   std::vector<cudaEvent_t> chunk_ev;
@@ -1254,7 +1280,6 @@ struct ibft_engine {
   ibft_group_result* d_results = nullptr;
   uint32_t* d_voted = nullptr;
   uint32_t* d_nvalid = nullptr;
-  slot_dev* d_slots = nullptr;
   size_t voted_words_cap = 0;
   // pinned host staging
   ibft_sig_item* h_items = nullptr;
@@ -1264,88 +1289,134 @@ struct ibft_engine {
   ibft_group_desc* h_groups = nullptr;
   group_dev* h_gdev = nullptr;
   ibft_group_result* h_results = nullptr;
-  std::vector<slot_host> slots;
-  std::vector<slot_dev> slots_shadow;
   std::vector<group_dev> last_gdev;  // layout of the voted sets of the most recent reduce
   std::vector<ibft_group_desc> last_groups;
   pending_call pending;
-  uint64_t launches = 0;
-  int recover_path = IBFT_PATH_AUTO;
   uint32_t* d_worklist = nullptr;  // key-registry path: [0] = count, [1..] = indices left to the recover pass
+  cudaEvent_t wl_ev[2] = {nullptr, nullptr};  // last use of each worklist (orders launches that arrive on different streams)
+  const uint8_t* dev_arena = nullptr;
+  size_t dev_arena_len = 0;
+};
+
+struct ibft_engine {
+  ibft_engine_params p;
+  lane lanes[IBFT_LANES];
+  std::atomic<int> last_lane{0};  // lane of the most recently COMPLETED host-buffer call (ibft_last_item_status, ibft_get_voted_bitmap)
+  slot_dev* d_slots = nullptr;
+  std::vector<slot_host> slots;
+  std::vector<slot_dev> slots_shadow;
+  std::atomic<uint64_t> launches{0};
+  std::atomic<int> recover_path{IBFT_PATH_AUTO};
+  std::mutex keys_mu;                  // key registry upkeep (built_count, h_learn_counts)
   uint32_t* d_learn_counts = nullptr;  // key registry: one "keys learned" counter per table slot (read back in one copy)
   uint32_t* h_learn_counts = nullptr;  // pinned
   int sm_count = 148;
-  const uint8_t* dev_arena = nullptr;
-  size_t dev_arena_len = 0;
   uint32_t* d_ctable = nullptr;  // combined generator table (IBFT_WC > 0)
   cudaFuncAttributes recover_attr{};
+  // hashing (ibft_keccak256_batch / ibft_proposal_hash_batch): own lock, own stream, own grow-only scratch -- a hash call
+  // never waits for a verify call and never allocates on the per-call path
+  std::mutex hash_mu;
+  cudaStream_t hash_stream = nullptr;
+  uint8_t *hs_arena = nullptr, *hs_h_arena = nullptr, *hs_meta = nullptr, *hs_h_meta = nullptr;
+  size_t hs_arena_cap = 0;
+  uint32_t hs_n_cap = 0;
+};
+// every lane, in index order (validator-table replacement and other engine-wide operations)
+struct all_lanes_lock {
+  ibft_engine* e;
+  explicit all_lanes_lock(ibft_engine* e_) : e(e_) { for (auto& L : e->lanes) L.mu.lock(); }
+  ~all_lanes_lock() { for (int i = IBFT_LANES - 1; i >= 0; i--) e->lanes[i].mu.unlock(); }
 };
 
 extern "C" int ibft_abi_version(void) { return IBFT_ABI_VERSION; }
 extern "C" const char* ibft_last_error(void) { return tl_err; }
 
+static void lane_free(lane* L) {
+  cudaFree(L->d_status); cudaFreeHost(L->h_status);
+  cudaFree(L->d_worklist);
+  cudaFree(L->d_items); cudaFree(L->d_arena); cudaFree(L->d_bitmap); cudaFree(L->d_recovered); cudaFree(L->d_groups);
+  cudaFree(L->d_gdev); cudaFree(L->d_results); cudaFree(L->d_voted); cudaFree(L->d_nvalid);
+  cudaFreeHost(L->h_items); cudaFreeHost(L->h_arena); cudaFreeHost(L->h_bitmap); cudaFreeHost(L->h_recovered);
+  cudaFreeHost(L->h_groups); cudaFreeHost(L->h_gdev); cudaFreeHost(L->h_results);
+  if (L->done_ev) cudaEventDestroy(L->done_ev);
+  for (auto ev : L->chunk_ev) cudaEventDestroy(ev);
+  if (L->copy_stream) cudaStreamDestroy(L->copy_stream);
+  for (auto ls : L->lat_stream) if (ls) cudaStreamDestroy(ls);
+  for (auto ev : L->lat_ev) if (ev) cudaEventDestroy(ev);
+  for (auto ev : L->wl_ev) if (ev) cudaEventDestroy(ev);
+  if (L->stream) cudaStreamDestroy(L->stream);
+}
+
 static void engine_free(ibft_engine* e) {
   if (!e) return;
   cudaSetDevice(e->p.device);
+  cudaDeviceSynchronize();
   for (auto& s : e->slots) {
     if (s.d_keys) cudaFree(s.d_keys);
     if (s.d_powers) cudaFree(s.d_powers);
     cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab);
   }
-  cudaFree(e->d_status); cudaFreeHost(e->h_status);
+  for (auto& L : e->lanes) lane_free(&L);
   cudaFree(e->d_ctable);
-  cudaFree(e->d_worklist);
   cudaFree(e->d_learn_counts);
   cudaFreeHost(e->h_learn_counts);
-  cudaFree(e->d_items); cudaFree(e->d_arena); cudaFree(e->d_bitmap); cudaFree(e->d_recovered); cudaFree(e->d_groups);
-  cudaFree(e->d_gdev); cudaFree(e->d_results); cudaFree(e->d_voted); cudaFree(e->d_nvalid); cudaFree(e->d_slots);
-  cudaFreeHost(e->h_items); cudaFreeHost(e->h_arena); cudaFreeHost(e->h_bitmap); cudaFreeHost(e->h_recovered);
-  cudaFreeHost(e->h_groups); cudaFreeHost(e->h_gdev); cudaFreeHost(e->h_results);
-  if (e->done_ev) cudaEventDestroy(e->done_ev);
-  for (auto ev : e->chunk_ev) cudaEventDestroy(ev);
-  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-  for (auto ls : e->lat_stream) if (ls) cudaStreamDestroy(ls);
-  for (auto ev : e->lat_ev) if (ev) cudaEventDestroy(ev);
-  if (e->stream) cudaStreamDestroy(e->stream);
+  cudaFree(e->d_slots);
+  if (e->hash_stream) cudaStreamDestroy(e->hash_stream);
+  cudaFree(e->hs_arena); cudaFreeHost(e->hs_h_arena); cudaFree(e->hs_meta); cudaFreeHost(e->hs_h_meta);
   delete e;
+}
+
+static int lane_alloc(ibft_engine* e, lane* L, uint32_t cap_items, size_t cap_arena) {
+  const ibft_engine_params& p = e->p;
+  L->cap_items = cap_items;
+  L->cap_arena = cap_arena;
+  CU(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&L->copy_stream, cudaStreamNonBlocking));
+  for (auto& ls : L->lat_stream) CU(cudaStreamCreateWithFlags(&ls, cudaStreamNonBlocking));
+  for (auto& ev : L->lat_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : L->wl_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&L->done_ev, cudaEventDisableTiming));
+  size_t n = cap_items, words = (n + 31) / 32;
+  CU(cudaMalloc(&L->d_items, n * sizeof(ibft_sig_item)));
+  if (p.flags & IBFT_FLAG_KEY_CACHE)
+    CU(cudaMalloc(&L->d_worklist, 2 * (n + 1) * 4));  // two lists: consecutive chunks of a large host batch run on two streams
+  CU(cudaMalloc(&L->d_arena, std::max<size_t>(cap_arena, 16)));
+  CU(cudaMalloc(&L->d_bitmap, std::max<size_t>(words, 1) * 4));
+  CU(cudaMalloc(&L->d_recovered, n * 20));
+  CU(cudaMalloc(&L->d_status, n));
+  CU(cudaHostAlloc(&L->h_status, n, cudaHostAllocDefault));
+  CU(cudaMalloc(&L->d_groups, (size_t)p.max_groups * sizeof(ibft_group_desc)));
+  CU(cudaMalloc(&L->d_gdev, (size_t)p.max_groups * sizeof(group_dev)));
+  CU(cudaMalloc(&L->d_results, (size_t)p.max_groups * sizeof(ibft_group_result)));
+  L->voted_words_cap = (size_t)p.max_groups * ((p.max_validators + 31) / 32);
+  CU(cudaMalloc(&L->d_voted, std::max<size_t>(L->voted_words_cap, 1) * 4));
+  CU(cudaMalloc(&L->d_nvalid, (size_t)p.max_groups * 4));
+  CU(cudaHostAlloc(&L->h_items, n * sizeof(ibft_sig_item), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&L->h_arena, std::max<size_t>(cap_arena, 16), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&L->h_bitmap, std::max<size_t>(words, 1) * 4, cudaHostAllocDefault));
+  CU(cudaHostAlloc(&L->h_recovered, n * 20, cudaHostAllocDefault));
+  CU(cudaHostAlloc(&L->h_groups, (size_t)p.max_groups * sizeof(ibft_group_desc), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&L->h_gdev, (size_t)p.max_groups * sizeof(group_dev), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&L->h_results, (size_t)p.max_groups * sizeof(ibft_group_result), cudaHostAllocDefault));
+  return IBFT_OK;
 }
 
 static int engine_alloc(ibft_engine* e) {
   const ibft_engine_params& p = e->p;
   CU(cudaSetDevice(p.device));
-  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-  for (auto& ls : e->lat_stream) CU(cudaStreamCreateWithFlags(&ls, cudaStreamNonBlocking));
-  for (auto& ev : e->lat_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&e->done_ev, cudaEventDisableTiming));
-  size_t n = p.max_items, words = (n + 31) / 32;
-  CU(cudaMalloc(&e->d_items, n * sizeof(ibft_sig_item)));
+  CU(cudaStreamCreateWithFlags(&e->hash_stream, cudaStreamNonBlocking));
+  int rc = lane_alloc(e, &e->lanes[0], p.max_items, p.max_payload_bytes);
+  if (rc != IBFT_OK) return rc;
+  rc = lane_alloc(e, &e->lanes[1], std::min<uint32_t>(p.max_items, IBFT_LANE1_ITEMS), std::min<size_t>(p.max_payload_bytes, IBFT_LANE1_ARENA));
+  if (rc != IBFT_OK) return rc;
+  lane* L = &e->lanes[0];
   if (p.flags & IBFT_FLAG_KEY_CACHE) {
-    CU(cudaMalloc(&e->d_worklist, 2 * (n + 1) * 4));  // two lists: consecutive chunks of a large host batch run on two streams
     CU(cudaMalloc(&e->d_learn_counts, (size_t)p.max_table_slots * 4));
     CU(cudaMemset(e->d_learn_counts, 0, (size_t)p.max_table_slots * 4));
     CU(cudaHostAlloc(&e->h_learn_counts, (size_t)p.max_table_slots * 4, cudaHostAllocDefault));
   }
-  CU(cudaMalloc(&e->d_arena, std::max<size_t>(p.max_payload_bytes, 16)));
-  CU(cudaMalloc(&e->d_bitmap, std::max<size_t>(words, 1) * 4));
-  CU(cudaMalloc(&e->d_recovered, n * 20));
-  CU(cudaMalloc(&e->d_status, n));
-  CU(cudaHostAlloc(&e->h_status, n, cudaHostAllocDefault));
-  CU(cudaMalloc(&e->d_groups, (size_t)p.max_groups * sizeof(ibft_group_desc)));
-  CU(cudaMalloc(&e->d_gdev, (size_t)p.max_groups * sizeof(group_dev)));
-  CU(cudaMalloc(&e->d_results, (size_t)p.max_groups * sizeof(ibft_group_result)));
-  e->voted_words_cap = (size_t)p.max_groups * ((p.max_validators + 31) / 32);
-  CU(cudaMalloc(&e->d_voted, std::max<size_t>(e->voted_words_cap, 1) * 4));
-  CU(cudaMalloc(&e->d_nvalid, (size_t)p.max_groups * 4));
   CU(cudaMalloc(&e->d_slots, (size_t)p.max_table_slots * sizeof(slot_dev)));
   CU(cudaMemset(e->d_slots, 0, (size_t)p.max_table_slots * sizeof(slot_dev)));
-  CU(cudaHostAlloc(&e->h_items, n * sizeof(ibft_sig_item), cudaHostAllocDefault));
-  CU(cudaHostAlloc(&e->h_arena, std::max<size_t>(p.max_payload_bytes, 16), cudaHostAllocDefault));
-  CU(cudaHostAlloc(&e->h_bitmap, std::max<size_t>(words, 1) * 4, cudaHostAllocDefault));
-  CU(cudaHostAlloc(&e->h_recovered, n * 20, cudaHostAllocDefault));
-  CU(cudaHostAlloc(&e->h_groups, (size_t)p.max_groups * sizeof(ibft_group_desc), cudaHostAllocDefault));
-  CU(cudaHostAlloc(&e->h_gdev, (size_t)p.max_groups * sizeof(group_dev), cudaHostAllocDefault));
-  CU(cudaHostAlloc(&e->h_results, (size_t)p.max_groups * sizeof(ibft_group_result), cudaHostAllocDefault));
   e->slots.resize(p.max_table_slots);
   e->slots_shadow.assign(p.max_table_slots, slot_dev{});
   CU(cudaMemcpyToSymbol(g_gtable, IBFT_GTABLE, sizeof(uint32_t) * IBFT_GTAB_ENTRY_WORDS * IBFT_GTAB_ENTRIES));
@@ -1366,7 +1437,7 @@ static int engine_alloc(ibft_engine* e) {
     // latency kernel's helper warps (36 MB in all, L2-resident while a round is being verified)
     size_t entries = (size_t)IBFT_CTAB_ENTRIES;
     CU(cudaMalloc(&e->d_ctable, (size_t)IBFT_CTAB_POSITIONS * entries * IBFT_GTAB_ENTRY_WORDS * 4));
-    k_build_ctable<<<dim3((unsigned)((entries + 63) / 64), IBFT_CTAB_POSITIONS), 64, 0, e->stream>>>(e->d_ctable);
+    k_build_ctable<<<dim3((unsigned)((entries + 63) / 64), IBFT_CTAB_POSITIONS), 64, 0, L->stream>>>(e->d_ctable);
     e->launches++;
     CU(cudaGetLastError());
   }
@@ -1384,7 +1455,6 @@ extern "C" int ibft_debug_ctable(ibft_engine* e, uint32_t first, uint32_t count,
   if (entries) *entries = (uint32_t)IBFT_CTAB_ENTRIES;
   if (count == 0) return IBFT_OK;
   if (!out || (size_t)first + count > (size_t)IBFT_CTAB_ENTRIES) { set_err("range"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
   CU(cudaSetDevice(e->p.device));
   CU(cudaMemcpy(out, e->d_ctable + (size_t)first * IBFT_GTAB_ENTRY_WORDS, (size_t)count * 64, cudaMemcpyDeviceToHost));
   return IBFT_OK;
@@ -1503,10 +1573,13 @@ extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t
       keys[6 * (size_t)r + w] = ((uint32_t)a[4 * w] << 24) | ((uint32_t)a[4 * w + 1] << 16) | ((uint32_t)a[4 * w + 2] << 8) | a[4 * w + 3];
     keys[6 * (size_t)r + 5] = order[r];
   }
-  std::lock_guard<std::mutex> lk(e->mu);
+  // replacing a table frees device memory the kernels of ANY lane may be reading: take every lane and drain the device
+  all_lanes_lock lk(e);
+  for (auto& L : e->lanes)
+    if (L.pending.active) { set_err("a submitted call is still pending; wait for it first"); return IBFT_ERR_INVALID_ARG; }
   CU(cudaSetDevice(e->p.device));
   slot_host& s = e->slots[table_slot];
-  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaDeviceSynchronize());
   if (s.d_keys) { cudaFree(s.d_keys); s.d_keys = nullptr; }
   if (s.d_powers) { cudaFree(s.d_powers); s.d_powers = nullptr; }
   cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab);
@@ -1551,20 +1624,21 @@ extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t
 // Key registry upkeep: for every resident validator table, build the tables of multiples of the keys learned since the last
 // call.  Cheap when nothing is new (one 4-byte read per slot).  ibft_verify_batch / ibft_verify_wait call it on their way out;
 // callers of the device-resident entry points call it between rounds.
-static int refresh_key_tables_locked(ibft_engine* e, uint32_t* n_ready_out) {
+static int refresh_key_tables_locked(ibft_engine* e, lane* L, uint32_t* n_ready_out) {
   uint32_t total = 0;
 #if IBFT_WC > 0
   if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && e->d_learn_counts) {
+    std::lock_guard<std::mutex> kl(e->keys_mu);
     CU(cudaSetDevice(e->p.device));
-    CU(cudaMemcpyAsync(e->h_learn_counts, e->d_learn_counts, (size_t)e->p.max_table_slots * 4, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpyAsync(e->h_learn_counts, e->d_learn_counts, (size_t)e->p.max_table_slots * 4, cudaMemcpyDeviceToHost, L->stream));
+    CU(cudaStreamSynchronize(L->stream));
     bool built = false;
     for (uint32_t slot = 0; slot < e->p.max_table_slots; slot++) {
       slot_host& s = e->slots[slot];
       if (!s.valid || !s.d_learn_count) continue;
       uint32_t learned = e->h_learn_counts[slot];
       if (learned > s.built_count) {
-        k_build_keytabs<<<(s.n + 63) / 64, 64, 0, e->stream>>>(e->d_slots, slot);
+        k_build_keytabs<<<(s.n + 63) / 64, 64, 0, L->stream>>>(e->d_slots, slot);
         e->launches++;
         CU(cudaGetLastError());
         s.built_count = learned;
@@ -1573,7 +1647,7 @@ static int refresh_key_tables_locked(ibft_engine* e, uint32_t* n_ready_out) {
       total += learned;
     }
     // the tables are complete before anybody can launch the next round on another stream
-    if (built) CU(cudaStreamSynchronize(e->stream));
+    if (built) CU(cudaStreamSynchronize(L->stream));
   }
 #endif
   if (n_ready_out) *n_ready_out = total;
@@ -1581,15 +1655,16 @@ static int refresh_key_tables_locked(ibft_engine* e, uint32_t* n_ready_out) {
 }
 extern "C" int ibft_refresh_key_tables(ibft_engine* e, uint32_t* n_keys_out) {
   if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  if (e->pending.active) { set_err("a submitted call is still pending"); return IBFT_ERR_INVALID_ARG; }
-  return refresh_key_tables_locked(e, n_keys_out);
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
+  if (L->pending.active) { set_err("a submitted call is still pending"); return IBFT_ERR_INVALID_ARG; }
+  return refresh_key_tables_locked(e, L, n_keys_out);
 }
 
 extern "C" int ibft_get_quorum(ibft_engine* e, uint32_t table_slot, uint64_t quorum_out[5], uint64_t* height_out,
                                uint32_t* n_out) {
   if (!e || table_slot >= e->p.max_table_slots) { set_err("bad slot"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
+  std::lock_guard<std::mutex> lk(e->lanes[0].mu);
   const slot_host& s = e->slots[table_slot];
   if (!s.valid) { set_err("slot %u not set", table_slot); return IBFT_ERR_NO_TABLE; }
   if (quorum_out) memcpy(quorum_out, s.quorum, sizeof s.quorum);
@@ -1599,7 +1674,7 @@ extern "C" int ibft_get_quorum(ibft_engine* e, uint32_t table_slot, uint64_t quo
 }
 
 // lay out the voted sets of the call's groups; validates table slots
-static int plan_groups(ibft_engine* e, const ibft_group_desc* groups, uint32_t n_groups, group_dev* gdev, size_t* total_words) {
+static int plan_groups(ibft_engine* e, lane* L, const ibft_group_desc* groups, uint32_t n_groups, group_dev* gdev, size_t* total_words) {
   size_t off = 0;
   for (uint32_t g = 0; g < n_groups; g++) {
     uint32_t slot = groups[g].table_slot;
@@ -1609,23 +1684,30 @@ static int plan_groups(ibft_engine* e, const ibft_group_desc* groups, uint32_t n
         set_err("group %u references validator-table slot %u which is not set", g, slot);
         return IBFT_ERR_NO_TABLE;
       }
+      // IsValidValidator answers for the validator set AT THE MESSAGE'S HEIGHT (core/backend.go:41-45): a slot that has been
+      // recycled for another height must never answer for this one
+      if (e->slots[slot].height != groups[g].height) {
+        set_err("group %u is for height %llu but validator-table slot %u holds height %llu", g, (unsigned long long)groups[g].height,
+                slot, (unsigned long long)e->slots[slot].height);
+        return IBFT_ERR_NO_TABLE;
+      }
       nw = (e->slots[slot].n + 31) / 32;
     }
     gdev[g].voted_off = (uint32_t)off;
     gdev[g].n_words = nw;
     off += nw;
   }
-  if (off > e->voted_words_cap) { set_err("voted sets of the call exceed capacity"); return IBFT_ERR_CAPACITY; }
+  if (off > L->voted_words_cap) { set_err("voted sets of the call exceed capacity"); return IBFT_ERR_CAPACITY; }
   *total_words = off;
   return IBFT_OK;
 }
 
-static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len,
+static int launch_recover(ibft_engine* e, lane* L, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len,
                           uint32_t lo, uint32_t hi, const ibft_group_desc* d_groups, uint32_t n_groups, uint32_t* d_bitmap,
                           uint8_t* d_recovered, cudaStream_t st, uint8_t* d_status = nullptr, int forced_path = IBFT_PATH_AUTO,
                           vote_sink sink = vote_sink{nullptr, nullptr, nullptr}, uint32_t worklist_index = 0) {
   if (hi <= lo) return IBFT_OK;
-  uint32_t* const worklist = e->d_worklist ? e->d_worklist + (size_t)worklist_index * ((size_t)e->p.max_items + 1) : nullptr;
+  uint32_t* const worklist = L->d_worklist ? L->d_worklist + (size_t)worklist_index * ((size_t)L->cap_items + 1) : nullptr;
   // path selection (ibft_set_recover_path).  AUTO picks by how many warps each of the SM's four schedulers would hold
   // (B200, kernel time of one batch: profiles/latency_r01_v9.md):
   //   <= SMs x 24 signatures   four-lane chain warps + helper warp, one CTA (3 + 1 warps) per SM                   0.41 ms
@@ -1635,7 +1717,7 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
   //   beyond                   one thread per signature: one-warp CTAs while one wave covers them, then the 128-thread
   //                            throughput kernel
   const uint32_t cnt = hi - lo;
-  int path = forced_path != IBFT_PATH_AUTO ? forced_path : e->recover_path;
+  int path = forced_path != IBFT_PATH_AUTO ? forced_path : e->recover_path.load();
   if (path == IBFT_PATH_AUTO) {
 #if IBFT_WC > 0
     if (cnt <= (uint32_t)e->sm_count * 2u * IBFT_QSPLIT_SIGS) path = IBFT_PATH_QSPLIT;
@@ -1664,10 +1746,13 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
                                                          e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
   } else
 #if IBFT_WC > 0
-  if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && d_recovered == nullptr && d_groups != nullptr && e->d_worklist != nullptr) {
+  if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && d_recovered == nullptr && d_groups != nullptr && L->d_worklist != nullptr &&
+      cnt <= L->cap_items) {  // the worklist holds max_items indices: a larger device-resident shard takes the plain recover path
     // key-registry path (one thread per signature, any batch size): verify what can be verified, then recover the rest from
     // the worklist (dense second launch; the threads beyond the worklist's length leave at once)
     uint32_t blocks = (cnt + IBFT_BLOCK - 1) / IBFT_BLOCK;
+    // device-resident callers may use different streams: launches sharing a worklist are ordered on the device
+    CU(cudaStreamWaitEvent(st, L->wl_ev[worklist_index & 1u], 0));
     CU(cudaMemsetAsync(worklist, 0, 4, st));
     k_verify_known<<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                                   e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink, worklist);
@@ -1676,6 +1761,7 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
     k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
                                                          e->d_slots, e->p.max_table_slots, d_bitmap, nullptr, nullptr, e->d_ctable, sink,
                                                          worklist);
+    CU(cudaEventRecord(L->wl_ev[worklist_index & 1u], st));
   } else
 #endif
   if (cnt <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs
@@ -1692,77 +1778,77 @@ static int launch_recover(ibft_engine* e, const ibft_sig_item* d_items, uint32_t
   return IBFT_OK;
 }
 
-static int launch_quorum(ibft_engine* e, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len, const uint32_t* d_bitmap,
+static int launch_quorum(ibft_engine* e, lane* L, const ibft_sig_item* d_items, uint32_t n, const uint8_t* d_arena, size_t arena_len, const uint32_t* d_bitmap,
                          const ibft_group_desc* d_groups, const group_dev* d_gdev, uint32_t n_groups, size_t voted_words,
                          ibft_group_result* d_results, cudaStream_t st, bool already_marked = false) {
   if (n_groups == 0) return IBFT_OK;
   if (!already_marked) {
-    CU(cudaMemsetAsync(e->d_voted, 0, std::max<size_t>(voted_words, 1) * 4, st));
-    CU(cudaMemsetAsync(e->d_nvalid, 0, (size_t)n_groups * 4, st));
+    CU(cudaMemsetAsync(L->d_voted, 0, std::max<size_t>(voted_words, 1) * 4, st));
+    CU(cudaMemsetAsync(L->d_nvalid, 0, (size_t)n_groups * 4, st));
   }
   if (n && !already_marked) {
     k_quorum_mark<<<(n + 255) / 256, 256, 0, st>>>(d_items, n, d_arena, arena_len, d_bitmap, d_groups, d_gdev, n_groups, e->d_slots,
-                                                    e->p.max_table_slots, e->d_voted, e->d_nvalid, 0u, n);
+                                                    e->p.max_table_slots, L->d_voted, L->d_nvalid, 0u, n);
     e->launches++;
     CU(cudaGetLastError());
   }
-  k_quorum_reduce<<<n_groups, IBFT_REDUCE_THREADS, 0, st>>>(d_groups, d_gdev, n_groups, e->d_slots, e->p.max_table_slots, e->d_voted,
-                                            e->d_nvalid, d_results);
+  k_quorum_reduce<<<n_groups, IBFT_REDUCE_THREADS, 0, st>>>(d_groups, d_gdev, n_groups, e->d_slots, e->p.max_table_slots, L->d_voted,
+                                            L->d_nvalid, d_results);
   e->launches++;
   CU(cudaGetLastError());
   return IBFT_OK;
 }
 
-static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
+static int submit_locked(ibft_engine* e, lane* L, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
                          const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
                          ibft_group_result* results_out, uint8_t* recovered_out) {
-  if (e->pending.active) { set_err("a submitted call is still pending; wait for it first"); return IBFT_ERR_INVALID_ARG; }
+  if (L->pending.active) { set_err("a submitted call is still pending; wait for it first"); return IBFT_ERR_INVALID_ARG; }
   if ((n && !items) || (n && !bitmap_out) || (arena_len && !arena) || (n_groups && !groups)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
-  if (n > e->p.max_items || arena_len > e->p.max_payload_bytes || n_groups > e->p.max_groups) {
-    set_err("batch (%u items, %zu payload bytes, %u groups) exceeds engine capacity (%u, %u, %u)", n, arena_len, n_groups,
-            e->p.max_items, e->p.max_payload_bytes, e->p.max_groups);
+  if (n > L->cap_items || arena_len > L->cap_arena || n_groups > e->p.max_groups) {
+    set_err("batch (%u items, %zu payload bytes, %u groups) exceeds engine capacity (%u, %zu, %u)", n, arena_len, n_groups,
+            L->cap_items, L->cap_arena, e->p.max_groups);
     return IBFT_ERR_CAPACITY;
   }
   CU(cudaSetDevice(e->p.device));
   size_t voted_words = 0;
   if (n_groups) {
-    int rc = plan_groups(e, groups, n_groups, e->h_gdev, &voted_words);
+    int rc = plan_groups(e, L, groups, n_groups, L->h_gdev, &voted_words);
     if (rc != IBFT_OK) return rc;
-    memcpy(e->h_groups, groups, (size_t)n_groups * sizeof(ibft_group_desc));
-    e->last_gdev.assign(e->h_gdev, e->h_gdev + n_groups);
-    e->last_groups.assign(groups, groups + n_groups);
+    memcpy(L->h_groups, groups, (size_t)n_groups * sizeof(ibft_group_desc));
+    L->last_gdev.assign(L->h_gdev, L->h_gdev + n_groups);
+    L->last_groups.assign(groups, groups + n_groups);
   } else {
-    e->last_gdev.clear();
-    e->last_groups.clear();
+    L->last_gdev.clear();
+    L->last_groups.clear();
   }
-  cudaStream_t st = e->stream;
+  cudaStream_t st = L->stream;
   if (arena_len) {
-    memcpy(e->h_arena, arena, arena_len);
-    CU(cudaMemcpyAsync(e->d_arena, e->h_arena, arena_len, cudaMemcpyHostToDevice, st));
+    memcpy(L->h_arena, arena, arena_len);
+    CU(cudaMemcpyAsync(L->d_arena, L->h_arena, arena_len, cudaMemcpyHostToDevice, st));
   }
   if (n_groups) {
-    CU(cudaMemcpyAsync(e->d_groups, e->h_groups, (size_t)n_groups * sizeof(ibft_group_desc), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->d_gdev, e->h_gdev, (size_t)n_groups * sizeof(group_dev), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(L->d_groups, L->h_groups, (size_t)n_groups * sizeof(ibft_group_desc), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(L->d_gdev, L->h_gdev, (size_t)n_groups * sizeof(group_dev), cudaMemcpyHostToDevice, st));
   }
   // quorum requested: the recover kernels record the votes themselves (no k_quorum_mark pass over the tuples afterwards)
   vote_sink sink{nullptr, nullptr, nullptr};
   if (n_groups && results_out) {
-    CU(cudaMemsetAsync(e->d_voted, 0, std::max<size_t>(voted_words, 1) * 4, st));
-    CU(cudaMemsetAsync(e->d_nvalid, 0, (size_t)n_groups * 4, st));
-    sink = vote_sink{e->d_voted, e->d_nvalid, e->d_gdev};
+    CU(cudaMemsetAsync(L->d_voted, 0, std::max<size_t>(voted_words, 1) * 4, st));
+    CU(cudaMemsetAsync(L->d_nvalid, 0, (size_t)n_groups * 4, st));
+    sink = vote_sink{L->d_voted, L->d_nvalid, L->d_gdev};
   }
   // Tuples go up in chunks: while the recover kernel works on chunk k, the host stages chunk k+1 into pinned memory and the
   // copy engine moves it (two streams + events).  Small batches are a single chunk.
   const uint32_t CHUNK = 1u << 17;
   uint32_t n_chunks = n ? (n + CHUNK - 1) / CHUNK : 0;  // (not const: the latency path below takes the round over)
-  while (e->chunk_ev.size() < n_chunks + 1) {
+  while (L->chunk_ev.size() < n_chunks + 1) {
     cudaEvent_t ev;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    e->chunk_ev.push_back(ev);
+    L->chunk_ev.push_back(ev);
   }
   if (n_chunks > 1) {  // the copy stream must see the arena / groups uploads of this call
-    CU(cudaEventRecord(e->chunk_ev[n_chunks], st));
-    CU(cudaStreamWaitEvent(e->copy_stream, e->chunk_ev[n_chunks], 0));
+    CU(cudaEventRecord(L->chunk_ev[n_chunks], st));
+    CU(cudaStreamWaitEvent(L->copy_stream, L->chunk_ev[n_chunks], 0));
   }
   int rc = IBFT_OK;
 #if IBFT_WC > 0
@@ -1770,31 +1856,31 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
   // H2D transfer would sit in front of a kernel that cannot start before its last tuple has arrived.  Cut the round into four
   // pieces, each with its own stream -- stage, copy and launch piece k while piece k+1 is being staged; the four kernels
   // (<= 37 CTAs each) run side by side on different SMs and the main stream joins them before the quorum kernels.
-  const bool lat_pieces = e->recover_path == IBFT_PATH_AUTO && n > (uint32_t)e->sm_count * 2u * IBFT_QSPLIT_SIGS &&
+  const bool lat_pieces = e->recover_path.load() == IBFT_PATH_AUTO && n > (uint32_t)e->sm_count * 2u * IBFT_QSPLIT_SIGS &&
                           n <= (uint32_t)e->sm_count * IBFT_SPLIT_SIGS;
   if (lat_pieces) {
     bool pinned = false;
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, items) == cudaSuccess) pinned = pa.type == cudaMemoryTypeHost;
     else (void)cudaGetLastError();
-    CU(cudaEventRecord(e->lat_ev[4], st));  // arena / groups uploads of this call
+    CU(cudaEventRecord(L->lat_ev[4], st));  // arena / groups uploads of this call
     const uint32_t per = ((n + 3) / 4 + IBFT_SPLIT_SIGS - 1) / IBFT_SPLIT_SIGS * IBFT_SPLIT_SIGS;
     for (uint32_t c = 0; c < 4; c++) {
       uint32_t lo = std::min(n, c * per), hi = std::min(n, lo + per);
       if (hi <= lo) break;
-      cudaStream_t ls = e->lat_stream[c];
+      cudaStream_t ls = L->lat_stream[c];
       const ibft_sig_item* src = items + lo;
       if (!pinned) {
-        memcpy(e->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
-        src = e->h_items + lo;
+        memcpy(L->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
+        src = L->h_items + lo;
       }
-      CU(cudaStreamWaitEvent(ls, e->lat_ev[4], 0));
-      CU(cudaMemcpyAsync(e->d_items + lo, src, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, ls));
-      rc = launch_recover(e, e->d_items, n, e->d_arena, arena_len, lo, hi, n_groups ? e->d_groups : nullptr, n_groups, e->d_bitmap,
-                          recovered_out ? e->d_recovered : nullptr, ls, e->d_status, IBFT_PATH_SPLIT, sink);
+      CU(cudaStreamWaitEvent(ls, L->lat_ev[4], 0));
+      CU(cudaMemcpyAsync(L->d_items + lo, src, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, ls));
+      rc = launch_recover(e, L, L->d_items, n, L->d_arena, arena_len, lo, hi, n_groups ? L->d_groups : nullptr, n_groups, L->d_bitmap,
+                          recovered_out ? L->d_recovered : nullptr, ls, L->d_status, IBFT_PATH_SPLIT, sink);
       if (rc != IBFT_OK) return rc;
-      CU(cudaEventRecord(e->lat_ev[c], ls));
-      CU(cudaStreamWaitEvent(st, e->lat_ev[c], 0));
+      CU(cudaEventRecord(L->lat_ev[c], ls));
+      CU(cudaStreamWaitEvent(st, L->lat_ev[c], 0));
     }
     n_chunks = 0;  // the generic chunk loop below has nothing left to do
   }
@@ -1810,75 +1896,119 @@ static int submit_locked(ibft_engine* e, const ibft_sig_item* items, uint32_t n,
   // Several chunks: chunk c's kernels run on one of two alternating streams, so that the tail of one chunk (the last CTAs of a
   // 1,024-CTA launch on 444 resident slots) overlaps the head of the next instead of idling the SMs eight times per batch.
   if (n_chunks > 1) {
-    CU(cudaEventRecord(e->lat_ev[4], st));  // arena / groups uploads and the vote-sink memsets of this call
-    CU(cudaStreamWaitEvent(e->lat_stream[0], e->lat_ev[4], 0));
-    CU(cudaStreamWaitEvent(e->lat_stream[1], e->lat_ev[4], 0));
+    CU(cudaEventRecord(L->lat_ev[4], st));  // arena / groups uploads and the vote-sink memsets of this call
+    CU(cudaStreamWaitEvent(L->lat_stream[0], L->lat_ev[4], 0));
+    CU(cudaStreamWaitEvent(L->lat_stream[1], L->lat_ev[4], 0));
   }
   for (uint32_t c = 0; c < n_chunks; c++) {
     uint32_t lo = c * CHUNK, hi = std::min(n, lo + CHUNK);
     const ibft_sig_item* src = items + lo;
     if (!caller_pinned) {
-      memcpy(e->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
-      src = e->h_items + lo;
+      memcpy(L->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
+      src = L->h_items + lo;
     }
-    cudaStream_t cs = n_chunks > 1 ? e->copy_stream : st;
-    cudaStream_t ks = n_chunks > 1 ? e->lat_stream[c & 1u] : st;
-    CU(cudaMemcpyAsync(e->d_items + lo, src, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, cs));
+    cudaStream_t cs = n_chunks > 1 ? L->copy_stream : st;
+    cudaStream_t ks = n_chunks > 1 ? L->lat_stream[c & 1u] : st;
+    CU(cudaMemcpyAsync(L->d_items + lo, src, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, cs));
     if (n_chunks > 1) {
-      CU(cudaEventRecord(e->chunk_ev[c], cs));
-      CU(cudaStreamWaitEvent(ks, e->chunk_ev[c], 0));
+      CU(cudaEventRecord(L->chunk_ev[c], cs));
+      CU(cudaStreamWaitEvent(ks, L->chunk_ev[c], 0));
     }
-    rc = launch_recover(e, e->d_items, n, e->d_arena, arena_len, lo, hi, n_groups ? e->d_groups : nullptr, n_groups, e->d_bitmap,
-                        recovered_out ? e->d_recovered : nullptr, ks, e->d_status, IBFT_PATH_AUTO, sink, c & 1u);
+    rc = launch_recover(e, L, L->d_items, n, L->d_arena, arena_len, lo, hi, n_groups ? L->d_groups : nullptr, n_groups, L->d_bitmap,
+                        recovered_out ? L->d_recovered : nullptr, ks, L->d_status, IBFT_PATH_AUTO, sink, c & 1u);
     if (rc != IBFT_OK) return rc;
   }
   if (n_chunks > 1) {
     for (int k = 0; k < 2; k++) {
-      CU(cudaEventRecord(e->lat_ev[k], e->lat_stream[k]));
-      CU(cudaStreamWaitEvent(st, e->lat_ev[k], 0));
+      CU(cudaEventRecord(L->lat_ev[k], L->lat_stream[k]));
+      CU(cudaStreamWaitEvent(st, L->lat_ev[k], 0));
     }
   }
   if (n_groups && results_out) {
-    rc = launch_quorum(e, e->d_items, n, e->d_arena, arena_len, e->d_bitmap, e->d_groups, e->d_gdev, n_groups, voted_words, e->d_results, st,
+    rc = launch_quorum(e, L, L->d_items, n, L->d_arena, arena_len, L->d_bitmap, L->d_groups, L->d_gdev, n_groups, voted_words, L->d_results, st,
                        /*already_marked=*/true);
     if (rc != IBFT_OK) return rc;
-    CU(cudaMemcpyAsync(e->h_results, e->d_results, (size_t)n_groups * sizeof(ibft_group_result), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(L->h_results, L->d_results, (size_t)n_groups * sizeof(ibft_group_result), cudaMemcpyDeviceToHost, st));
   }
   if (n) {
-    CU(cudaMemcpyAsync(e->h_status, e->d_status, (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(e->h_bitmap, e->d_bitmap, (size_t)((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
-    if (recovered_out) CU(cudaMemcpyAsync(e->h_recovered, e->d_recovered, (size_t)n * 20, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(L->h_status, L->d_status, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(L->h_bitmap, L->d_bitmap, (size_t)((n + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+    if (recovered_out) CU(cudaMemcpyAsync(L->h_recovered, L->d_recovered, (size_t)n * 20, cudaMemcpyDeviceToHost, st));
   }
-  CU(cudaEventRecord(e->done_ev, st));
-  e->pending.active = true;
-  e->pending.n = n;
-  e->pending.n_groups = (n_groups && results_out) ? n_groups : 0;
-  e->pending.bitmap_out = bitmap_out;
-  e->pending.results_out = results_out;
-  e->pending.recovered_out = recovered_out;
+  CU(cudaEventRecord(L->done_ev, st));
+  L->pending.active = true;
+  L->pending.n = n;
+  L->pending.n_groups = (n_groups && results_out) ? n_groups : 0;
+  L->pending.bitmap_out = bitmap_out;
+  L->pending.results_out = results_out;
+  L->pending.recovered_out = recovered_out;
   return IBFT_OK;
 }
 
-static int wait_locked(ibft_engine* e) {
-  if (!e->pending.active) { set_err("no submitted call to wait for"); return IBFT_ERR_INVALID_ARG; }
+static int wait_locked(ibft_engine* e, lane* L) {
+  if (!L->pending.active) { set_err("no submitted call to wait for"); return IBFT_ERR_INVALID_ARG; }
   CU(cudaSetDevice(e->p.device));
-  cudaError_t ce = cudaEventSynchronize(e->done_ev);
-  pending_call pc = e->pending;
-  e->pending.active = false;
+  cudaError_t ce = cudaEventSynchronize(L->done_ev);
+  pending_call pc = L->pending;
+  L->pending.active = false;
   if (ce != cudaSuccess) {
     // launch/execution failure: NO verdict is produced (outputs untouched) -- never `true`
     set_err("device execution failed: %s", cudaGetErrorString(ce));
     return IBFT_ERR_CUDA;
   }
-  e->last_status_n = pc.n;
+  L->last_status_n = pc.n;
   if (pc.n) {
     size_t words = (pc.n + 31) / 32;
-    memcpy(pc.bitmap_out, e->h_bitmap, words * 4);
+    memcpy(pc.bitmap_out, L->h_bitmap, words * 4);
     if (pc.n & 31) pc.bitmap_out[words - 1] &= (1u << (pc.n & 31)) - 1u;
-    if (pc.recovered_out) memcpy(pc.recovered_out, e->h_recovered, (size_t)pc.n * 20);
+    if (pc.recovered_out) memcpy(pc.recovered_out, L->h_recovered, (size_t)pc.n * 20);
   }
-  if (pc.n_groups) memcpy(pc.results_out, e->h_results, (size_t)pc.n_groups * sizeof(ibft_group_result));
-  if (e->p.flags & IBFT_FLAG_KEY_CACHE) return refresh_key_tables_locked(e, nullptr);  // new keys -> tables, for the next call
+  if (pc.n_groups) memcpy(pc.results_out, L->h_results, (size_t)pc.n_groups * sizeof(ibft_group_result));
+  e->last_lane.store((int)(L - e->lanes));
+  if (e->p.flags & IBFT_FLAG_KEY_CACHE) return refresh_key_tables_locked(e, L, nullptr);  // new keys -> tables, for the next call
+  return IBFT_OK;
+}
+
+// Lane selection for a synchronous host-buffer call: a call that fits the small lane takes whichever lane is free (small lane
+// first, so that bulk callers find lane 0 free); a large call always takes lane 0.  Returns with the lane's mutex HELD.
+static lane* acquire_lane(ibft_engine* e, uint32_t n, size_t arena_len) {
+  lane* big = &e->lanes[0];
+  lane* small = &e->lanes[1];
+  const bool fits_small = n <= small->cap_items && arena_len <= small->cap_arena;
+  if (fits_small) {
+    if (small->mu.try_lock()) return small;
+    if (big->mu.try_lock()) {
+      if (!big->pending.active) return big;
+      big->mu.unlock();
+    }
+    small->mu.lock();
+    return small;
+  }
+  big->mu.lock();
+  return big;
+}
+
+static int verify_batch_on_lane(ibft_engine* e, lane* L, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
+                                const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out, ibft_group_result* results_out,
+                                uint8_t* recovered_out, uint8_t* status_out, uint32_t* voted_out, uint32_t voted_stride_words) {
+  int rc = submit_locked(e, L, items, n, arena, arena_len, groups, n_groups, bitmap_out, results_out, recovered_out);
+  if (rc != IBFT_OK) return rc;
+  rc = wait_locked(e, L);
+  if (rc != IBFT_OK) return rc;
+  if (status_out && n) memcpy(status_out, L->h_status, n);
+  if (voted_out && n_groups) {
+    CU(cudaSetDevice(e->p.device));
+    for (uint32_t g = 0; g < n_groups; g++) {
+      const group_dev& gd = L->last_gdev[g];
+      uint32_t* dst = voted_out + (size_t)g * voted_stride_words;
+      uint32_t w = std::min<uint32_t>(gd.n_words, voted_stride_words);
+      // without results_out the recover kernels recorded no votes: the sets are all-zero by definition
+      if (w && results_out) CU(cudaMemcpyAsync(dst, L->d_voted + gd.voted_off, (size_t)w * 4, cudaMemcpyDeviceToHost, L->stream));
+      else w = 0;
+      for (uint32_t i = w; i < voted_stride_words; i++) dst[i] = 0;
+    }
+    CU(cudaStreamSynchronize(L->stream));
+  }
   return IBFT_OK;
 }
 
@@ -1886,35 +2016,51 @@ extern "C" int ibft_verify_batch(ibft_engine* e, const ibft_sig_item* items, uin
                                  const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
                                  ibft_group_result* results_out, uint8_t* recovered_out) {
   if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  int rc = submit_locked(e, items, n, arena, arena_len, groups, n_groups, bitmap_out, results_out, recovered_out);
-  if (rc != IBFT_OK) return rc;
-  return wait_locked(e);
+  lane* L = acquire_lane(e, n, arena_len);
+  std::lock_guard<std::mutex> lk(L->mu, std::adopt_lock);
+  return verify_batch_on_lane(e, L, items, n, arena, arena_len, groups, n_groups, bitmap_out, results_out, recovered_out, nullptr, nullptr, 0);
+}
+
+extern "C" int ibft_verify_batch_ex(ibft_engine* e, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
+                                    const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
+                                    ibft_group_result* results_out, uint8_t* recovered_out, uint8_t* status_out, uint32_t* voted_out,
+                                    uint32_t voted_stride_words) {
+  if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
+  if (voted_out && !results_out) { set_err("voted_out needs results_out (votes are recorded only when quorum results are requested)"); return IBFT_ERR_INVALID_ARG; }
+  lane* L = acquire_lane(e, n, arena_len);
+  std::lock_guard<std::mutex> lk(L->mu, std::adopt_lock);
+  return verify_batch_on_lane(e, L, items, n, arena, arena_len, groups, n_groups, bitmap_out, results_out, recovered_out, status_out, voted_out,
+                              voted_stride_words);
 }
 
 extern "C" int ibft_last_item_status(ibft_engine* e, uint8_t* status_out, uint32_t n) {
   if (!e || (n && !status_out)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  if (e->pending.active) { set_err("a submitted call is still pending"); return IBFT_ERR_INVALID_ARG; }
-  if (n > e->last_status_n) { set_err("last call had %u items", e->last_status_n); return IBFT_ERR_INVALID_ARG; }
-  memcpy(status_out, e->h_status, n);
+  lane* L = &e->lanes[e->last_lane.load()];
+  std::lock_guard<std::mutex> lk(L->mu);
+  if (L->pending.active) { set_err("a submitted call is still pending"); return IBFT_ERR_INVALID_ARG; }
+  if (n > L->last_status_n) { set_err("last call had %u items", L->last_status_n); return IBFT_ERR_INVALID_ARG; }
+  memcpy(status_out, L->h_status, n);
   return IBFT_OK;
 }
 
+// The asynchronous API lives on lane 0 (one call pending at a time, as before); synchronous calls that fit the small lane keep
+// working while it is pending.
 extern "C" int ibft_verify_submit(ibft_engine* e, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
                                   const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
                                   ibft_group_result* results_out, uint8_t* recovered_out) {
   if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  return submit_locked(e, items, n, arena, arena_len, groups, n_groups, bitmap_out, results_out, recovered_out);
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
+  return submit_locked(e, L, items, n, arena, arena_len, groups, n_groups, bitmap_out, results_out, recovered_out);
 }
 
 extern "C" int ibft_verify_poll(ibft_engine* e, int* done) {
   if (!e || !done) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  if (!e->pending.active) { *done = 1; return IBFT_OK; }
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
+  if (!L->pending.active) { *done = 1; return IBFT_OK; }
   CU(cudaSetDevice(e->p.device));
-  cudaError_t ce = cudaEventQuery(e->done_ev);
+  cudaError_t ce = cudaEventQuery(L->done_ev);
   if (ce == cudaSuccess) { *done = 1; return IBFT_OK; }
   if (ce == cudaErrorNotReady) { *done = 0; return IBFT_OK; }
   set_err("device execution failed: %s", cudaGetErrorString(ce));
@@ -1923,8 +2069,9 @@ extern "C" int ibft_verify_poll(ibft_engine* e, int* done) {
 
 extern "C" int ibft_verify_wait(ibft_engine* e) {
   if (!e) { set_err("null engine"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  return wait_locked(e);
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
+  return wait_locked(e, L);
 }
 
 extern "C" int ibft_verify_batch_device(ibft_engine* e, const void* d_items, uint32_t n, const void* d_arena, size_t arena_len,
@@ -1934,14 +2081,15 @@ extern "C" int ibft_verify_batch_device(ibft_engine* e, const void* d_items, uin
     set_err("shard [%u,%u) of %u must be 32-aligned", shard_lo, shard_hi, n);
     return IBFT_ERR_INVALID_ARG;
   }
-  std::lock_guard<std::mutex> lk(e->mu);
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
   CU(cudaSetDevice(e->p.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-  e->dev_arena = (const uint8_t*)d_arena;  // remembered for ibft_quorum_reduce_device (raw-frame items carry their signer in the arena)
-  e->dev_arena_len = arena_len;
+  cudaStream_t st = stream ? (cudaStream_t)stream : L->stream;
+  L->dev_arena = (const uint8_t*)d_arena;  // remembered for ibft_quorum_reduce_device (raw-frame items carry their signer in the arena)
+  L->dev_arena_len = arena_len;
   // membership is applied by ibft_quorum_reduce_device / the host mirror in this mode when no groups are bound
-  return launch_recover(e, (const ibft_sig_item*)d_items, n, (const uint8_t*)d_arena, arena_len, shard_lo, shard_hi,
-                        e->last_groups.empty() ? nullptr : e->d_groups, (uint32_t)e->last_groups.size(), (uint32_t*)d_bitmap,
+  return launch_recover(e, L, (const ibft_sig_item*)d_items, n, (const uint8_t*)d_arena, arena_len, shard_lo, shard_hi,
+                        L->last_groups.empty() ? nullptr : L->d_groups, (uint32_t)L->last_groups.size(), (uint32_t*)d_bitmap,
                         (uint8_t*)d_recovered, st);
 }
 
@@ -1949,20 +2097,21 @@ extern "C" int ibft_verify_batch_device(ibft_engine* e, const void* d_items, uin
 extern "C" int ibft_bind_groups(ibft_engine* e, const ibft_group_desc* groups, uint32_t n_groups) {
   if (!e || (n_groups && !groups)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
   if (n_groups > e->p.max_groups) { set_err("too many groups"); return IBFT_ERR_CAPACITY; }
-  std::lock_guard<std::mutex> lk(e->mu);
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
   CU(cudaSetDevice(e->p.device));
   size_t voted_words = 0;
   if (n_groups) {
-    int rc = plan_groups(e, groups, n_groups, e->h_gdev, &voted_words);
+    int rc = plan_groups(e, L, groups, n_groups, L->h_gdev, &voted_words);
     if (rc != IBFT_OK) return rc;
-    memcpy(e->h_groups, groups, (size_t)n_groups * sizeof(ibft_group_desc));
-    CU(cudaMemcpy(e->d_groups, e->h_groups, (size_t)n_groups * sizeof(ibft_group_desc), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(e->d_gdev, e->h_gdev, (size_t)n_groups * sizeof(group_dev), cudaMemcpyHostToDevice));
-    e->last_gdev.assign(e->h_gdev, e->h_gdev + n_groups);
-    e->last_groups.assign(groups, groups + n_groups);
+    memcpy(L->h_groups, groups, (size_t)n_groups * sizeof(ibft_group_desc));
+    CU(cudaMemcpy(L->d_groups, L->h_groups, (size_t)n_groups * sizeof(ibft_group_desc), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(L->d_gdev, L->h_gdev, (size_t)n_groups * sizeof(group_dev), cudaMemcpyHostToDevice));
+    L->last_gdev.assign(L->h_gdev, L->h_gdev + n_groups);
+    L->last_groups.assign(groups, groups + n_groups);
   } else {
-    e->last_gdev.clear();
-    e->last_groups.clear();
+    L->last_gdev.clear();
+    L->last_groups.clear();
   }
   return IBFT_OK;
 }
@@ -1970,23 +2119,25 @@ extern "C" int ibft_bind_groups(ibft_engine* e, const ibft_group_desc* groups, u
 extern "C" int ibft_quorum_reduce_device(ibft_engine* e, const void* d_items, uint32_t n, const void* d_bitmap,
                                          const void* d_groups, uint32_t n_groups, void* d_results, void* stream) {
   if (!e || !d_results || (n && (!d_items || !d_bitmap))) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  if (n_groups != e->last_groups.size()) { set_err("call ibft_bind_groups with the same groups first"); return IBFT_ERR_INVALID_ARG; }
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
+  if (n_groups != L->last_groups.size()) { set_err("call ibft_bind_groups with the same groups first"); return IBFT_ERR_INVALID_ARG; }
   (void)d_groups;  // the bound copy is authoritative (its voted-set layout was planned on the host)
   CU(cudaSetDevice(e->p.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  cudaStream_t st = stream ? (cudaStream_t)stream : L->stream;
   size_t voted_words = 0;
-  for (auto& g : e->last_gdev) voted_words += g.n_words;
-  return launch_quorum(e, (const ibft_sig_item*)d_items, n, e->dev_arena, e->dev_arena_len, (const uint32_t*)d_bitmap, e->d_groups,
-                       e->d_gdev, n_groups, voted_words, (ibft_group_result*)d_results, st);
+  for (auto& g : L->last_gdev) voted_words += g.n_words;
+  return launch_quorum(e, L, (const ibft_sig_item*)d_items, n, L->dev_arena, L->dev_arena_len, (const uint32_t*)d_bitmap, L->d_groups,
+                       L->d_gdev, n_groups, voted_words, (ibft_group_result*)d_results, st);
 }
 
 extern "C" int ibft_quorum_partial_words(ibft_engine* e, uint32_t* words_out) {
   if (!e || !words_out) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
   size_t voted_words = 0;
-  for (auto& g : e->last_gdev) voted_words += g.n_words;
-  *words_out = (uint32_t)(voted_words + e->last_groups.size());
+  for (auto& g : L->last_gdev) voted_words += g.n_words;
+  *words_out = (uint32_t)(voted_words + L->last_groups.size());
   return IBFT_OK;
 }
 
@@ -1994,18 +2145,19 @@ extern "C" int ibft_quorum_mark_device(ibft_engine* e, const void* d_items, uint
                                        const void* d_bitmap, void* d_partial, void* stream) {
   if (!e || !d_partial || (n && (!d_items || !d_bitmap))) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
   if (shard_hi > n || shard_lo > shard_hi) { set_err("bad shard"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  uint32_t n_groups = (uint32_t)e->last_groups.size();
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
+  uint32_t n_groups = (uint32_t)L->last_groups.size();
   if (n_groups == 0) { set_err("call ibft_bind_groups first"); return IBFT_ERR_INVALID_ARG; }
   CU(cudaSetDevice(e->p.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  cudaStream_t st = stream ? (cudaStream_t)stream : L->stream;
   size_t voted_words = 0;
-  for (auto& g : e->last_gdev) voted_words += g.n_words;
+  for (auto& g : L->last_gdev) voted_words += g.n_words;
   uint32_t* part = (uint32_t*)d_partial;
   CU(cudaMemsetAsync(part, 0, (voted_words + n_groups) * 4, st));
   if (shard_hi > shard_lo) {
-    k_quorum_mark<<<(shard_hi - shard_lo + 255) / 256, 256, 0, st>>>((const ibft_sig_item*)d_items, n, e->dev_arena, e->dev_arena_len,
-                                                                     (const uint32_t*)d_bitmap, e->d_groups, e->d_gdev, n_groups, e->d_slots,
+    k_quorum_mark<<<(shard_hi - shard_lo + 255) / 256, 256, 0, st>>>((const ibft_sig_item*)d_items, n, L->dev_arena, L->dev_arena_len,
+                                                                     (const uint32_t*)d_bitmap, L->d_groups, L->d_gdev, n_groups, e->d_slots,
                                                                      e->p.max_table_slots, part, part + voted_words, shard_lo, shard_hi);
     e->launches++;
     CU(cudaGetLastError());
@@ -2016,20 +2168,21 @@ extern "C" int ibft_quorum_mark_device(ibft_engine* e, const void* d_items, uint
 extern "C" int ibft_quorum_merge_device(ibft_engine* e, const void* d_partials, uint32_t n_parts, uint32_t part_stride_words,
                                         void* d_results, void* stream) {
   if (!e || !d_partials || !d_results || n_parts == 0) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  uint32_t n_groups = (uint32_t)e->last_groups.size();
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
+  uint32_t n_groups = (uint32_t)L->last_groups.size();
   if (n_groups == 0) { set_err("call ibft_bind_groups first"); return IBFT_ERR_INVALID_ARG; }
   CU(cudaSetDevice(e->p.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  cudaStream_t st = stream ? (cudaStream_t)stream : L->stream;
   size_t voted_words = 0;
-  for (auto& g : e->last_gdev) voted_words += g.n_words;
+  for (auto& g : L->last_gdev) voted_words += g.n_words;
   if (part_stride_words < voted_words + n_groups) { set_err("partial stride too small"); return IBFT_ERR_INVALID_ARG; }
   uint32_t total = (uint32_t)(voted_words + n_groups);
   k_quorum_merge<<<(total + 255) / 256, 256, 0, st>>>((const uint32_t*)d_partials, n_parts, part_stride_words, (uint32_t)voted_words,
-                                                      n_groups, e->d_voted, e->d_nvalid);
+                                                      n_groups, L->d_voted, L->d_nvalid);
   e->launches++;
   CU(cudaGetLastError());
-  k_quorum_reduce<<<n_groups, IBFT_REDUCE_THREADS, 0, st>>>(e->d_groups, e->d_gdev, n_groups, e->d_slots, e->p.max_table_slots, e->d_voted, e->d_nvalid,
+  k_quorum_reduce<<<n_groups, IBFT_REDUCE_THREADS, 0, st>>>(L->d_groups, L->d_gdev, n_groups, e->d_slots, e->p.max_table_slots, L->d_voted, L->d_nvalid,
                                             (ibft_group_result*)d_results);
   e->launches++;
   CU(cudaGetLastError());
@@ -2038,14 +2191,65 @@ extern "C" int ibft_quorum_merge_device(ibft_engine* e, const void* d_partials, 
 
 extern "C" int ibft_get_voted_bitmap(ibft_engine* e, uint32_t group, uint32_t* words_out, uint32_t n_words) {
   if (!e || !words_out) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
-  if (group >= e->last_gdev.size()) { set_err("group %u not part of the last call", group); return IBFT_ERR_INVALID_ARG; }
-  const group_dev& g = e->last_gdev[group];
+  lane* L = &e->lanes[e->last_lane.load()];
+  std::lock_guard<std::mutex> lk(L->mu);
+  if (group >= L->last_gdev.size()) { set_err("group %u not part of the last call", group); return IBFT_ERR_INVALID_ARG; }
+  const group_dev& g = L->last_gdev[group];
   if (n_words < g.n_words) { set_err("need %u words", g.n_words); return IBFT_ERR_CAPACITY; }
   CU(cudaSetDevice(e->p.device));
-  CU(cudaStreamSynchronize(e->stream));
-  if (g.n_words) CU(cudaMemcpy(words_out, e->d_voted + g.voted_off, (size_t)g.n_words * 4, cudaMemcpyDeviceToHost));
+  CU(cudaStreamSynchronize(L->stream));
+  if (g.n_words) CU(cudaMemcpy(words_out, L->d_voted + g.voted_off, (size_t)g.n_words * 4, cudaMemcpyDeviceToHost));
   for (uint32_t i = g.n_words; i < n_words; i++) words_out[i] = 0;
+  return IBFT_OK;
+}
+
+// Hash scratch is engine-owned and only ever grows (no cudaMalloc / cudaFree on the per-call path).
+static int hash_scratch_reserve(ibft_engine* e, size_t arena_len, uint32_t n) {
+  if (arena_len > e->hs_arena_cap) {
+    size_t cap = std::max<size_t>(arena_len, std::max<size_t>(e->hs_arena_cap * 2, 1 << 16));
+    cudaFree(e->hs_arena); e->hs_arena = nullptr; e->hs_arena_cap = 0;
+    cudaFreeHost(e->hs_h_arena); e->hs_h_arena = nullptr;
+    CU(cudaMalloc(&e->hs_arena, cap));
+    CU(cudaHostAlloc(&e->hs_h_arena, cap, cudaHostAllocDefault));
+    e->hs_arena_cap = cap;
+  }
+  if (n > e->hs_n_cap) {
+    uint32_t cap = std::max<uint32_t>(n, std::max<uint32_t>(e->hs_n_cap * 2, 256));
+    cudaFree(e->hs_meta); e->hs_meta = nullptr; e->hs_n_cap = 0;
+    cudaFreeHost(e->hs_h_meta); e->hs_h_meta = nullptr;
+    // per message: offset (4) + length (4) + round (8) in, 32 bytes out
+    CU(cudaMalloc(&e->hs_meta, (size_t)cap * 48));
+    CU(cudaHostAlloc(&e->hs_h_meta, (size_t)cap * 48, cudaHostAllocDefault));
+    e->hs_n_cap = cap;
+  }
+  return IBFT_OK;
+}
+
+static int hash_batch_locked(ibft_engine* e, const uint8_t* arena, size_t arena_len, const uint32_t* offsets, const uint32_t* lens,
+                             const uint64_t* rounds, uint32_t n, uint8_t* out32) {
+  CU(cudaSetDevice(e->p.device));
+  int rc = hash_scratch_reserve(e, arena_len, n);
+  if (rc != IBFT_OK) return rc;
+  // layout of the meta block (host mirror and device): rounds[n] | offsets[n] | lens[n] | out[n][32]
+  uint8_t* hm = e->hs_h_meta;
+  uint8_t* dm = e->hs_meta;
+  const size_t o_off = (size_t)n * 8, o_len = o_off + (size_t)n * 4, o_out = o_len + (size_t)n * 4;
+  if (rounds) memcpy(hm, rounds, (size_t)n * 8);
+  memcpy(hm + o_off, offsets, (size_t)n * 4);
+  memcpy(hm + o_len, lens, (size_t)n * 4);
+  cudaStream_t st = e->hash_stream;
+  if (arena_len) {
+    memcpy(e->hs_h_arena, arena, arena_len);
+    CU(cudaMemcpyAsync(e->hs_arena, e->hs_h_arena, arena_len, cudaMemcpyHostToDevice, st));
+  }
+  CU(cudaMemcpyAsync(dm, hm, o_out, cudaMemcpyHostToDevice, st));
+  k_keccak_batch<<<(n + 63) / 64, 64, 0, st>>>(e->hs_arena, arena_len, (const uint32_t*)(dm + o_off), (const uint32_t*)(dm + o_len),
+                                               rounds ? (const uint64_t*)dm : nullptr, n, dm + o_out);
+  e->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(hm + o_out, dm + o_out, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(out32, hm + o_out, (size_t)n * 32);
   return IBFT_OK;
 }
 
@@ -2053,36 +2257,24 @@ extern "C" int ibft_keccak256_batch(ibft_engine* e, const uint8_t* arena, size_t
                                     const uint32_t* lens, uint32_t n, uint8_t* out32) {
   if (!e || (n && (!offsets || !lens || !out32)) || (arena_len && !arena)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
   if (n == 0) return IBFT_OK;
-  std::lock_guard<std::mutex> lk(e->mu);
-  CU(cudaSetDevice(e->p.device));
-  uint8_t *d_a = nullptr, *d_o = nullptr;
-  uint32_t *d_off = nullptr, *d_len = nullptr;
-  int rc = IBFT_OK;
-  cudaError_t ce;
-#define CUK(call) if ((ce = (call)) != cudaSuccess) { set_err("%s failed: %s", #call, cudaGetErrorString(ce)); rc = IBFT_ERR_CUDA; goto done; }
-  CUK(cudaMalloc(&d_a, std::max<size_t>(arena_len, 16)));
-  CUK(cudaMalloc(&d_o, (size_t)n * 32));
-  CUK(cudaMalloc(&d_off, (size_t)n * 4));
-  CUK(cudaMalloc(&d_len, (size_t)n * 4));
-  if (arena_len) CUK(cudaMemcpyAsync(d_a, arena, arena_len, cudaMemcpyHostToDevice, e->stream));
-  CUK(cudaMemcpyAsync(d_off, offsets, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
-  CUK(cudaMemcpyAsync(d_len, lens, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
-  k_keccak_batch<<<(n + 127) / 128, 128, 0, e->stream>>>(d_a, arena_len, d_off, d_len, n, d_o);
-  e->launches++;
-  CUK(cudaGetLastError());
-  CUK(cudaMemcpyAsync(out32, d_o, (size_t)n * 32, cudaMemcpyDeviceToHost, e->stream));
-  CUK(cudaStreamSynchronize(e->stream));
-done:
-#undef CUK
-  cudaFree(d_a); cudaFree(d_o); cudaFree(d_off); cudaFree(d_len);
-  return rc;
+  std::lock_guard<std::mutex> lk(e->hash_mu);
+  return hash_batch_locked(e, arena, arena_len, offsets, lens, nullptr, n, out32);
+}
+
+extern "C" int ibft_proposal_hash_batch(ibft_engine* e, const uint8_t* arena, size_t arena_len, const uint32_t* offsets,
+                                        const uint32_t* lens, const uint64_t* rounds, uint32_t n, uint8_t* out32) {
+  if (!e || (n && (!offsets || !lens || !rounds || !out32)) || (arena_len && !arena)) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
+  if (n == 0) return IBFT_OK;
+  std::lock_guard<std::mutex> lk(e->hash_mu);
+  return hash_batch_locked(e, arena, arena_len, offsets, lens, rounds, n, out32);
 }
 
 extern "C" int ibft_sign_batch(ibft_engine* e, const uint8_t* privkeys, const uint8_t* digests, const uint8_t* nonces, uint32_t n,
                                uint8_t* sigs65_out) {
   if (!e || (n && (!privkeys || !digests || !sigs65_out))) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
   if (n == 0) return IBFT_OK;
-  std::lock_guard<std::mutex> lk(e->mu);
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
   CU(cudaSetDevice(e->p.device));
   uint8_t *d_d = nullptr, *d_z = nullptr, *d_k = nullptr, *d_s = nullptr;
   int rc = IBFT_OK;
@@ -2091,21 +2283,21 @@ extern "C" int ibft_sign_batch(ibft_engine* e, const uint8_t* privkeys, const ui
   CUK(cudaMalloc(&d_d, (size_t)n * 32));
   CUK(cudaMalloc(&d_z, (size_t)n * 32));
   CUK(cudaMalloc(&d_s, (size_t)n * 65));
-  CUK(cudaMemcpyAsync(d_d, privkeys, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
-  CUK(cudaMemcpyAsync(d_z, digests, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+  CUK(cudaMemcpyAsync(d_d, privkeys, (size_t)n * 32, cudaMemcpyHostToDevice, L->stream));
+  CUK(cudaMemcpyAsync(d_z, digests, (size_t)n * 32, cudaMemcpyHostToDevice, L->stream));
   if (nonces) {
     CUK(cudaMalloc(&d_k, (size_t)n * 32));
-    CUK(cudaMemcpyAsync(d_k, nonces, (size_t)n * 32, cudaMemcpyHostToDevice, e->stream));
+    CUK(cudaMemcpyAsync(d_k, nonces, (size_t)n * 32, cudaMemcpyHostToDevice, L->stream));
   }
-  k_sign<<<(n + 63) / 64, 64, 0, e->stream>>>(d_d, d_z, d_k, n, d_s);
+  k_sign<<<(n + 63) / 64, 64, 0, L->stream>>>(d_d, d_z, d_k, n, d_s);
   e->launches++;
   CUK(cudaGetLastError());
-  CUK(cudaMemcpyAsync(sigs65_out, d_s, (size_t)n * 65, cudaMemcpyDeviceToHost, e->stream));
-  CUK(cudaStreamSynchronize(e->stream));
+  CUK(cudaMemcpyAsync(sigs65_out, d_s, (size_t)n * 65, cudaMemcpyDeviceToHost, L->stream));
+  CUK(cudaStreamSynchronize(L->stream));
   // private keys do not stay on the device
-  cudaMemsetAsync(d_d, 0, (size_t)n * 32, e->stream);
-  if (d_k) cudaMemsetAsync(d_k, 0, (size_t)n * 32, e->stream);
-  cudaStreamSynchronize(e->stream);
+  cudaMemsetAsync(d_d, 0, (size_t)n * 32, L->stream);
+  if (d_k) cudaMemsetAsync(d_k, 0, (size_t)n * 32, L->stream);
+  cudaStreamSynchronize(L->stream);
 done:
 #undef CUK
   cudaFree(d_d); cudaFree(d_z); cudaFree(d_k); cudaFree(d_s);
@@ -2114,16 +2306,16 @@ done:
 
 extern "C" int ibft_set_recover_path(ibft_engine* e, int path) {
   if (e == nullptr || path < IBFT_PATH_AUTO || path > IBFT_PATH_QSPLIT) { set_err("bad recover path"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> g(e->mu);
-  e->recover_path = path;
+  e->recover_path.store(path);
   return IBFT_OK;
 }
 
-uint64_t ibft_engine_launch_count(ibft_engine* e) { return e ? e->launches : 0; }
+extern "C" uint64_t ibft_engine_launch_count(ibft_engine* e) { return e ? e->launches.load() : 0; }
 
 extern "C" int ibft_probe_int_peak(ibft_engine* e, double* imad_per_s, double* wide_mac_per_s) {
   if (!e || !imad_per_s || !wide_mac_per_s) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
   CU(cudaSetDevice(e->p.device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, e->p.device));
@@ -2136,10 +2328,10 @@ extern "C" int ibft_probe_int_peak(ibft_engine* e, double* imad_per_s, double* w
   double best[2] = {0, 0};
   for (int which = 0; which < 2; which++) {
     for (int rep = 0; rep < 4; rep++) {
-      CU(cudaEventRecord(e0, e->stream));
-      if (which == 0) k_probe_imad<<<blocks, threads, 0, e->stream>>>(d_out, 3, 5);
-      else k_probe_wide<<<blocks, threads, 0, e->stream>>>(d_out, 3, 5);
-      CU(cudaEventRecord(e1, e->stream));
+      CU(cudaEventRecord(e0, L->stream));
+      if (which == 0) k_probe_imad<<<blocks, threads, 0, L->stream>>>(d_out, 3, 5);
+      else k_probe_wide<<<blocks, threads, 0, L->stream>>>(d_out, 3, 5);
+      CU(cudaEventRecord(e1, L->stream));
       CU(cudaEventSynchronize(e1));
       float ms = 0;
       CU(cudaEventElapsedTime(&ms, e0, e1));
@@ -2159,7 +2351,8 @@ extern "C" int ibft_probe_int_peak(ibft_engine* e, double* imad_per_s, double* w
 extern "C" int ibft_debug_op(ibft_engine* e, int op, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint32_t n,
                              uint8_t* out, uint32_t out_stride) {
   if (!e || !a || !out || n == 0) { set_err("null argument"); return IBFT_ERR_INVALID_ARG; }
-  std::lock_guard<std::mutex> lk(e->mu);
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
   CU(cudaSetDevice(e->p.device));
   uint8_t *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_o = nullptr;
   int rc = IBFT_OK;
@@ -2171,10 +2364,10 @@ extern "C" int ibft_debug_op(ibft_engine* e, int op, const uint8_t* a, const uin
   if (c) { CUK(cudaMalloc(&d_c, (size_t)n * 64)); CUK(cudaMemcpy(d_c, c, (size_t)n * 64, cudaMemcpyHostToDevice)); }
   CUK(cudaMalloc(&d_o, (size_t)n * out_stride));
   CUK(cudaMemset(d_o, 0, (size_t)n * out_stride));
-  k_debug_op<<<(n + 63) / 64, 64, 0, e->stream>>>(op, d_a, d_b, d_c, n, d_o, out_stride);
+  k_debug_op<<<(n + 63) / 64, 64, 0, L->stream>>>(op, d_a, d_b, d_c, n, d_o, out_stride);
   e->launches++;
   CUK(cudaGetLastError());
-  CUK(cudaStreamSynchronize(e->stream));
+  CUK(cudaStreamSynchronize(L->stream));
   CUK(cudaMemcpy(out, d_o, (size_t)n * out_stride, cudaMemcpyDeviceToHost));
 done:
 #undef CUK

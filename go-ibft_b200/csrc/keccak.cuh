@@ -126,20 +126,28 @@ IBFT_HD void keccak256_two_spans(const uint8_t* p1, uint32_t n1, const uint8_t* 
   uint64_t st[25];
 #pragma unroll
   for (int i = 0; i < 25; i++) st[i] = 0;
+  // a rate block is staged byte by byte (the spans are not aligned to each other) and absorbed as 17 whole lanes, so that the
+  // state never needs a dynamically indexed access (a prepared certificate is ~6,700 blocks)
+  uint8_t blk[136];
   uint32_t pos = 0;
   for (int span = 0; span < 2; span++) {
     const uint8_t* p = span ? p2 : p1;
     uint32_t n = span ? n2 : n1;
     for (uint32_t i = 0; i < n; i++) {
-      st[pos >> 3] ^= (uint64_t)p[i] << (8 * (pos & 7));
+      blk[pos] = p[i];
       if (++pos == 136) {
+#pragma unroll
+        for (int k = 0; k < 17; k++) st[k] ^= load_le64_partial(blk + 8 * k, 8);
         keccak_f1600(st);
         pos = 0;
       }
     }
   }
-  st[pos >> 3] ^= (uint64_t)0x01 << (8 * (pos & 7));
-  st[16] ^= 0x8000000000000000ULL;
+  for (uint32_t i = pos; i < 136; i++) blk[i] = 0;
+  blk[pos] = 0x01;
+  blk[135] |= 0x80;
+#pragma unroll
+  for (int k = 0; k < 17; k++) st[k] ^= load_le64_partial(blk + 8 * k, 8);
   keccak_f1600(st);
 #pragma unroll
   for (int i = 0; i < 4; i++)

@@ -55,7 +55,7 @@ IBFT_HD fe fe_beta() {
 #endif
 
 // dbl-2009-l: 2M + 5S
-IBFT_PT jac jac_double(const jac& p) {
+IBFT_PT jac jac_double_body(const jac& p) {
   jac r;
   // Y = 0 never happens on secp256k1 (no points of order 2), so no exceptional case besides infinity.
   fe a = DSQR(p.x);
@@ -76,7 +76,115 @@ IBFT_PT jac jac_double(const jac& p) {
   return r;
 }
 
+#if defined(IBFT_POINT_BYVAL) && defined(__CUDA_ARCH__)
+// IBFT_POINT_BYVAL: the two hot group-law routines are out-of-line functions taking the point BY VALUE (the whole accumulator
+// travels in registers, like the by-value fe operands of fe_mul) with the field multiplier inlined inside them: one call per
+// point operation, no per-multiplication operand marshalling.
+#undef DMUL
+#undef DSQR
+#undef PMUL
+#undef PSQR
+#define DMUL fe_mul_i
+#define DSQR fe_sqr_i
+#define PMUL fe_mul_i
+#define PSQR fe_sqr_i
+struct jac24 { uint32_t w[24]; };
+__device__ __noinline__ jac24 jac_double_v(jac24 in) {
+  jac p;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { p.x.v[i] = in.w[i]; p.y.v[i] = in.w[8 + i]; p.z.v[i] = in.w[16 + i]; }
+  p.inf = false;
+  fe a = DSQR(p.x);
+  fe b = DSQR(p.y);
+  fe c = DSQR(b);
+  fe t = fe_add(p.x, b);
+  t = DSQR(t);
+  t = fe_sub(t, a);
+  t = fe_sub(t, c);
+  fe d = fe_dbl(t);
+  fe e = fe_add(fe_dbl(a), a);
+  fe f = DSQR(e);
+  fe rx = fe_sub(f, fe_dbl(d));
+  fe c8 = fe_dbl(fe_dbl(fe_dbl(c)));
+  fe ry = fe_sub(DMUL(e, fe_sub(d, rx)), c8);
+  fe rz = fe_dbl(DMUL(p.y, p.z));
+  jac24 o;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { o.w[i] = rx.v[i]; o.w[8 + i] = ry.v[i]; o.w[16 + i] = rz.v[i]; }
+  return o;
+}
+__device__ __forceinline__ jac jac_double(const jac& p) {
+  jac24 in;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { in.w[i] = p.x.v[i]; in.w[8 + i] = p.y.v[i]; in.w[16 + i] = p.z.v[i]; }
+  jac24 o = jac_double_v(in);
+  jac r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { r.x.v[i] = o.w[i]; r.y.v[i] = o.w[8 + i]; r.z.v[i] = o.w[16 + i]; }
+  r.inf = p.inf;
+  return r;
+}
+#else
+IBFT_PT jac jac_double(const jac& p) { return jac_double_body(p); }
+#endif
+
 // p + (qx, qy) with q affine (never infinity): 8M + 3S.  h_out (optional): Z3 / Z1 of the generic case (= H), 1 otherwise.
+#if defined(IBFT_POINT_BYVAL) && defined(__CUDA_ARCH__)
+// generic case only; *flag = 0 generic result, 1 = P + P (caller doubles), 2 = P + (-P) (infinity)
+struct jac33 { uint32_t w[33]; };
+__device__ __noinline__ jac33 jac_madd_v(jac24 in, fe qx, fe qy) {
+  jac p;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { p.x.v[i] = in.w[i]; p.y.v[i] = in.w[8 + i]; p.z.v[i] = in.w[16 + i]; }
+  fe z1z1 = PSQR(p.z);
+  fe u2 = PMUL(qx, z1z1);
+  fe s2 = PMUL(PMUL(qy, p.z), z1z1);
+  fe h = fe_sub(u2, p.x);
+  fe rr = fe_sub(s2, p.y);
+  uint32_t flag = 0;
+  if (fe_is_zero(h)) flag = fe_is_zero(rr) ? 1u : 2u;
+  fe hh = PSQR(h);
+  fe hhh = PMUL(h, hh);
+  fe v = PMUL(p.x, hh);
+  fe rx = fe_sub(fe_sub(PSQR(rr), hhh), fe_dbl(v));
+  fe ry = fe_sub(PMUL(rr, fe_sub(v, rx)), PMUL(p.y, hhh));
+  fe rz = PMUL(p.z, h);
+  jac33 o;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { o.w[i] = rx.v[i]; o.w[8 + i] = ry.v[i]; o.w[16 + i] = rz.v[i]; o.w[24 + i] = h.v[i]; }
+  o.w[32] = flag;
+  return o;
+}
+__device__ __forceinline__ jac jac_add_affine(const jac& p, const fe& qx, const fe& qy, fe* h_out = nullptr) {
+  jac r;
+  if (h_out) *h_out = fe_from_u32(1);
+  if (p.inf) {
+    r.x = qx;
+    r.y = qy;
+    r.z = fe_from_u32(1);
+    r.inf = false;
+    return r;
+  }
+  jac24 in;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { in.w[i] = p.x.v[i]; in.w[8 + i] = p.y.v[i]; in.w[16 + i] = p.z.v[i]; }
+  jac33 o = jac_madd_v(in, qx, qy);
+  if (o.w[32] != 0) {
+    if (o.w[32] == 1u) return jac_double(p);  // P + P
+    r = p;
+    r.inf = true;  // P + (-P)
+    return r;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) { r.x.v[i] = o.w[i]; r.y.v[i] = o.w[8 + i]; r.z.v[i] = o.w[16 + i]; }
+  r.inf = false;
+  if (h_out) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) h_out->v[i] = o.w[24 + i];
+  }
+  return r;
+}
+#else
 IBFT_PT jac jac_add_affine(const jac& p, const fe& qx, const fe& qy, fe* h_out = nullptr) {
   jac r;
   if (h_out) *h_out = fe_from_u32(1);
@@ -108,6 +216,17 @@ IBFT_PT jac jac_add_affine(const jac& p, const fe& qx, const fe& qy, fe* h_out =
   if (h_out) *h_out = h;
   return r;
 }
+#endif
+#if defined(IBFT_POINT_BYVAL) && defined(__CUDA_ARCH__)
+#undef DMUL
+#undef DSQR
+#undef PMUL
+#undef PSQR
+#define PMUL fe_mul
+#define PSQR fe_sqr
+#define DMUL fe_mul
+#define DSQR fe_sqr
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Lane executors.  The group law below is written as LEVELS of up to four independent field multiplications.

@@ -35,6 +35,17 @@ IBFT_HD bool item_digest(const ibft_sig_item& it, const uint8_t* arena, size_t a
       if ((size_t)it.payload_off + it.payload_len > arena_len) return false;
       if (want) keccak256_bytes(arena + it.payload_off, it.payload_len, z);
       return true;
+    case IBFT_KIND_PAYLOAD2: {
+      uint64_t off2 = 0;
+      uint32_t len2 = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) off2 |= (uint64_t)it.digest[i] << (8 * i);
+#pragma unroll
+      for (int i = 0; i < 4; i++) len2 |= (uint32_t)it.digest[8 + i] << (8 * i);
+      if ((size_t)it.payload_off + it.payload_len > arena_len || off2 > arena_len || (size_t)len2 > arena_len - off2) return false;
+      if (want) keccak256_two_spans(arena + it.payload_off, it.payload_len, arena + off2, len2, z);
+      return true;
+    }
     case IBFT_KIND_SEAL: {
       if (!want) return true;
       uint8_t buf[33];

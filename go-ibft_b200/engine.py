@@ -14,7 +14,7 @@ import numpy as np
 from . import build as _build
 
 IBFT_OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_CAPACITY, ERR_VOTING_POWER, ERR_NO_TABLE = range(7)
-KIND_DIGEST, KIND_PAYLOAD, KIND_SEAL, KIND_WIRE, KIND_WIRE_SEAL, KIND_INVALID = 0, 1, 2, 3, 4, 255
+KIND_DIGEST, KIND_PAYLOAD, KIND_SEAL, KIND_WIRE, KIND_WIRE_SEAL, KIND_PAYLOAD2, KIND_INVALID = 0, 1, 2, 3, 4, 5, 255
 ITEM_OK, ITEM_NEEDS_HOST = 0, 1
 NO_TABLE = 0xFFFF
 DBG = dict(FE_MUL=1, FE_SQR=2, FE_INV=3, FE_SQRT=4, SC_MUL=5, SC_INV=6, ECMULT=7, FE_ADD=8, FE_SUB=9, GLV=10)
@@ -24,15 +24,15 @@ ITEM_DTYPE = np.dtype([
     ("r", "u1", 32), ("s", "u1", 32), ("digest", "u1", 32), ("signer", "u1", 20),
     ("v", "u1"), ("kind", "u1"), ("group", "<u2"), ("payload_off", "<u4"), ("payload_len", "<u4"),
 ])
-GROUP_DTYPE = np.dtype([("table_slot", "<u2"), ("flags", "<u2"), ("reserved", "<u4")])
+GROUP_DTYPE = np.dtype([("table_slot", "<u2"), ("flags", "<u2"), ("reserved", "<u4"), ("height", "<u8")])
 RESULT_DTYPE = np.dtype([("power", "<u8", 5), ("n_valid", "<u4"), ("n_distinct", "<u4"), ("has_quorum", "<u4"), ("reserved", "<u4")])
-assert ITEM_DTYPE.itemsize == 128 and GROUP_DTYPE.itemsize == 8 and RESULT_DTYPE.itemsize == 56
+assert ITEM_DTYPE.itemsize == 128 and GROUP_DTYPE.itemsize == 16 and RESULT_DTYPE.itemsize == 56
 
 EXPORTS = [
     "ibft_abi_version", "ibft_last_error", "ibft_engine_create", "ibft_engine_destroy", "ibft_engine_device_info",
-    "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_last_item_status", "ibft_verify_submit", "ibft_verify_poll",
+    "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_verify_batch_ex", "ibft_last_item_status", "ibft_verify_submit", "ibft_verify_poll",
     "ibft_verify_wait", "ibft_bind_groups", "ibft_verify_batch_device", "ibft_quorum_reduce_device", "ibft_quorum_partial_words", "ibft_quorum_mark_device", "ibft_quorum_merge_device",
-    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_set_recover_path", "ibft_refresh_key_tables", "ibft_probe_int_peak", "ibft_debug_op", "ibft_debug_ctable",
+    "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_proposal_hash_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_set_recover_path", "ibft_refresh_key_tables", "ibft_probe_int_peak", "ibft_debug_op", "ibft_debug_ctable",
 ]
 
 
@@ -78,6 +78,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.ibft_get_quorum.argtypes = [c_void_p, c_uint32, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint32)]
     for name in ("ibft_verify_batch", "ibft_verify_submit"):
         getattr(lib, name).argtypes = [c_void_p, c_void_p, c_uint32, c_void_p, c_size_t, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p]
+    lib.ibft_verify_batch_ex.argtypes = [c_void_p, c_void_p, c_uint32, c_void_p, c_size_t, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_uint32]
     lib.ibft_last_item_status.argtypes = [c_void_p, c_void_p, c_uint32]
     lib.ibft_verify_poll.argtypes = [c_void_p, POINTER(c_int)]
     lib.ibft_verify_wait.argtypes = [c_void_p]
@@ -89,6 +91,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.ibft_quorum_merge_device.argtypes = [c_void_p, c_void_p, c_uint32, c_uint32, c_void_p, c_void_p]
     lib.ibft_get_voted_bitmap.argtypes = [c_void_p, c_uint32, c_void_p, c_uint32]
     lib.ibft_keccak256_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_uint32, c_void_p]
+    lib.ibft_proposal_hash_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]
     lib.ibft_sign_batch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]
     lib.ibft_probe_int_peak.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double)]
     lib.ibft_debug_ctable.argtypes = [c_void_p, c_uint32, c_uint32, c_void_p, POINTER(c_int), POINTER(c_uint32)]
@@ -111,6 +114,7 @@ class Engine:
         self.lib = load_library()
         self.params = EngineParams(device, max_items, max_payload_bytes, max_groups, max_table_slots, max_validators, 1 if key_cache else 0)
         self.handle = c_void_p()
+        self.slot_height: dict[int, int] = {}  # slot -> height of the resident validator table (mirrors the engine's own record)
         rc = self.lib.ibft_engine_create(ctypes.byref(self.params), ctypes.byref(self.handle))
         if rc != IBFT_OK:
             self.handle = None
@@ -165,6 +169,17 @@ class Engine:
             assert len(powers_be) == len(addrs)
         self._check(self.lib.ibft_set_validators(self.handle, slot, height, _ptr(addrs) if len(addrs) else None,
                                                  _ptr(powers_be), len(addrs)))
+        self.slot_height[slot] = height
+
+    def groups(self, n_groups: int, slot=0) -> np.ndarray:
+        """n group descriptors; `slot` is one slot for all groups or a sequence of slots.  Each group carries the height of the
+        table resident in its slot (ibft_group_desc.height: a group for another height is refused with ERR_NO_TABLE)."""
+        g = np.zeros(n_groups, dtype=GROUP_DTYPE)
+        slots = [slot] * n_groups if np.isscalar(slot) else list(slot)
+        for i, sl in enumerate(slots):
+            g[i]["table_slot"] = sl
+            g[i]["height"] = self.slot_height.get(int(sl), 0) if sl != NO_TABLE else 0
+        return g
 
     def get_quorum(self, slot: int):
         q = (c_uint64 * 5)()
@@ -173,6 +188,27 @@ class Engine:
         return sum(int(q[i]) << (64 * i) for i in range(5)), int(h.value), int(n.value)
 
     # ---- host-buffer verify (the e2e call)
+    def verify_batch_ex(self, items: np.ndarray, arena: bytes | np.ndarray = b"", groups: np.ndarray | None = None,
+                        voted_stride_words: int = 0):
+        """ibft_verify_batch_ex: returns (bitmap, results, status, voted) -- everything from the call itself (concurrent callers)."""
+        items = np.ascontiguousarray(items)
+        assert items.dtype == ITEM_DTYPE
+        n = len(items)
+        arena_np = np.frombuffer(arena, dtype=np.uint8) if isinstance(arena, (bytes, bytearray)) else np.ascontiguousarray(arena, dtype=np.uint8)
+        bitmap = np.zeros(max(1, (n + 31) // 32), dtype=np.uint32)
+        ng = 0 if groups is None else len(groups)
+        if groups is not None:
+            groups = np.ascontiguousarray(groups)
+            assert groups.dtype == GROUP_DTYPE
+        results = np.zeros(ng, dtype=RESULT_DTYPE) if ng else None
+        status = np.zeros(max(1, n), dtype=np.uint8)
+        voted = np.zeros((ng, voted_stride_words), dtype=np.uint32) if (ng and voted_stride_words) else None
+        self._check(self.lib.ibft_verify_batch_ex(self.handle, _ptr(items) if n else None, n,
+                                                  _ptr(arena_np) if len(arena_np) else None, len(arena_np),
+                                                  _ptr(groups) if ng else None, ng, _ptr(bitmap), _ptr(results), None,
+                                                  _ptr(status), _ptr(voted), voted_stride_words))
+        return bitmap[: (n + 31) // 32], results, status[:n], voted
+
     def verify_batch(self, items: np.ndarray, arena: bytes | np.ndarray = b"", groups: np.ndarray | None = None,
                      want_results: bool = True, want_recovered: bool = False):
         items = np.ascontiguousarray(items)
@@ -254,6 +290,21 @@ class Engine:
         arena = np.frombuffer(b"".join(messages), dtype=np.uint8) if int(lens.sum()) else np.zeros(0, dtype=np.uint8)
         out = np.zeros((n, 32), dtype=np.uint8)
         self._check(self.lib.ibft_keccak256_batch(self.handle, _ptr(arena) if len(arena) else None, len(arena), _ptr(offs), _ptr(lens), n, _ptr(out)))
+        return [bytes(out[i]) for i in range(n)]
+
+    def proposal_hash_batch(self, proposals: list[bytes], rounds: list[int]) -> list[bytes]:
+        """Keccak-256(Keccak-256(raw) || u64_be(round)) for each proposal, both sponges in one launch (IsValidProposalHash)."""
+        n = len(proposals)
+        if n == 0:
+            return []
+        offs = np.zeros(n, dtype=np.uint32)
+        lens = np.array([len(m) for m in proposals], dtype=np.uint32)
+        offs[1:] = np.cumsum(lens)[:-1]
+        arena = np.frombuffer(b"".join(proposals), dtype=np.uint8) if int(lens.sum()) else np.zeros(0, dtype=np.uint8)
+        rd = np.array(rounds, dtype=np.uint64)
+        out = np.zeros((n, 32), dtype=np.uint8)
+        self._check(self.lib.ibft_proposal_hash_batch(self.handle, _ptr(arena) if len(arena) else None, len(arena), _ptr(offs), _ptr(lens),
+                                                      _ptr(rd), n, _ptr(out)))
         return [bytes(out[i]) for i in range(n)]
 
     # ---- signing (MessageConstructor side)

@@ -65,7 +65,12 @@ def load_host() -> ctypes.CDLL:
         lib.ibfthost_num_messages.restype = c_uint64
         lib.ibfthost_prune_by_height.argtypes = [c_void_p, c_uint64]
         lib.ibfthost_prune_by_height.restype = None
-        for f in ("ibfthost_signal_count", "ibfthost_seal_count", "ibfthost_latest_pc_prepares", "ibfthost_gpu_device_calls", "ibfthost_gpu_items_verified"):
+        lib.ibfthost_ingress_storm.argtypes = [c_void_p, c_char_p, POINTER(c_uint32), c_uint32, c_uint32, c_void_p, c_void_p]
+        lib.ibfthost_ingress_storm.restype = ctypes.c_double
+        lib.ibfthost_set_ingress.argtypes = [c_void_p, c_uint32, c_uint32, c_uint32]
+        lib.ibfthost_set_ingress.restype = None
+        for f in ("ibfthost_signal_count", "ibfthost_seal_count", "ibfthost_latest_pc_prepares", "ibfthost_gpu_device_calls", "ibfthost_gpu_items_verified",
+                  "ibfthost_gpu_ingress_requests", "ibfthost_gpu_ingress_flushes"):
             getattr(lib, f).argtypes = [c_void_p]
             getattr(lib, f).restype = c_uint64
         lib.ibfthost_handle_commit.argtypes = [c_void_p, c_uint64, c_uint64]
@@ -260,3 +265,27 @@ class HostContext:
 
     def gpu_items_verified(self) -> int:
         return int(self.lib.ibfthost_gpu_items_verified(self.ctx))
+
+    # ---- ingress coalescer (single-message IsValidValidator calls from many threads)
+    def set_ingress(self, max_batch: int = 4096, min_batch: int = 1, linger_us: int = 0):
+        self.lib.ibfthost_set_ingress(self.ctx, max_batch, min_batch, linger_us)
+
+    def ingress_storm(self, wires: list[bytes], threads: int):
+        """Every wire message is checked with ONE single-message IsValidValidator call, from `threads` concurrent native
+        threads.  Returns (verdicts uint8[n], per-call latency in us float32[n], elapsed us)."""
+        import numpy as np
+        n = len(wires)
+        lens = (c_uint32 * n)(*[len(w) for w in wires])
+        verdicts = np.zeros(n, dtype=np.uint8)
+        lat = np.zeros(n, dtype=np.float32)
+        us = self.lib.ibfthost_ingress_storm(self.ctx, b"".join(wires), lens, n, threads, verdicts.ctypes.data_as(c_void_p),
+                                             lat.ctypes.data_as(c_void_p))
+        if us < 0:
+            raise ValueError("undecodable wire message")
+        return verdicts, lat, float(us)
+
+    def gpu_ingress_requests(self) -> int:
+        return int(self.lib.ibfthost_gpu_ingress_requests(self.ctx))
+
+    def gpu_ingress_flushes(self) -> int:
+        return int(self.lib.ibfthost_gpu_ingress_flushes(self.ctx))

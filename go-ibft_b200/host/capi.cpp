@@ -4,7 +4,10 @@
 // every decision (tests/test_host_logic.py); (2) it is the shape of the calls the Go shim makes.
 // Verifier kinds: 0 = callback verifier (function pointers; the reference's mockBackend), 1 = GPU verifier (C ABI ->
 // CUDA kernels).  Everything is plain C types; byte strings are (ptr, len); variable-size outputs use caller buffers.
+#include <algorithm>
+#include <chrono>
 #include <cstring>
+#include <thread>
 
 #include "ibft_logic.hpp"
 
@@ -253,6 +256,45 @@ int ibfthost_verify_committed_seals(ibfthost_ctx* c, const uint8_t* hash, size_t
   if (n_valid) *n_valid = cnt;
   return (int)c->vm.HasQuorum(who);
 }
+
+// Ingress storm (test + bench harness of the coalescer): `count` wire messages are checked with SINGLE-message
+// IsValidValidator calls from `threads` concurrent threads (thread t takes messages t, t+threads, ...), exactly the call
+// pattern of the reference's gossip ingress (core/ibft.go:1101-1128).  verdicts[i] = the call's answer; lat_us[i] = its
+// wall-clock latency (may be NULL).  Returns the elapsed wall time in microseconds, or -1 on a decode error.
+double ibfthost_ingress_storm(ibfthost_ctx* c, const uint8_t* wires, const uint32_t* lens, uint32_t count, uint32_t threads,
+                              uint8_t* verdicts, float* lat_us) {
+  std::vector<MessagePtr> msgs(count);
+  size_t off = 0;
+  for (uint32_t i = 0; i < count; i++) {
+    msgs[i] = dec(wires + off, lens[i]);
+    off += lens[i];
+    if (!msgs[i]) return -1.0;
+  }
+  if (threads == 0) threads = 1;
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> pool;
+  for (uint32_t t = 0; t < threads; t++) {
+    pool.emplace_back([&, t]() {
+      for (uint32_t i = t; i < count; i += threads) {
+        auto a = std::chrono::steady_clock::now();
+        bool ok = c->verifier->IsValidValidator(*msgs[i]);
+        auto b = std::chrono::steady_clock::now();
+        verdicts[i] = ok ? 1 : 0;
+        if (lat_us) lat_us[i] = std::chrono::duration<float, std::micro>(b - a).count();
+      }
+    });
+  }
+  for (auto& th : pool) th.join();
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+}
+void ibfthost_set_ingress(ibfthost_ctx* c, uint32_t max_batch, uint32_t min_batch, uint32_t linger_us) {
+  if (!c->gpu) return;
+  c->gpu->ingress_max_batch = max_batch ? max_batch : 1;
+  c->gpu->ingress_min_batch = min_batch;
+  c->gpu->ingress_linger_us = linger_us;
+}
+uint64_t ibfthost_gpu_ingress_requests(ibfthost_ctx* c) { return c->gpu ? c->gpu->ingress_requests() : 0; }
+uint64_t ibfthost_gpu_ingress_flushes(ibfthost_ctx* c) { return c->gpu ? c->gpu->ingress_flushes() : 0; }
 
 uint64_t ibfthost_gpu_device_calls(ibfthost_ctx* c) { return c->gpu ? c->gpu->device_calls() : 0; }
 uint64_t ibfthost_gpu_items_verified(ibfthost_ctx* c) { return c->gpu ? c->gpu->items_verified() : 0; }

@@ -167,9 +167,15 @@ inline Bytes payload_no_sig(const IbftMessage& m) { return encode_message(m, fal
 
 // ----------------------------------------------------------------------------------------------- decoder
 namespace wire {
+// Nesting bound of the decoder.  A valid frame nests at most 4 messages deep (PREPREPARE -> RoundChangeCertificate ->
+// ROUND_CHANGE -> PreparedCertificate -> PREPARE); decoding runs BEFORE any signature check, so an unauthenticated peer must
+// not be able to exhaust the native stack with a few hundred KB of nested wrappers (protobuf-go caps recursion at 10,000 on
+// growable stacks; a C++ frame is not growable).  Every sub-reader inherits depth + 1; decode_message refuses depth > kMaxDepth.
+constexpr int kMaxDepth = 32;
 struct Reader {
   const uint8_t* p;
   const uint8_t* end;
+  int depth = 0;
   bool done() const { return p >= end; }
   uint64_t varint() {
     uint64_t v = 0;
@@ -194,7 +200,8 @@ struct Reader {
       case 2: {
         uint64_t n = varint();
         if (n > (uint64_t)(end - p)) throw DecodeError("truncated bytes");
-        sub = Reader{p, p + n};
+        sub = Reader{p, p + n, depth + 1};
+        if (sub.depth > kMaxDepth) throw DecodeError("message nesting too deep");
         p += n;
         break;
       }
@@ -220,7 +227,7 @@ inline std::shared_ptr<Proposal> decode_proposal(wire::Reader r) {
   auto p = std::make_shared<Proposal>();
   uint32_t num, wt;
   uint64_t val;
-  wire::Reader sub{nullptr, nullptr};
+  wire::Reader sub{nullptr, nullptr, 0};
   while (r.next(num, wt, val, sub)) {
     if (num == 1 && wt == 2) p->raw_proposal = sub.bytes();
     else if (num == 2 && wt == 0) p->round = val;
@@ -231,7 +238,7 @@ inline std::shared_ptr<PreparedCertificate> decode_pc(wire::Reader r) {
   auto pc = std::make_shared<PreparedCertificate>();
   uint32_t num, wt;
   uint64_t val;
-  wire::Reader sub{nullptr, nullptr};
+  wire::Reader sub{nullptr, nullptr, 0};
   while (r.next(num, wt, val, sub)) {
     if (num == 1 && wt == 2) pc->proposal_message = decode_message(sub);
     else if (num == 2 && wt == 2) pc->prepare_messages.push_back(decode_message(sub));
@@ -242,7 +249,7 @@ inline std::shared_ptr<RoundChangeCertificate> decode_rcc(wire::Reader r) {
   auto c = std::make_shared<RoundChangeCertificate>();
   uint32_t num, wt;
   uint64_t val;
-  wire::Reader sub{nullptr, nullptr};
+  wire::Reader sub{nullptr, nullptr, 0};
   while (r.next(num, wt, val, sub))
     if (num == 1 && wt == 2) c->round_change_messages.push_back(decode_message(sub));
   return c;
@@ -252,13 +259,13 @@ inline MessagePtr decode_message(wire::Reader r) {
   auto m = std::make_shared<IbftMessage>();
   uint32_t num, wt;
   uint64_t val;
-  wire::Reader sub{nullptr, nullptr};
+  wire::Reader sub{nullptr, nullptr, 0};
   while (r.next(num, wt, val, sub)) {
     if (num == 1 && wt == 2) {
       auto v = std::make_shared<View>();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr};
+      wire::Reader s2{nullptr, nullptr, 0};
       while (sub.next(n2, w2, v2, s2)) {
         if (n2 == 1 && w2 == 0) v->height = v2;
         else if (n2 == 2 && w2 == 0) v->round = v2;
@@ -275,7 +282,7 @@ inline MessagePtr decode_message(wire::Reader r) {
       m->preprepare = PrePrepareMessage();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr};
+      wire::Reader s2{nullptr, nullptr, 0};
       while (sub.next(n2, w2, v2, s2)) {
         if (n2 == 1 && w2 == 2) m->preprepare.proposal = decode_proposal(s2);
         else if (n2 == 2 && w2 == 2) m->preprepare.proposal_hash = s2.bytes();
@@ -286,7 +293,7 @@ inline MessagePtr decode_message(wire::Reader r) {
       m->prepare = PrepareMessage();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr};
+      wire::Reader s2{nullptr, nullptr, 0};
       while (sub.next(n2, w2, v2, s2))
         if (n2 == 1 && w2 == 2) m->prepare.proposal_hash = s2.bytes();
     } else if (num == 7 && wt == 2) {
@@ -294,7 +301,7 @@ inline MessagePtr decode_message(wire::Reader r) {
       m->commit = CommitMessage();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr};
+      wire::Reader s2{nullptr, nullptr, 0};
       while (sub.next(n2, w2, v2, s2)) {
         if (n2 == 1 && w2 == 2) m->commit.proposal_hash = s2.bytes();
         else if (n2 == 2 && w2 == 2) m->commit.committed_seal = s2.bytes();
@@ -304,7 +311,7 @@ inline MessagePtr decode_message(wire::Reader r) {
       m->round_change = RoundChangeMessage();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr};
+      wire::Reader s2{nullptr, nullptr, 0};
       while (sub.next(n2, w2, v2, s2)) {
         if (n2 == 1 && w2 == 2) m->round_change.last_prepared_proposal = decode_proposal(s2);
         else if (n2 == 2 && w2 == 2) m->round_change.latest_prepared_certificate = decode_pc(s2);
@@ -315,7 +322,7 @@ inline MessagePtr decode_message(wire::Reader r) {
 }
 
 inline MessagePtr decode_message(const uint8_t* data, size_t len) {
-  MessagePtr m = decode_message(wire::Reader{data, data + len});
+  MessagePtr m = decode_message(wire::Reader{data, data + len, 0});
   m->raw_wire.assign((const char*)data, len);
   return m;
 }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IBFT_ABI_VERSION 1
+#define IBFT_ABI_VERSION 2
 
 /* status codes */
 #define IBFT_OK 0
@@ -32,7 +32,7 @@ extern "C" {
 #define IBFT_ERR_CUDA 3        /* a CUDA call or kernel launch failed; see ibft_last_error() */
 #define IBFT_ERR_CAPACITY 4    /* batch exceeds the capacity given at ibft_engine_create */
 #define IBFT_ERR_VOTING_POWER 5 /* total voting power is zero: core/validator_manager.go:66-68 errVotingPowerNotCorrect */
-#define IBFT_ERR_NO_TABLE 6    /* a group references a validator-table slot that was never set */
+#define IBFT_ERR_NO_TABLE 6    /* a group references a validator-table slot that was never set, or that holds ANOTHER height's table */
 
 /* ibft_sig_item.kind */
 #define IBFT_KIND_DIGEST 0   /* `digest` is the 32-byte message digest z itself */
@@ -47,6 +47,12 @@ extern "C" {
                                 and item status IBFT_ITEM_NEEDS_HOST: the host re-submits those as IBFT_KIND_PAYLOAD. */
 #define IBFT_KIND_WIRE_SEAL 4 /* same frame; checks the committed seal instead: commitData.committedSeal over
                                 Keccak-256(commitData.proposalHash || 0x02), signer = From (IsValidCommittedSeal on the frame) */
+#define IBFT_KIND_PAYLOAD2 5  /* z = Keccak-256(arena[payload_off .. +payload_len] || arena[off2 .. +len2]) with off2 = u64 little-endian in
+                                digest[0..8) and len2 = u32 little-endian in digest[8..12): PayloadNoSig given as TWO spans.  A
+                                ROUND_CHANGE message's signed bytes end with its whole prepared certificate (909 KB at 10k validators,
+                                messages/proto/messages.proto:95-103); the 10,000 ROUND_CHANGE messages of a round mostly embed the SAME
+                                certificate, so the caller uploads each distinct certificate once and every message's tuple names
+                                (its own head, the shared tail).  Same verdict as IBFT_KIND_PAYLOAD over the concatenation. */
 #define IBFT_KIND_INVALID 255 /* structurally invalid on the host side (nil seal, signature length != 65, ...):
                                  verdict is always 0.  Mirrors "malformed input => false" (messages/helpers.go:38-42). */
 
@@ -73,12 +79,17 @@ typedef struct ibft_sig_item {
 } ibft_sig_item;        /* sizeof == 128 */
 
 /* A group is one quorum domain: all items of one (height, round, message type).  Its validator
- * table supplies set membership and voting power (core/validator_manager.go:77-96 HasQuorum). */
+ * table supplies set membership and voting power (core/validator_manager.go:77-96 HasQuorum).
+ * `height` is the height the group's messages carry (msg.View.Height): IsValidValidator must answer for "one of the validators
+ * at the height in message" (core/backend.go:41-45), so a call whose group names a slot that currently holds ANOTHER height's
+ * table (e.g. a caller mapping height % slots after the slot was recycled) fails with IBFT_ERR_NO_TABLE -- it is never
+ * answered from the wrong validator set. */
 typedef struct ibft_group_desc {
   uint16_t table_slot; /* slot given to ibft_set_validators, or IBFT_NO_TABLE */
   uint16_t flags;      /* reserved, 0 */
-  uint32_t reserved;
-} ibft_group_desc;
+  uint32_t reserved;   /* 0 */
+  uint64_t height;     /* height of the group's messages; must equal the height the slot was set with (ignored for IBFT_NO_TABLE) */
+} ibft_group_desc;     /* sizeof == 16 */
 
 /* Per-group result of the on-device quorum reduction.
  * power[] is the little-endian 320-bit sum of votingPower over the DISTINCT validators with >= 1 valid
@@ -154,6 +165,20 @@ int ibft_verify_batch(ibft_engine* e, const ibft_sig_item* items, uint32_t n, co
                       const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
                       ibft_group_result* results_out, uint8_t* recovered_out);
 
+/* The same call with everything a CONCURRENT caller needs returned by the call itself (the two getters below describe "the
+ * most recent completed call of the engine", which is only meaningful to a single-threaded caller -- and a goroutine may
+ * change OS threads between two cgo calls):
+ *   status_out  NULL, or n bytes receiving the per-item status (IBFT_ITEM_*)
+ *   voted_out   NULL, or n_groups x voted_stride_words words: row g = the voted set of group g (bit i = validator i of the
+ *               group's table has >= 1 valid item), zero-padded -- the bitmap core/validator_manager.go's quorum check reads
+ *               (HasQuorumVoted in INTEGRATION.md).  Requires results_out.
+ * Concurrency: the engine runs up to two host-buffer calls at a time (a full-capacity lane and a small lane of
+ * min(max_items, 16,384) items / 4 MiB of payload); further callers block.  ibft_set_validators waits for both. */
+int ibft_verify_batch_ex(ibft_engine* e, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
+                         const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
+                         ibft_group_result* results_out, uint8_t* recovered_out, uint8_t* status_out, uint32_t* voted_out,
+                         uint32_t voted_stride_words);
+
 /* Per-item status (IBFT_ITEM_*) of the most recent completed ibft_verify_batch / ibft_verify_wait on this engine. */
 int ibft_last_item_status(ibft_engine* e, uint8_t* status_out, uint32_t n);
 
@@ -205,6 +230,14 @@ int ibft_get_voted_bitmap(ibft_engine* e, uint32_t group, uint32_t* words_out, u
 int ibft_keccak256_batch(ibft_engine* e, const uint8_t* arena, size_t arena_len, const uint32_t* offsets,
                          const uint32_t* lens, uint32_t n, uint8_t* out32);
 
+/* The proposal hash of this engine's synthetic convention (real embedders hash an RLP header), both sponges in
+ * ONE launch: out32[i] = Keccak-256(Keccak-256(rawProposal_i) || u64_be(rounds[i])).  IsValidProposalHash(proposal, hash)
+ * (core/backend.go:50-51; "hash matches keccak(proposal)", core/ibft.go:648-649, :781-787) compares this with the claimed hash.
+ * Same argument layout as ibft_keccak256_batch.  Hash calls have their own lock, stream and grow-only scratch: they neither
+ * wait for verify calls nor allocate device memory per call.  HOST buffers. */
+int ibft_proposal_hash_batch(ibft_engine* e, const uint8_t* arena, size_t arena_len, const uint32_t* offsets,
+                             const uint32_t* lens, const uint64_t* rounds, uint32_t n, uint8_t* out32);
+
 /* signing (the MessageConstructor side) --------------------------------------------------------------- */
 /* Batched ECDSA signing for MessageConstructor (core/backend.go:12-34: every Build*Message must be signed by the validator,
  * BuildCommitMessage must create the committed seal).  privkeys, digests: n x 32 bytes big-endian; nonces: n x 32 bytes or
@@ -221,7 +254,8 @@ int ibft_sign_batch(ibft_engine* e, const uint8_t* privkeys, const uint8_t* dige
  *   SPLIT   chain warps (one lane per signature) + a helper warp per CTA that takes the digest, r^-1, sqrt and u1*G off the
  *           chain (mid-size batches: up to SMs x 96 signatures in one wave, e.g. a 10k-validator COMMIT round);
  *   QSPLIT  both: four-lane chain warps + a helper warp (small rounds: up to SMs x 24 signatures in one wave).
- * North star: "one CUDA thread (or several lanes) per signature".  Returns IBFT_ERR_INVALID_ARG for an unknown path. */
+ * (The north star asks for one warp per signature; DESIGN.md §3.1 measures why the throughput path uses one thread per
+ * signature and the latency paths four lanes / a chain+helper warp pair instead.)  Returns IBFT_ERR_INVALID_ARG for an unknown path. */
 #define IBFT_PATH_AUTO 0
 #define IBFT_PATH_THREAD 1
 #define IBFT_PATH_QUAD 2

@@ -16,4 +16,21 @@ anchored on independent known-answer vectors (Keccak KATs, privkey 1 -> G -> add
 package (OpenSSL) in tests/test_oracle_crypto.py.  What the reference's tests DO pin -- quorum
 arithmetic, validPC / validateProposal decision tables, store pruning semantics, proto encoding --
 is restated in ``ibft_logic.py`` / ``ibft_proto.py`` and checked against those tables.
+
+THIRD-PARTY ANCHORS (round 2).  The arithmetic's real home is the go-ethereum lineage (polygon-edge's Backend: btcec-based
+recovery + legacy Keccak).  tests/golden/third_party_recover.json holds published known answers from that lineage --
+go-ethereum's crypto/signature_test.go triple (testmsg, testsig, testpubkey), the EIP-155 worked example, five RFC 6979
+secp256k1 known answers (nonce, r, s) -- each validated mathematically (the triple recovers the PUBLISHED key; the RFC 6979
+entries reproduce the published k, r, s bit for bit; OpenSSL agrees on the verify equation) and run against both oracles
+(tests/test_oracle_crypto.py) and the CUDA kernels (tests/test_gpu_round2.py).  Which malformed inputs each source accepts:
+
+  source                                   high-s   v >= 2                      x = r + n
+  this engine / this oracle                accept   reject                      unsupported (reject)
+  go-ethereum crypto.Ecrecover (libsecp)   accept   2,3 = x = r + n             accept when r + n < p
+  btcec RecoverCompact                     accept   header 27..34 = recid 0..3  accept
+  polygon-edge crypto.RecoverPubkey        accept   V != 1 is READ AS 0         (recid 2,3 unreachable)
+
+High-s is accepted everywhere on the recover path (low-s is a transaction rule, EIP-2), and so it is here.  The two places
+this engine is stricter -- V outside {0,1}, and nonce points with x >= n (probability 2^-128, not targetable) -- can only be
+reached by a Byzantine sender and only make that sender's own message invalid on this node.
 """

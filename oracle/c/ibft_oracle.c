@@ -478,6 +478,20 @@ int oracle_item_digest(const ibft_sig_item* it, const uint8_t* arena, size_t are
       if ((size_t)it->payload_off + it->payload_len > arena_len) return 0;
       oracle_keccak256(arena + it->payload_off, it->payload_len, z);
       return 1;
+    case IBFT_KIND_PAYLOAD2: { /* PayloadNoSig as two spans (a ROUND_CHANGE head + its shared prepared certificate) */
+      uint64_t off2 = 0; uint32_t len2 = 0;
+      for (int i = 0; i < 8; i++) off2 |= (uint64_t)it->digest[i] << (8 * i);
+      for (int i = 0; i < 4; i++) len2 |= (uint32_t)it->digest[8 + i] << (8 * i);
+      if ((size_t)it->payload_off + it->payload_len > arena_len || off2 > arena_len || (size_t)len2 > arena_len - off2) return 0;
+      size_t total = (size_t)it->payload_len + len2;
+      uint8_t* buf = (uint8_t*)malloc(total ? total : 1);
+      if (!buf) return 0;
+      memcpy(buf, arena + it->payload_off, it->payload_len);
+      memcpy(buf + it->payload_len, arena + off2, len2);
+      oracle_keccak256(buf, total, z);
+      free(buf);
+      return 1;
+    }
     case IBFT_KIND_SEAL: {
       uint8_t buf[33];
       memcpy(buf, it->digest, 32);
@@ -517,7 +531,10 @@ static void* worker(void* arg) {
   for (uint32_t i = j->lo; i < j->hi; i++) {
     const ibft_sig_item* it = &j->items[i];
     const uint8_t* tab = NULL; uint32_t tn = 0;
-    if (j->group_table && it->group < j->n_groups && j->group_table[it->group] != 0xFFFF) {
+    /* an item whose group index is outside the call's groups belongs to no quorum domain and no validator set: verdict 0
+     * (IsValidValidator needs "one of the validators at the height in message", core/backend.go:41-45) */
+    if (j->group_table && it->group >= j->n_groups) { j->verdict[i] = 0; continue; }
+    if (j->group_table && j->group_table[it->group] != 0xFFFF) {
       tab = j->tables[j->group_table[it->group]];
       tn = j->table_n[j->group_table[it->group]];
     }
@@ -568,4 +585,97 @@ int oracle_verify_batch(const ibft_sig_item* items, uint32_t n, const uint8_t* a
   for (uint32_t t = 0; t < n_tables; t++) free(sorted_tabs[t]);
   free(sorted_tabs);
   return 0;
+}
+
+/* ---- bulk workload generation (tests/workloads.py: the full-size BASELINE configs 4 and 5 need 10^5 keys and signatures;
+ * one ctypes call per key from Python would take minutes).  Same primitives as above, spread over threads. ---- */
+typedef void (*range_fn)(uint32_t lo, uint32_t hi, void* ctx);
+typedef struct { range_fn fn; uint32_t lo, hi; void* ctx; } range_job;
+static void* range_worker(void* a) { range_job* j = (range_job*)a; j->fn(j->lo, j->hi, j->ctx); return NULL; }
+static void parallel_ranges(uint32_t n, int n_threads, range_fn fn, void* ctx) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  pthread_once(&g_once, init_g_table);
+  pthread_t th[256];
+  range_job jobs[256];
+  uint32_t per = (n + (uint32_t)n_threads - 1) / (uint32_t)n_threads;
+  int started = 0;
+  for (int t = 0; t < n_threads; t++) {
+    uint32_t lo = (uint32_t)t * per, hi = lo + per > n ? n : lo + per;
+    if (lo >= hi) break;
+    jobs[t] = (range_job){fn, lo, hi, ctx};
+    if (n_threads == 1) range_worker(&jobs[t]);
+    else pthread_create(&th[t], NULL, range_worker, &jobs[t]);
+    started++;
+  }
+  if (n_threads > 1)
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+}
+
+/* privkey_i = Keccak-256("ibft-b200-validator" || u32_be(seed) || u32_be(i)) mod (n-1) + 1   (SURVEY.md §8d), i = first.. */
+void oracle_privkeys(uint32_t seed, uint32_t first, uint32_t n, uint8_t* out32) {
+  u256 one = {{1, 0, 0, 0}}, nm1;
+  sub256(&nm1, &FN, &one);
+  for (uint32_t k = 0; k < n; k++) {
+    uint32_t i = first + k;
+    uint8_t buf[27] = "ibft-b200-validator";
+    buf[19] = (uint8_t)(seed >> 24); buf[20] = (uint8_t)(seed >> 16); buf[21] = (uint8_t)(seed >> 8); buf[22] = (uint8_t)seed;
+    buf[23] = (uint8_t)(i >> 24); buf[24] = (uint8_t)(i >> 16); buf[25] = (uint8_t)(i >> 8); buf[26] = (uint8_t)i;
+    uint8_t h[32];
+    oracle_keccak256(buf, 27, h);
+    u256 x = from_be(h);
+    while (cmp256(&x, &nm1) >= 0) sub256(&x, &x, &nm1);
+    add256(&x, &x, &one);
+    to_be(&x, out32 + 32 * (size_t)k);
+  }
+}
+
+typedef struct { const uint8_t* privs; uint8_t* out20; } addr_ctx;
+static void addr_range(uint32_t lo, uint32_t hi, void* c) {
+  addr_ctx* a = (addr_ctx*)c;
+  for (uint32_t i = lo; i < hi; i++) {
+    uint8_t pub[64], h[32];
+    if (!oracle_pubkey_from_scalar(a->privs + 32 * (size_t)i, pub)) { memset(a->out20 + 20 * (size_t)i, 0, 20); continue; }
+    oracle_keccak256(pub, 64, h);
+    memcpy(a->out20 + 20 * (size_t)i, h + 12, 20);
+  }
+}
+/* address_i = Keccak-256(X||Y)[12:] of privs[i]*G */
+void oracle_addresses(const uint8_t* privs32, uint32_t n, uint8_t* out20, int n_threads) {
+  addr_ctx c = {privs32, out20};
+  parallel_ranges(n, n_threads, addr_range, &c);
+}
+
+typedef struct { const uint8_t* privs; const uint8_t* digests; uint8_t* out65; } sign_ctx;
+static void sign_range(uint32_t lo, uint32_t hi, void* c) {
+  sign_ctx* s = (sign_ctx*)c;
+  for (uint32_t i = lo; i < hi; i++) {
+    const uint8_t* d = s->privs + 32 * (size_t)i;
+    const uint8_t* z = s->digests + 32 * (size_t)i;
+    uint8_t* o = s->out65 + 65 * (size_t)i;
+    int ok = 0;
+    /* derived nonce, the rule of the engine's k_sign: k = Keccak-256(d || z || ctr), ctr = 0, 1, ... until usable */
+    for (uint32_t ctr = 0; ctr < 4 && !ok; ctr++) {
+      uint8_t buf[65], k[32];
+      memcpy(buf, d, 32); memcpy(buf + 32, z, 32); buf[64] = (uint8_t)ctr;
+      oracle_keccak256(buf, 65, k);
+      ok = oracle_sign_with_k(d, z, k, 1, o);
+    }
+    if (!ok) memset(o, 0, 65);
+  }
+}
+/* sigs[i] = ECDSA(privs[i], digests[i]) with the deterministic Keccak-derived nonce, low-s, R||S||V */
+void oracle_sign_derived_batch(const uint8_t* privs32, const uint8_t* digests32, uint32_t n, uint8_t* out65, int n_threads) {
+  sign_ctx c = {privs32, digests32, out65};
+  parallel_ranges(n, n_threads, sign_range, &c);
+}
+
+typedef struct { const uint8_t* arena; const uint64_t* offs; const uint32_t* lens; uint8_t* out32; } kb_ctx;
+static void kb_range(uint32_t lo, uint32_t hi, void* c) {
+  kb_ctx* k = (kb_ctx*)c;
+  for (uint32_t i = lo; i < hi; i++) oracle_keccak256(k->arena + k->offs[i], k->lens[i], k->out32 + 32 * (size_t)i);
+}
+void oracle_keccak256_batch(const uint8_t* arena, const uint64_t* offs, const uint32_t* lens, uint32_t n, uint8_t* out32, int n_threads) {
+  kb_ctx c = {arena, offs, lens, out32};
+  parallel_ranges(n, n_threads, kb_range, &c);
 }

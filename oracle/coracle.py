@@ -117,3 +117,43 @@ def verify_batch(items: np.ndarray, arena: bytes = b"", tables=None, group_table
     if rc != 0:
         raise RuntimeError("oracle_verify_batch failed")
     return bitmap
+
+
+# ---- bulk workload generation (tests/workloads.py: full-size configs 4 and 5)
+def _u8(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def privkeys(seed: int, n: int, first: int = 0) -> np.ndarray:
+    """(n, 32) big-endian private keys of SURVEY.md §8d's derivation."""
+    out = np.zeros((n, 32), dtype=np.uint8)
+    lib().oracle_privkeys(ctypes.c_uint32(seed), ctypes.c_uint32(first), ctypes.c_uint32(n), out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def addresses(privs: np.ndarray, n_threads: int = 8) -> np.ndarray:
+    privs = _u8(privs).reshape(-1, 32)
+    out = np.zeros((len(privs), 20), dtype=np.uint8)
+    lib().oracle_addresses(privs.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(len(privs)), out.ctypes.data_as(ctypes.c_void_p),
+                           ctypes.c_int(n_threads))
+    return out
+
+
+def sign_derived_batch(privs: np.ndarray, digests: np.ndarray, n_threads: int = 8) -> np.ndarray:
+    """(n, 65) signatures R||S||V with the deterministic Keccak-derived nonce (k = Keccak-256(d || z || ctr)), low-s."""
+    privs, digests = _u8(privs).reshape(-1, 32), _u8(digests).reshape(-1, 32)
+    assert len(privs) == len(digests)
+    out = np.zeros((len(privs), 65), dtype=np.uint8)
+    lib().oracle_sign_derived_batch(privs.ctypes.data_as(ctypes.c_void_p), digests.ctypes.data_as(ctypes.c_void_p),
+                                    ctypes.c_uint32(len(privs)), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n_threads))
+    return out
+
+
+def keccak256_batch(arena: bytes | np.ndarray, offs, lens, n_threads: int = 8) -> np.ndarray:
+    a = np.frombuffer(arena, dtype=np.uint8) if isinstance(arena, (bytes, bytearray)) else _u8(arena)
+    offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    lens = np.ascontiguousarray(lens, dtype=np.uint32)
+    out = np.zeros((len(offs), 32), dtype=np.uint8)
+    lib().oracle_keccak256_batch(a.ctypes.data_as(ctypes.c_void_p), offs.ctypes.data_as(ctypes.c_void_p), lens.ctypes.data_as(ctypes.c_void_p),
+                                 ctypes.c_uint32(len(offs)), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n_threads))
+    return out

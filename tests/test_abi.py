@@ -26,8 +26,8 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = ib.load_library()
-    assert lib.ibft_abi_version() == 1
-    assert ib.ITEM_DTYPE.itemsize == 128 and ib.GROUP_DTYPE.itemsize == 8 and ib.RESULT_DTYPE.itemsize == 56
+    assert lib.ibft_abi_version() == 2
+    assert ib.ITEM_DTYPE.itemsize == 128 and ib.GROUP_DTYPE.itemsize == 16 and ib.RESULT_DTYPE.itemsize == 56
 
 
 @pytest.mark.skipif(has_gpu(), reason="only meaningful on a CPU-only box")

@@ -187,7 +187,7 @@ def test_quorum_from_gpu_voted_bitmap(engine):
     d = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "config2.npz"))
     items = np.ascontiguousarray(d["items"]).view(ib.ITEM_DTYPE).reshape(-1)
     engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
-    groups = np.zeros(len(d["groups"]), dtype=ib.GROUP_DTYPE)
+    groups = engine.groups(len(d["groups"]))
     seal_group = list(d["groups"]).index("COMMIT_SEAL")
     sub = items[items["group"] == seal_group]
     c = host.HostContext("callback")

@@ -25,7 +25,7 @@ def test_learn_then_verify_gives_the_golden_bitmap(name):
     try:
         eng.set_recover_path(ib.Engine.PATH_THREAD)  # the kernel that holds the verify path
         eng.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
-        groups = groups_for(len(d["groups"]))
+        groups = groups_for(eng, len(d["groups"]))
         assert eng.refresh_key_tables() == 0
         bm1, res1, _ = eng.verify_batch(items, d["arena"], groups)          # recover path, keys learned, tables built on the way out
         assert np.array_equal(bm1, d["bitmap"])
@@ -62,7 +62,7 @@ def test_rejected_verifications_fall_back_to_recovery_exactly():
     try:
         eng.set_recover_path(ib.Engine.PATH_THREAD)
         eng.set_validators(0, 9, vs.addr_array(), vs.power_array())
-        groups = groups_for(1)
+        groups = groups_for(eng, 1)
         # round 1: everybody signs once -> all keys learned
         dig0 = co.keccak256(b"round-1")
         warm = np.concatenate([wl.make_item(wl.sign(vs.keys[i], dig0), vs.addrs[i], 0, dig0) for i in range(48)])  # 16 stay unknown

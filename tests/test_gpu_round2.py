@@ -1,0 +1,217 @@
+"""Round-2 boundary and concurrency tests (GPU): height-checked group descriptors, oracle/kernel agreement on out-of-range
+groups, the two-span payload kind, the _ex call, concurrent host-buffer calls (two lanes), the ingress coalescer, the one-launch
+proposal hash, and the third-party recover vectors on the device."""
+import importlib
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import ibft_b200 as ib
+import workloads as wl
+from oracle import coracle as co
+from oracle import ibft_proto as ip
+
+pytestmark = pytest.mark.gpu
+host = importlib.import_module("go-ibft_b200.host")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_group_for_another_height_is_refused_not_answered_from_the_wrong_table(engine):
+    """core/backend.go:41-45: "one of the validators at the height in message".  A slot recycled for height H + k*slots must
+    not answer for H (the Go-shim defect of round 1): the engine compares ibft_group_desc.height with the slot's height."""
+    vs = wl.ValidatorSet(31, 8)
+    engine.set_validators(3, 1_000_003, vs.addr_array(), None)
+    dig = co.keccak256(b"height check")
+    it = wl.make_item(wl.sign(vs.keys[0], dig), vs.addrs[0], 0, dig, 0)
+    g = engine.groups(1, slot=3)
+    assert int(g[0]["height"]) == 1_000_003
+    bitmap, _, _ = engine.verify_batch(it, b"", g)
+    assert int(bitmap[0]) == 1
+    g[0]["height"] = 1_000_003 + 16            # same slot under "height % 16", another height
+    with pytest.raises(ib.EngineError) as ei:
+        engine.verify_batch(it, b"", g)
+    assert ei.value.code == ib.engine.ERR_NO_TABLE
+    with pytest.raises(ib.EngineError) as ei:
+        engine.bind_groups(g)
+    assert ei.value.code == ib.engine.ERR_NO_TABLE
+    # IBFT_NO_TABLE groups carry no height
+    g2 = engine.groups(1, slot=ib.NO_TABLE)
+    g2[0]["height"] = 12345
+    bitmap, _, _ = engine.verify_batch(it, b"", g2)
+    assert int(bitmap[0]) == 1
+
+
+def test_out_of_range_group_matches_the_oracle(engine):
+    """round-1 verdict: oracle and kernel disagreed by construction on group >= n_groups.  Both now answer 0."""
+    vs = wl.ValidatorSet(32, 6)
+    engine.set_validators(2, 77, vs.addr_array(), None)
+    dig = co.keccak256(b"group range")
+    its = np.concatenate([wl.make_item(wl.sign(vs.keys[i], dig), vs.addrs[i], 0, dig, g) for i, g in enumerate([0, 1, 2, 9, 0, 65535])])
+    groups = engine.groups(2, slot=2)
+    bitmap, results, _ = engine.verify_batch(its, b"", groups)
+    want = co.verify_batch(its, b"", tables=[vs.addr_array()], group_table=[0, 0], n_threads=2)
+    assert np.array_equal(bitmap, want) and int(bitmap[0]) == 0b010011
+    assert int(results[0]["n_valid"]) == 2 and int(results[1]["n_valid"]) == 1
+
+
+def test_two_span_payload_kind_matches_single_span(engine):
+    vs = wl.ValidatorSet(33, 5)
+    engine.set_validators(6, 5, vs.addr_array(), None)
+    rng = np.random.default_rng(9)
+    arena = bytearray()
+    single, double, want = [], [], []
+    for i, (n1, n2) in enumerate([(1, 1), (50, 200), (136, 136), (135, 1), (7, 909_000), (300, 0), (0, 300), (1095, 4096)]):
+        a, b = rng.integers(0, 256, n1, dtype=np.uint8).tobytes(), rng.integers(0, 256, n2, dtype=np.uint8).tobytes()
+        sig = wl.sign(vs.keys[i % 5], co.keccak256(a + b))
+        if i == 3:
+            sig = sig[:40] + bytes([sig[40] ^ 1]) + sig[41:]
+        off1 = len(arena); arena.extend(a)
+        off2 = len(arena); arena.extend(b)
+        offc = len(arena); arena.extend(a + b)
+        it = wl.make_item(sig, vs.addrs[i % 5], wl.KIND_PAYLOAD2, b"", 0, off1, n1)
+        it["digest"][0][:8] = np.frombuffer(off2.to_bytes(8, "little"), np.uint8)
+        it["digest"][0][8:12] = np.frombuffer(n2.to_bytes(4, "little"), np.uint8)
+        double.append(it)
+        single.append(wl.make_item(sig, vs.addrs[i % 5], wl.KIND_PAYLOAD, b"", 0, offc, n1 + n2))
+    oob = double[1].copy()
+    oob["digest"][0][:8] = np.frombuffer((len(arena) - 10).to_bytes(8, "little"), np.uint8)   # second span runs past the arena
+    its = np.concatenate(double + single + [oob])
+    bitmap, _, _ = engine.verify_batch(its, bytes(arena), engine.groups(1, slot=6))
+    bits = np.unpackbits(bitmap.view(np.uint8), bitorder="little")[: len(its)]
+    assert list(bits[:8]) == list(bits[8:16]) == [1, 1, 1, 0, 1, 1, 1, 1] and bits[16] == 0
+    assert np.array_equal(bitmap, co.verify_batch(its, bytes(arena), tables=[vs.addr_array()], group_table=[0], n_threads=2))
+
+
+def test_verify_batch_ex_returns_status_and_voted_sets_with_the_call(engine):
+    d = np.load(os.path.join(HERE, "golden", "config2.npz"))
+    items = np.ascontiguousarray(d["items"]).view(ib.ITEM_DTYPE).reshape(-1)
+    engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+    groups = engine.groups(len(d["groups"]))
+    stride = (len(d["addrs"]) + 31) // 32 + 3
+    bitmap, results, status, voted = engine.verify_batch_ex(items, d["arena"], groups, voted_stride_words=stride)
+    assert np.array_equal(bitmap, d["bitmap"]) and not status.any()
+    for g in range(len(groups)):
+        assert np.array_equal(voted[g, : stride - 3], engine.voted_bitmap(g, len(d["addrs"]))) and not voted[g, stride - 3:].any()
+        assert int(results[g]["n_distinct"]) == sum(bin(int(x)).count("1") for x in voted[g])
+
+
+def test_two_host_buffer_calls_run_concurrently_and_stay_bit_exact():
+    """The engine serialised every call behind one mutex in round 1.  Two lanes now: a bulk handler batch and small ingress
+    batches proceed side by side; every call still gets exactly its own verdicts."""
+    d = np.load(os.path.join(HERE, "golden", "config3.npz"))
+    items = np.ascontiguousarray(d["items"]).view(ib.ITEM_DTYPE).reshape(-1)
+    e = ib.Engine(device=0, max_items=1 << 17, max_payload_bytes=1 << 24, max_groups=8, max_table_slots=2, max_validators=16384)
+    try:
+        e.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+        groups = e.groups(len(d["groups"]))
+        big = np.tile(items, 5)                                   # 100k tuples: lane 0, ~3 ms on the device
+        gold = np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(items)]
+        errors, small_done = [], []
+
+        def bulk():
+            try:
+                for _ in range(4):
+                    bm, res, _ = e.verify_batch(big, d["arena"], groups)
+                    got = np.unpackbits(bm.view(np.uint8), bitorder="little")[: len(big)]
+                    assert np.array_equal(got, np.tile(gold, 5))
+            except Exception as ex:  # noqa: BLE001
+                errors.append(ex)
+
+        def small(k):
+            try:
+                for j in range(40):
+                    lo = (97 * (k * 40 + j)) % (len(items) - 64)
+                    sub = items[lo:lo + 1 + (j % 64)]
+                    bm, res, status, _ = e.verify_batch_ex(sub, d["arena"], groups)
+                    got = np.unpackbits(bm.view(np.uint8), bitorder="little")[: len(sub)]
+                    assert np.array_equal(got, gold[lo:lo + len(sub)])
+                    small_done.append(1)
+            except Exception as ex:  # noqa: BLE001
+                errors.append(ex)
+        ts = [threading.Thread(target=bulk)] + [threading.Thread(target=small, args=(k,)) for k in range(4)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errors, errors
+        assert len(small_done) == 160
+    finally:
+        e.close()
+
+
+def test_ingress_coalescer_64_threads_of_single_message_calls():
+    """Round-1 verdict, "missing" #1: a cache miss of IsValidValidator was a device call of ONE item.  64 threads x 1,000
+    single-message calls (the reference's gossip ingress, core/ibft.go:1101-1128) must take >= 20x fewer device calls than
+    calls, with every answer equal to the oracle's."""
+    n_threads, per = 64, 1000
+    total = n_threads * per
+    w = wl.build_round(41, 2000, 1_000_000, 0, with_prepare=True, with_commit_sender=True, with_seals=False)
+    distinct = w["wire"]                                           # 4,000 distinct signed messages, ~1 % adversarial
+    members = {bytes(a) for a in w["addrs"]}
+
+    def oracle_answer(wire):                                       # IsValidValidator restated with the oracle (core/backend.go:41-45)
+        m = ip.decode_ibft_message(wire)
+        if m.view is None or len(m.from_) != 20 or len(m.signature) != 65:
+            return 0
+        return int(co.ecrecover_address(co.keccak256(m.payload_no_sig()), m.signature) == m.from_ and m.from_ in members)
+    want = np.array([oracle_answer(x) for x in distinct], dtype=np.uint8)
+    assert 0 < int((want == 0).sum()) < 80
+    # the verdict cache answers repeats, so every message is asked exactly once per verifier: 16 verifiers x 4,000 messages
+    calls = flushes = asked = 0
+    lat_all = []
+    for rnd in range(total // len(distinct)):
+        params = host.EngineParams(0, 1 << 14, 1 << 22, 32, 8, 4096, 0)
+        c = host.HostContext("gpu", {}, b"", params)
+        assert c.set_validators(1_000_000, [bytes(a) for a in w["addrs"]], None) == 0
+        verdicts, lat, us = c.ingress_storm(distinct, n_threads)
+        assert np.array_equal(verdicts, want), "coalesced answers differ from the oracle"
+        calls += c.gpu_device_calls()
+        flushes += c.gpu_ingress_flushes()
+        asked += c.gpu_ingress_requests()
+        lat_all.append(lat)
+        c.close()
+    assert asked == total
+    assert flushes == calls and calls * 20 <= total, (calls, total)
+
+
+def test_proposal_hash_is_one_launch_and_matches_the_oracle(engine):
+    rng = np.random.default_rng(3)
+    props = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (0, 1, 135, 136, 137, 1024, 70_000)]
+    rounds = [0, 1, 2, 3, 2**40, 2**64 - 1, 7]
+    before = engine.launch_count()
+    got = engine.proposal_hash_batch(props, rounds)
+    assert engine.launch_count() - before == 1
+    assert got == [wl.proposal_hash(p, r) for p, r in zip(props, rounds)]
+    # through the reference-facing call: hashed once per (proposal, round), answered from the cache afterwards
+    params = host.EngineParams(0, 1 << 10, 1 << 20, 8, 4, 64, 0)
+    c = host.HostContext("gpu", {}, b"", params)
+    raw = props[5]
+    calls0 = c.gpu_device_calls()
+    assert c.is_valid_proposal_hash(raw, 3, wl.proposal_hash(raw, 3))
+    assert c.gpu_device_calls() - calls0 == 1
+    for _ in range(50):
+        assert c.is_valid_proposal_hash(raw, 3, wl.proposal_hash(raw, 3))
+        assert not c.is_valid_proposal_hash(raw, 3, wl.proposal_hash(raw, 4))
+    assert c.gpu_device_calls() - calls0 == 1
+    assert not c.is_valid_proposal_hash(raw, 4, wl.proposal_hash(raw, 3))
+    c.close()
+
+
+def test_third_party_recover_vectors_on_the_device(engine):
+    """tests/golden/third_party_recover.json (sources recorded in the file) through the CUDA recover path."""
+    vec = json.load(open(os.path.join(HERE, "golden", "third_party_recover.json")))
+    its, want = [], []
+    for v in vec["recover"]:
+        sig = bytes.fromhex(v["sig"])
+        dig = bytes.fromhex(v["digest"])
+        addr = bytes.fromhex(v["address"]) if v.get("address") else bytes(20)
+        its.append(wl.make_item(sig, addr, 0, dig, 0))
+        want.append(1 if v["valid"] else 0)
+    its = np.concatenate(its)
+    bitmap, _, recovered = engine.verify_batch(its, b"", None, want_results=False, want_recovered=True)
+    bits = np.unpackbits(bitmap.view(np.uint8), bitorder="little")[: len(its)]
+    assert list(bits) == want
+    for i, v in enumerate(vec["recover"]):
+        if v["valid"]:
+            assert bytes(recovered[i]) == bytes.fromhex(v["address"])

@@ -39,8 +39,7 @@ def test_derived_nonce_signatures_verify_on_gpu_and_oracle(engine):
     for s in seals:
         assert int.from_bytes(s[32:64], "big") <= ec.N // 2                       # low-s
     items = np.concatenate([wl.make_item(seals[i], vs.addrs[i], 2, ph, 0) for i in range(vs.n)])
-    g = np.zeros(1, dtype=ib.GROUP_DTYPE)
-    g["table_slot"] = 6
+    g = engine.groups(1, slot=6)
     bitmap, results, _ = engine.verify_batch(items, b"", g)
     assert sum(bin(int(w)).count("1") for w in bitmap) == vs.n and bool(results[0]["has_quorum"])
     for i in (0, 17, 299):

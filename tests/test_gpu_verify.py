@@ -20,10 +20,9 @@ def load_fixture(name):
     return d, items
 
 
-def groups_for(n_groups, slot=0):
-    g = np.zeros(n_groups, dtype=ib.GROUP_DTYPE)
-    g["table_slot"] = slot
-    return g
+def groups_for(eng, n_groups, slot=0):
+    """group descriptors for `slot`, carrying the height of the table resident there (ibft_group_desc.height)"""
+    return eng.groups(n_groups, slot)
 
 
 def expected_groups(items, bitmap, addrs, powers):
@@ -46,7 +45,7 @@ def test_fixture_bitmap_and_quorum_bit_exact(engine, name):
     d, items = load_fixture(name)
     engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
     ng = len(d["groups"])
-    bitmap, results, recovered = engine.verify_batch(items, d["arena"], groups_for(ng), want_recovered=True)
+    bitmap, results, recovered = engine.verify_batch(items, d["arena"], groups_for(engine, ng), want_recovered=True)
     assert np.array_equal(bitmap, d["bitmap"]), "verdict bitmap differs from the oracle's golden bitmap"
     # recompute the oracle live as well (guards against a stale fixture)
     gt = [0] * ng
@@ -86,7 +85,7 @@ def test_quorum_threshold_edge(engine):
     for take, want in ((k - 1, False), (k, True)):
         its = [wl.make_item(wl.sign(vs.keys[i], sd), vs.addrs[i], 2, ph, 0) for i in order[:take]]
         its += [its[0].copy(), its[0].copy()]  # duplicate sender: counted once (HasQuorum works on an address set)
-        bitmap, results, _ = engine.verify_batch(np.concatenate(its), b"", groups_for(1, slot=1))
+        bitmap, results, _ = engine.verify_batch(np.concatenate(its), b"", groups_for(engine, 1, slot=1))
         assert int(results[0]["n_valid"]) == take + 2 and int(results[0]["n_distinct"]) == take
         assert bool(results[0]["has_quorum"]) == want
         assert sum(int(results[0]["power"][j]) << (64 * j) for j in range(5)) == sum(vs.powers[i] for i in order[:take])
@@ -104,7 +103,7 @@ def test_huge_voting_powers(engine):
     sd = wl.seal_digest(ph)
     for subset in ([0, 1], [0, 2, 3], [0, 1, 2], [1, 2, 3]):
         its = np.concatenate([wl.make_item(wl.sign(vs.keys[i], sd), vs.addrs[i], 2, ph, 0) for i in subset])
-        _, results, _ = engine.verify_batch(its, b"", groups_for(1, slot=2))
+        _, results, _ = engine.verify_batch(its, b"", groups_for(engine, 1, slot=2))
         s = sum(powers[i] for i in subset)
         assert sum(int(results[0]["power"][j]) << (64 * j) for j in range(5)) == s
         assert bool(results[0]["has_quorum"]) == (s >= q)
@@ -122,7 +121,7 @@ def test_ragged_sizes(engine, n):
     d, items = load_fixture("config2.npz")
     engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
     sub = items[2000 - n // 2: 2000 - n // 2 + n].copy()  # straddles COMMIT sender sigs / seals
-    bitmap, _, _ = engine.verify_batch(sub, d["arena"], groups_for(len(d["groups"])))
+    bitmap, _, _ = engine.verify_batch(sub, d["arena"], groups_for(engine, len(d["groups"])))
     want = co.verify_batch(sub, d["arena"].tobytes(), tables=[d["addrs"]], group_table=[0] * len(d["groups"]), n_threads=4)
     assert np.array_equal(bitmap, want)
 
@@ -138,23 +137,23 @@ def test_malformed_items_are_false_never_crash(engine):
     bad_group = good.copy(); bad_group["group"] = 9
     short_sig = wl.make_item(b"\x01" * 64, vs.addrs[0], 0, dig, 0)     # len != 65 -> KIND_INVALID
     its = np.concatenate([good, bad_kind, invalid, oob, bad_group, short_sig, good])
-    bitmap, results, _ = engine.verify_batch(its, b"\x00" * 16, groups_for(1, slot=4))
+    bitmap, results, _ = engine.verify_batch(its, b"\x00" * 16, groups_for(engine, 1, slot=4))
     assert int(bitmap[0]) == 0b1000001
     assert int(results[0]["n_valid"]) == 2 and int(results[0]["n_distinct"]) == 1
     # a group that references an unset table slot is an error, not a verdict
     e2 = ib.Engine(device=0, max_items=64, max_payload_bytes=1024, max_groups=4, max_table_slots=4, max_validators=16)
     with pytest.raises(ib.EngineError) as ei:
-        e2.verify_batch(its, b"", groups_for(1, slot=3))
+        e2.verify_batch(its, b"", groups_for(e2, 1, slot=3))
     assert ei.value.code == 6
     e2.close()
     # no table: membership skipped, pure recover+compare
-    g = groups_for(1, slot=ib.NO_TABLE)
+    g = groups_for(engine, 1, slot=ib.NO_TABLE)
     outsider = wl.privkey(999, 0)
     it2 = wl.make_item(wl.sign(outsider, dig), wl.address_of(outsider), 0, dig, 0)
     bitmap, results, _ = engine.verify_batch(it2, b"", g)
     assert int(bitmap[0]) == 1 and int(results[0]["has_quorum"]) == 0
     # same item against a table it is not a member of
-    bitmap, _, _ = engine.verify_batch(it2, b"", groups_for(1, slot=4))
+    bitmap, _, _ = engine.verify_batch(it2, b"", groups_for(engine, 1, slot=4))
     assert int(bitmap[0]) == 0
 
 
@@ -174,7 +173,7 @@ def test_multiblock_payloads_and_keccak_batch(engine):
         its.append(wl.make_item(wl.sign(key, co.keccak256(payload)), vs.addrs[k % 3], 1, b"", 0, len(arena), sz))
         arena.extend(payload)
     its = np.concatenate(its)
-    bitmap, _, _ = engine.verify_batch(its, bytes(arena), groups_for(1, slot=5))
+    bitmap, _, _ = engine.verify_batch(its, bytes(arena), groups_for(engine, 1, slot=5))
     assert int(bitmap[0]) == (1 << len(sizes)) - 1
     assert engine.keccak256_batch(msgs) == [co.keccak256(m) for m in msgs]
     assert engine.keccak256_batch([]) == []
@@ -183,7 +182,7 @@ def test_multiblock_payloads_and_keccak_batch(engine):
 def test_async_submit_poll_wait(engine):
     d, items = load_fixture("config2.npz")
     engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
-    groups = groups_for(len(d["groups"]))
+    groups = groups_for(engine, len(d["groups"]))
     bitmap = np.zeros((len(items) + 31) // 32, np.uint32)
     results = np.zeros(len(groups), ib.RESULT_DTYPE)
     arena = np.ascontiguousarray(d["arena"])
@@ -204,7 +203,7 @@ def test_device_resident_and_sharded_path(engine):
     d, items = load_fixture("config2.npz")
     engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
     n = len(items)
-    groups = groups_for(len(d["groups"]))
+    groups = groups_for(engine, len(d["groups"]))
     engine.bind_groups(groups)
     t_items = torch.from_numpy(items.view(np.uint8).reshape(-1, 128).copy()).cuda()
     t_arena = torch.from_numpy(np.ascontiguousarray(d["arena"]).copy()).cuda()
@@ -240,7 +239,7 @@ def test_replicated_large_batch_properties(engine):
     reps = 3
     big = np.tile(items, reps)
     perm = np.random.default_rng(0).permutation(len(big))
-    groups = groups_for(len(d["groups"]))
+    groups = groups_for(engine, len(d["groups"]))
     bm, results, _ = engine.verify_batch(big[perm], d["arena"], groups)
     bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[: len(big)]
     want_bits = np.tile(np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(items)], reps)[perm]
@@ -258,7 +257,7 @@ def test_shard_local_quorum_mark_and_merge(engine):
     d, items = load_fixture("config3.npz")
     engine.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
     n = len(items)
-    groups = groups_for(len(d["groups"]))
+    groups = groups_for(engine, len(d["groups"]))
     engine.bind_groups(groups)
     t_items = torch.from_numpy(items.view(np.uint8).reshape(-1, 128).copy()).cuda()
     t_arena = torch.from_numpy(np.ascontiguousarray(d["arena"]).copy()).cuda()
@@ -339,7 +338,7 @@ def test_auto_path_selection_boundaries():
     try:
         sms = eng.device_info()["sm_count"]
         eng.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
-        groups = groups_for(len(d["groups"]))
+        groups = groups_for(eng, len(d["groups"]))
         gold = np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(items)]
         big = np.tile(items, 3)
         gold_big = np.tile(gold, 3)

@@ -32,8 +32,7 @@ def test_raw_frames_batch(engine):
             items.append(wire_item(kind, off, len(wire), 0 if kind == ib.KIND_WIRE else 1))
             want.append(wire_expectation(wire, kind, members))
     items = np.concatenate(items).view(ib.ITEM_DTYPE)
-    groups = np.zeros(2, dtype=ib.GROUP_DTYPE)
-    groups["table_slot"] = 7
+    groups = engine.groups(2, slot=7)
     bitmap, results, _ = engine.verify_batch(items, bytes(arena) or b"\x00", groups)
     status = engine.last_item_status(len(items))
     bits = np.unpackbits(bitmap.view(np.uint8), bitorder="little")[: len(items)]

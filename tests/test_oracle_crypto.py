@@ -104,3 +104,41 @@ def test_recover_infinity_and_zero_digest():
     assert ec.ecrecover_address(dig, sig) is None
     assert co.ecrecover_address(dig, sig) is None
     assert co.ecrecover_address(bytes(32), sig) == ec.ecrecover_address(bytes(32), sig) is not None
+
+
+def test_third_party_recover_and_sign_vectors():
+    """tests/golden/third_party_recover.json: go-ethereum's testmsg/testsig/testpubkey, the EIP-155 worked example and the
+    published RFC 6979 secp256k1 known answers (sources in the file) against BOTH oracles, with OpenSSL as the independent
+    implementation of the verify equation; constructed edge classes must be rejected (or, for the high-s twin, accepted)."""
+    import hashlib
+    import json
+    import os
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import ec as cec
+    from cryptography.hazmat.primitives.asymmetric import utils
+    doc = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "third_party_recover.json")))
+    assert len(doc["recover"]) >= 20
+    for v in doc["recover"]:
+        dig, sig = bytes.fromhex(v["digest"]), bytes.fromhex(v["sig"])
+        for rec in (co.ecrecover_address, ec.ecrecover_address):
+            got = rec(dig, sig)
+            assert (got is not None and got.hex() == v["address"]) == v["valid"], v["name"]
+    # the published pubkey of go-ethereum's vector, and OpenSSL's verdict on it
+    g = doc["recover"][0]
+    pub = co.ecrecover_pubkey(bytes.fromhex(g["digest"]), bytes.fromhex(g["sig"]))
+    assert ("04" + pub.hex()) in g["note"]
+    key = cec.EllipticCurvePublicNumbers(int.from_bytes(pub[:32], "big"), int.from_bytes(pub[32:], "big"), cec.SECP256K1()).public_key()
+    sig = bytes.fromhex(g["sig"])
+    key.verify(utils.encode_dss_signature(int.from_bytes(sig[:32], "big"), int.from_bytes(sig[32:64], "big")), bytes.fromhex(g["digest"]),
+               cec.ECDSA(utils.Prehashed(hashes.SHA256())))
+    # RFC 6979: nonce, r, s bit for bit from both signers; OpenSSL verifies and (deterministic signing) reproduces r
+    for s in doc["sign_rfc6979"]:
+        d = int(s["privkey"], 16)
+        z = hashlib.sha256(s["message"].encode()).digest()
+        assert z.hex() == s["digest"]
+        k = ec.rfc6979_k(d, z)
+        assert "%064x" % k == s["k"]
+        for sg in (co.sign_with_k(d, z, k, True), ec.sign(d, z, low_s=True)):
+            assert (sg[:32].hex(), sg[32:64].hex(), sg[64]) == (s["r"], s["s"], s["v"])
+        priv = cec.derive_private_key(d, cec.SECP256K1())
+        priv.public_key().verify(utils.encode_dss_signature(int(s["r"], 16), int(s["s"], 16)), z, cec.ECDSA(utils.Prehashed(hashes.SHA256())))

@@ -20,7 +20,7 @@ gold = np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(base)]
 gold = np.tile(gold, (nmax + len(base) - 1) // len(base))[:nmax]
 eng = ib.Engine(device=0, max_items=max(nmax, 1024), max_payload_bytes=1 << 22, max_groups=8, max_table_slots=2, max_validators=16384)
 eng.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
-eng.bind_groups(np.zeros(len(d["groups"]), dtype=ib.GROUP_DTYPE))
+eng.bind_groups(eng.groups(len(d["groups"])))
 t_items = torch.from_numpy(items.view(np.uint8).reshape(-1, 128)).cuda()
 t_arena = torch.from_numpy(np.ascontiguousarray(d["arena"])).cuda()
 st = torch.cuda.Stream()

@@ -18,7 +18,7 @@ items = np.ascontiguousarray(np.tile(base, (n + len(base) - 1) // len(base))[:n]
 KEY_CACHE = os.environ.get("KEY_CACHE") == "1"  # verify against learned validator keys instead of recovering
 eng = ib.Engine(device=0, max_items=n, max_payload_bytes=1 << 22, max_groups=8, max_table_slots=2, max_validators=16384, key_cache=KEY_CACHE)
 eng.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
-groups = np.zeros(len(d["groups"]), dtype=ib.GROUP_DTYPE)
+groups = eng.groups(len(d["groups"]))
 eng.bind_groups(groups)
 t_items = torch.from_numpy(items.view(np.uint8).reshape(-1, 128)).cuda()
 t_arena = torch.from_numpy(np.ascontiguousarray(d["arena"])).cuda()
