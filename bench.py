@@ -13,6 +13,9 @@ pass/fail bitmap words) -> K3 quorum kernels over the complete bitmap.
   roofline  integer-issue roofline: verifies/s x 5.0e5 IMAD-class instructions / measured IMAD peak
   cpu_baseline / --impl reference   the C oracle (a port; the Go reference has no crypto and no toolchain here) on the
           box's host cores, on a bounded sample of the same workload.
+  strong_scaling  ONE 10,000-seal round and ONE config-5 backlog (100k messages, 16 heights x 10k validators) split over the N
+          ranks, every rank holding only its shard: host-to-host latency p50/p95 per N (go-ibft_b200/sharding.py ShardedVerifier)
+  ingress   64 threads of single-message IsValidValidator calls through the reference-facing verifier (the coalescer)
 """
 from __future__ import annotations
 
@@ -176,9 +179,275 @@ def workload_config(n_gpus):
             "l2": "inputs (128 MiB of tuples per GPU) exceed the 126 MB L2; no flush needed"}
 
 
-# rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on the GPU boxes) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+def _pct(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(len(xs) * q))] if xs else None
+
+
+def load_full_cache(name):
+    """The full-size BASELINE configs 4 / 5 (tests/workloads.py config4_n10k / config5_full) as regenerated and cached by
+    __graft_entry__.build() / the test suite under tests/golden/_cache/ (bench.py itself never runs the generator: it lives with
+    the oracle).  Returns (workload, pin) or (None, reason)."""
+    import hashlib
+    import pickle
+    cache = os.path.join(ROOT, "tests", "golden", "_cache", name + ".pkl")
+    pin_path = os.path.join(ROOT, "tests", "golden", name + "_pin.npz")
+    if not os.path.exists(cache) or not os.path.exists(pin_path):
+        return None, f"{cache} absent (python -c 'import __graft_entry__ as g; g.build()' regenerates it)"
+    pin = np.load(pin_path)
+    with open(cache, "rb") as f:
+        w = pickle.load(f)
+    sha = lambda a: hashlib.sha256(a if isinstance(a, (bytes, bytearray)) else np.ascontiguousarray(a).tobytes()).digest()  # noqa: E731
+    if sha(w["items"]) != bytes(pin["sha_items"]) or sha(w["arena"]) != bytes(pin["sha_arena"]):
+        return None, "cached workload does not match the committed fingerprint"
+    return w, pin
+
+
+def strong_scaling_legs(args, ib, eng_weak, d, base_items, groups3, world, rank, local_rank, stream):
+    """ONE 10,000-seal COMMIT round and ONE config-5 backlog split over the `world` ranks: each rank holds only its shard (tuples
+    and payload bytes), verifies it, marks its votes, and ONE all-gather of (bitmap words | partial voted sets | counts) gives
+    every rank the complete bitmap and the quorum results.  Timed host-to-host per repetition: barrier, then pinned host shard ->
+    H2D -> kernels -> collective -> merge -> D2H of results + bitmap on every rank; the per-repetition time is the MAX over ranks.
+    The bitmap of every repetition's configuration is checked against the golden fixture / the committed pin."""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    sharding = importlib.import_module("go-ibft_b200.sharding")
+    out = {"n_gpus": world, "timing": "wall clock around barrier .. results+bitmap on the host, max over ranks per repetition",
+           "collective": "one all_gather_into_tensor of (bitmap words | partial voted sets | valid counts) per round"}
+
+    def timed(sv, reps):
+        ts = []
+        for i in range(reps + 5):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res, bm = sv.run()
+            ts.append((time.perf_counter() - t0) * 1e6)
+        t = torch.tensor(ts[5:], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()], res, bm
+
+    # ---- (a) one 10,000-seal round (config 3's committed seals)
+    seal_group = list(d["groups"]).index("COMMIT_SEAL")
+    sel = base_items["group"] == seal_group
+    seals = np.ascontiguousarray(base_items[sel])
+    gold = np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(base_items)][sel]
+    n = len(seals)
+    lo, hi = sharding.shard_bounds(n, world, rank)
+    li, la = sharding.rebase_shard(seals, np.zeros(0, np.uint8), lo, hi)
+    sv = sharding.ShardedVerifier(eng_weak, n, groups3, world, rank, li, la, stream)
+    ts, res, bm = timed(sv, args.latency_reps)
+    bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[:n]
+    if not np.array_equal(bits, gold):
+        raise SystemExit("bench: sharded 10k round: bitmap differs from the golden fixture")
+    out["round10k"] = {"workload": "ONE 10k-validator COMMIT round: 10,000 committed seals, weighted quorum", "items": n,
+                       "items_per_gpu": int(hi - lo), "p50_us": _pct(ts, 0.5), "p95_us": _pct(ts, 0.95), "reps": len(ts),
+                       "has_quorum": bool(res[seal_group]["has_quorum"]), "bitmap_matches_golden": True}
+    # ---- (b) config 5 at its stated size
+    w, pin = load_full_cache("config5")
+    if w is None:
+        out["config5"] = {"skipped": pin}
+    else:
+        items, arena = w["items"], np.frombuffer(w["arena"], np.uint8)
+        n = len(items)
+        lo, hi = sharding.shard_bounds(n, world, rank)
+        eng5 = ib.Engine(device=local_rank, max_items=max(32, hi - lo), max_payload_bytes=1 << 24, max_groups=w["n_groups"], max_table_slots=16,
+                         max_validators=10_000)
+        for k in range(16):
+            eng5.set_validators(k, w["heights"][k], w["tables"][k], w["powers"])
+        groups5 = eng5.groups(w["n_groups"], slot=w["group_table"])
+        li, la = sharding.rebase_shard(items, arena, lo, hi)
+        sv5 = sharding.ShardedVerifier(eng5, n, groups5, world, rank, li, la, stream)
+        ts, res, bm = timed(sv5, max(20, args.latency_reps // 4))
+        if not np.array_equal(bm, pin["bitmap"]):
+            raise SystemExit("bench: sharded config 5: bitmap differs from the committed oracle pin")
+        want = pin["results"]
+        for g in range(w["n_groups"]):
+            if (int(res[g]["n_valid"]), int(res[g]["n_distinct"]), int(res[g]["has_quorum"])) != tuple(int(x) for x in want[g, :3]):
+                raise SystemExit("bench: sharded config 5: quorum results differ from the committed oracle pin")
+        p50 = _pct(ts, 0.5)
+        out["config5"] = {"workload": "100,000 pending messages (144,953 signature tuples), 16 concurrent heights x 10,000-validator tables, "
+                                      "45/45/9/1 PREPARE/COMMIT/ROUND_CHANGE/PREPREPARE, 1% adversarial; sharded by contiguous index range",
+                          "items": n, "items_per_gpu": int(hi - lo), "payload_bytes_per_gpu": int(la.size), "groups": int(w["n_groups"]),
+                          "p50_us": p50, "p95_us": _pct(ts, 0.95), "reps": len(ts), "verifies_per_s_at_p50": n / (p50 * 1e-6),
+                          "bitmap_and_quorum_match_pin": True}
+        eng5.close()
+    return out
+
+
+def wire_frames_from_payload_items(items, arena):
+    """Gossip frames for the KIND_PAYLOAD tuples of a fixture: PayloadNoSig with the signature field (3) put back right after
+    From (field 2) -- the canonical encoding of the signed message (messages/proto/messages.proto:24-44)."""
+    frames = []
+    a = np.ascontiguousarray(arena).tobytes()
+    for it in items:
+        p = a[int(it["payload_off"]): int(it["payload_off"]) + int(it["payload_len"])]
+        assert p[0] == 0x0A and p[1] < 0x80 and p[2 + p[1]] == 0x12 and p[3 + p[1]] == 20
+        cut = 2 + p[1] + 22
+        sig = bytes(it["r"]) + bytes(it["s"]) + bytes([int(it["v"])])
+        frames.append(p[:cut] + b"\x1a\x41" + sig + p[cut:])
+    return frames
+
+
+def ingress_leg(local_rank):
+    """64 threads of SINGLE-message IsValidValidator calls through the reference-facing verifier (the call pattern of
+    core/ibft.go:1101-1128): the coalescer turns them into a few device batches.  Config 2's 2,000 PREPARE + COMMIT sender messages,
+    each asked once per verifier, 8 verifiers (the verdict cache would answer repeats)."""
+    import importlib
+    host = importlib.import_module("go-ibft_b200.host")
+    d2 = np.load(os.path.join(ROOT, "tests", "golden", "config2.npz"))
+    import ibft_b200 as ib
+    items = np.ascontiguousarray(d2["items"]).view(ib.ITEM_DTYPE).reshape(-1)
+    sel = items["kind"] == ib.KIND_PAYLOAD
+    frames = wire_frames_from_payload_items(items[sel], d2["arena"])
+    # what every frame's answer must be: the BULK path's verdict for the same message (tuple with signer = the frame's From)
+    tuples = items[sel].copy()
+    a = np.ascontiguousarray(d2["arena"]).tobytes()
+    for k, it in enumerate(tuples):
+        off = int(it["payload_off"])
+        vlen = a[off + 1]
+        tuples["signer"][k] = np.frombuffer(a[off + 4 + vlen: off + 24 + vlen], np.uint8)
+    e0 = ib.Engine(device=local_rank, max_items=1 << 12, max_payload_bytes=1 << 22, max_groups=8, max_table_slots=2, max_validators=4096)
+    e0.set_validators(0, int(d2["meta"][2]), d2["addrs"], d2["powers"])
+    bulk, _, _ = e0.verify_batch(tuples, d2["arena"], e0.groups(len(d2["groups"])))
+    e0.close()
+    gold = np.unpackbits(bulk.view(np.uint8), bitorder="little")[: len(tuples)]
+    addrs = [bytes(x) for x in d2["addrs"]]
+    lat, elapsed, calls, asked, mismatches = [], 0.0, 0, 0, 0
+    for _ in range(8):
+        c = host.HostContext("gpu", {}, b"", host.EngineParams(local_rank, 1 << 14, 1 << 22, 32, 8, 4096, 0))
+        c.set_validators(int(d2["meta"][2]), addrs, None)
+        v, l, us = c.ingress_storm(frames, 64)
+        mismatches += int((v != gold).sum())
+        lat.extend(float(x) for x in l)
+        elapsed += us
+        calls += c.gpu_device_calls()
+        asked += c.gpu_ingress_requests()
+        c.close()
+    if mismatches:
+        raise SystemExit("bench: ingress leg: coalesced single-message answers differ from the bulk path's verdicts")
+    return {"threads": 64, "single_message_calls": asked, "device_calls": calls, "calls_per_device_call": asked / max(1, calls),
+            "msgs_per_s": asked / (elapsed * 1e-6), "p50_us": _pct(lat, 0.5), "p95_us": _pct(lat, 0.95),
+            "answers_equal_bulk_path": True,
+            "note": "IsValidValidator per inbound gossip message from 64 threads (core/ibft.go:1101-1128); a cache miss joins the "
+                    "ingress queue, one leader flushes the queue in ONE device call (group commit, no timer)"}
+
+
+def cpu_latency_legs(d, base_items, cores):
+    """Metric 2's CPU side: the same 10,000 committed seals on the host cores -- all threads, and ONE thread in
+    store order (the reference verifies one message at a time under its per-type mutex, messages/messages.go:174-176)."""
+    from oracle import coracle as co
+    seal_group = list(d["groups"]).index("COMMIT_SEAL")
+    seals = np.ascontiguousarray(base_items[base_items["group"] == seal_group])
+    gt = [0] * len(d["groups"])
+    allc, serial = [], []
+    for _ in range(7):
+        t0 = time.perf_counter()
+        co.verify_batch(seals, b"", tables=[d["addrs"]], group_table=gt, n_threads=cores)
+        allc.append((time.perf_counter() - t0) * 1e6)
+    for _ in range(3):
+        t0 = time.perf_counter()
+        co.verify_batch(seals, b"", tables=[d["addrs"]], group_table=gt, n_threads=1)
+        serial.append((time.perf_counter() - t0) * 1e6)
+    out = {"all_cores_p50": _pct(allc, 0.5), "all_cores_p95": _pct(allc, 0.95), "all_cores_threads": cores, "all_cores_reps": len(allc),
+           "serial_reference_semantics_p50": _pct(serial, 0.5), "serial_reps": len(serial),
+           "impl": "C oracle port (oracle/c/ibft_oracle.c)"}
+    if co.ossl_lib() is not None:
+        t0 = time.perf_counter()
+        bm = co.ossl_verify_batch(seals, b"", d["addrs"], cores)
+        out["openssl_all_cores_us"] = (time.perf_counter() - t0) * 1e6
+    return out
+
+
+def hash_crossover_leg(eng):
+    """IsValidProposalHash for ONE proposal (both sponges in one launch, host buffers in / 32 bytes out) against one CPU core, by
+    proposal size; and the batch size from which the device wins at 1 KiB."""
+    from oracle import coracle as co
+    rng = np.random.default_rng(7)
+    rows = []
+    for size in (1 << 10, 1 << 16, 1 << 20):
+        raw = rng.integers(0, 256, size, dtype=np.uint8).tobytes()
+        g, c = [], []
+        want = co.keccak256(co.keccak256(raw) + (3).to_bytes(8, "big"))
+        for i in range(12):
+            t0 = time.perf_counter()
+            got = eng.proposal_hash_batch([raw], [3])[0]
+            g.append((time.perf_counter() - t0) * 1e6)
+            t0 = time.perf_counter()
+            co.keccak256(co.keccak256(raw) + (3).to_bytes(8, "big"))
+            c.append((time.perf_counter() - t0) * 1e6)
+        rows.append({"proposal_bytes": size, "gpu_us_p50": _pct(g[2:], 0.5), "cpu_1core_us_p50": _pct(c[2:], 0.5), "match": got == want})
+    batch = []
+    raw1k = [rng.integers(0, 256, 1 << 10, dtype=np.uint8).tobytes() for _ in range(4096)]
+    for nb in (1, 16, 256, 4096):
+        t0 = time.perf_counter()
+        eng.proposal_hash_batch(raw1k[:nb], [0] * nb)
+        tg = (time.perf_counter() - t0) * 1e6
+        t0 = time.perf_counter()
+        for r in raw1k[:nb]:
+            co.keccak256(co.keccak256(r) + bytes(8))
+        batch.append({"proposals": nb, "gpu_us": tg, "cpu_1core_us": (time.perf_counter() - t0) * 1e6})
+    return {"single_proposal": rows, "batch_of_1KiB_proposals": batch,
+            "note": "a sponge is serial: for ONE proposal the device pays launch + copies and then runs one slow thread, so one CPU core "
+                    "wins at every size; the device wins for batches.  The reference asks once per PREPARE and COMMIT (core/ibft.go:858, "
+                    ":938); GpuVerifier hashes once per (proposal, round) and answers the other 19,999 calls from its cache."}
+
+
+def config4_legs(ib, local_rank, stream):
+    """BASELINE config 4 at 10k validators.  dedup mode: the 20,003 unique tuples of 10,000 ROUND_CHANGE messages with nested
+    prepared certificates (10,000 of them IBFT_KIND_PAYLOAD2: a 1.1 KB head + a shared 909 KB certificate -- 9 GB of sponge input),
+    host buffers in, bitmap + decision out.  raw mode: the nested PREPARE checks WITHOUT dedup, a 2^24-tuple slice, device resident."""
+    import torch
+    w, pin = load_full_cache("config4_n10k")
+    if w is None:
+        return {"skipped": pin}
+    eng = ib.Engine(device=local_rank, max_items=1 << 15, max_payload_bytes=1 << 25, max_groups=4, max_table_slots=2, max_validators=10_000)
+    eng.set_validators(0, w["height"], w["addrs"], None)
+    g = eng.groups(1)
+    ts = []
+    for i in range(6):
+        t0 = time.perf_counter()
+        bm, res, _ = eng.verify_batch(w["items"], w["arena"], g)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    if not np.array_equal(bm, pin["bitmap"]):
+        raise SystemExit("bench: config 4 dedup mode: bitmap differs from the committed oracle pin")
+    out = {"dedup_mode": {"tuples": int(len(w["items"])), "round_change_messages": int(w["n"]), "signed_bytes_hashed": int(sum(
+        int(it["payload_len"]) + (int.from_bytes(bytes(it["digest"][8:12]), "little") if it["kind"] == 5 else 0) for it in w["items"])),
+        "arena_bytes_uploaded": len(w["arena"]), "ms_p50": _pct(ts[1:], 0.5), "bitmap_matches_pin": True,
+        "note": "host tuples -> bitmap + quorum on the host; dominated by the 10,000 sender digests (6,700 Keccak permutations each)"}}
+    eng.close()
+    # raw mode: 2^24 nested PREPARE checks (the 9,999 distinct PREPARE tuples tiled), one device-resident launch
+    n_raw = 1 << 24
+    prep = w["items"][w["n"] + 1: w["n"] + 1 + (w["n"] - 1)]
+    free, _ = torch.cuda.mem_get_info()
+    if free < 3 * n_raw * 128:
+        out["raw_mode"] = {"skipped": "not enough free device memory for 2^24 tuples"}
+        return out
+    local, larena = __import__("importlib").import_module("go-ibft_b200.sharding").rebase_shard(prep, np.frombuffer(w["arena"], np.uint8), 0, len(prep))
+    big = tile_items(local, n_raw)
+    eng = ib.Engine(device=local_rank, max_items=1 << 12, max_payload_bytes=1 << 22, max_groups=4, max_table_slots=2, max_validators=10_000)
+    eng.set_validators(0, w["height"], w["addrs"], None)
+    eng.bind_groups(eng.groups(1))
+    t_items = torch.from_numpy(big.view(np.uint8).reshape(-1, 128)).cuda()
+    t_arena = torch.from_numpy(larena.copy()).cuda()
+    t_bm = torch.zeros(n_raw // 32, dtype=torch.int32, device="cuda")
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.verify_device(t_items.data_ptr(), n_raw, t_arena.data_ptr(), t_arena.numel(), 0, n_raw, t_bm.data_ptr(), 0, stream.cuda_stream)
+    a.record(stream)
+    for _ in range(2):
+        eng.verify_device(t_items.data_ptr(), n_raw, t_arena.data_ptr(), t_arena.numel(), 0, n_raw, t_bm.data_ptr(), 0, stream.cuda_stream)
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 2
+    ok = bool((t_bm == -1).all().item())
+    out["raw_mode"] = {"tuples": n_raw, "ms_per_launch": ms, "verifies_per_s": n_raw / (ms * 1e-3), "all_valid": ok,
+                       "note": "nested PREPARE checks of the certificates without dedup (~10k x 6,667 = 6.7e7 per round): 2^24-tuple slice, tuples resident"}
+    del t_items, t_bm
+    eng.close()
+    return out
 
 
 def main():
@@ -221,12 +490,19 @@ def main():
     groups = eng.groups(len(d["groups"]))
     eng.bind_groups(groups)
 
-    # ---- device-resident inputs (every rank holds the global tuple array: the quorum kernels read every signer)
-    host_global = tile_items(base_items, n_global)
-    t_items = torch.from_numpy(host_global.view(np.uint8).reshape(-1, 128)).cuda()
+    # ---- device-resident inputs: every rank holds ONLY ITS SHARD of the tuples (after the shard-local quorum change nothing reads
+    # outside [lo, hi)); the kernels index tuples and bitmap words by GLOBAL item number, so they get rebased pointers
+    reps_needed = (n_global + len(base_items) - 1) // len(base_items)
+    host_local_np = np.ascontiguousarray(np.tile(base_items, reps_needed)[lo:hi]) if n_gpus > 1 else tile_items(base_items, n_global)
+    t_items_local = torch.from_numpy(host_local_np.view(np.uint8).reshape(-1, 128)).cuda()
+
+    class _ItemsView:                      # what the old code called t_items: a base pointer valid for indices [lo, hi)
+        def data_ptr(self_inner):
+            return t_items_local.data_ptr() - lo * 128
+    t_items = _ItemsView()
     t_arena = torch.from_numpy(np.ascontiguousarray(d["arena"])).cuda()
     words_local = n_local // 32
-    t_bitmap = torch.zeros(n_global // 32, dtype=torch.int32, device="cuda")
+    t_bitmap = torch.zeros(n_global // 32 if world == 1 else 1, dtype=torch.int32, device="cuda")
     t_results = torch.zeros(len(groups) * ib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.Stream()  # a real (non-default) stream: the C ABI launches on exactly this one
     torch.cuda.set_stream(stream)
@@ -308,7 +584,7 @@ def main():
 
     # ---- e2e: host buffers through ibft_verify_batch (H2D + kernels + D2H inside the timed region)
     # the step's inputs live in PINNED host memory (torch pin_memory); the C ABI detects that and DMA-copies straight from it
-    host_local = torch.from_numpy(np.ascontiguousarray(host_global[lo:hi]).view(np.uint8)).pin_memory().numpy().view(ib.ITEM_DTYPE).reshape(-1)
+    host_local = torch.from_numpy(host_local_np.view(np.uint8)).pin_memory().numpy().view(ib.ITEM_DTYPE).reshape(-1)
     arena_host = np.ascontiguousarray(d["arena"])
     e2e_steps = max(3, min(args.steps, 5))
     eng.verify_batch(host_local, arena_host, groups)
@@ -331,6 +607,20 @@ def main():
         raise SystemExit("bench: e2e leg: verdict bitmap differs from the golden bitmap -- refusing to report a number")
     h2d = host_local.nbytes + arena_host.nbytes + groups.nbytes
     d2h = (n_local // 8) + n_local + len(groups) * ib.RESULT_DTYPE.itemsize  # bitmap + per-item status bytes + quorum results
+    # the same call from PAGEABLE memory (what a cgo caller hands over: Go heap): the engine stages every chunk into its pinned
+    # buffer on the calling thread before the DMA
+    e2e_pageable = None
+    if world == 1:
+        eng.verify_batch(host_local_np, arena_host, groups)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            bm_pg, _, _ = eng.verify_batch(host_local_np, arena_host, groups)
+        e2e_pageable = n_global * e2e_steps / (time.perf_counter() - t0)
+        if not np.array_equal(bm_pg, bm_local):
+            raise SystemExit("bench: pageable e2e leg: bitmap differs")
+
+    # ---- strong scaling: ONE round / ONE backlog split over the N ranks (all ranks take part)
+    strong = strong_scaling_legs(args, ib, eng, d, base_items, groups, world, rank, local_rank, stream)
 
     if rank != 0:
         if world > 1:
@@ -469,7 +759,10 @@ def main():
         "dtype": "u32 (256-bit modular integer)", "data": "synthetic", "config": workload_config(n_gpus),
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "api": "ibft_verify_batch (host buffers -> pinned staging -> H2D -> kernels -> D2H bitmap + quorum)"},
+                "steps": e2e_steps, "api": "ibft_verify_batch (host buffers -> pinned staging -> H2D -> kernels -> D2H bitmap + quorum)",
+                "input_memory": "caller-pinned (DMA straight from the caller's buffer)", "pageable_input_value": e2e_pageable,
+                "pageable_note": "same call from pageable memory (a cgo caller's Go heap): + one host memcpy of every chunk into the engine's pinned staging"},
+        "strong_scaling": strong,
         "gpu_launches": int(launches),
         "roofline": {"bound": "int32-imad-issue", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-class instr/s",
                      "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per k_recover launch (ncu)",
@@ -503,7 +796,24 @@ def main():
         ok = np.array_equal(np.unpackbits(bm.view(np.uint8), bitorder="little")[:n_s], np.tile(gold_bits, n_s // len(base_items) + 1)[:n_s])
         line["cpu_baseline"] = {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_s} items (the config-3 batch repeated), C oracle (oracle/c/ibft_oracle.c), {cores} threads, ~12 s",
-                                "single_thread": v1, "matches_golden": bool(ok), "logical_cpus_visible": os.cpu_count()}
+                                "single_thread": v1, "matches_golden": bool(ok), "logical_cpus_visible": os.cpu_count(),
+                                "threads_rule": "threads = the container's cgroup CPU quota (cpu.max), capped by affinity -- the same rule in BENCH and SCALE runs"}
+        # a second arm with a LIBRARY's point arithmetic (BASELINE.md §3 planned OpenSSL): OpenSSL 3's generic-curve code is slower
+        # than the port on secp256k1; a libsecp256k1-class library (~4x the port per core) is not available offline
+        from oracle import coracle as co
+        if co.ossl_lib() is not None:
+            sub = tile_items(base_items, 4096 * max(1, cores // 4))
+            t0 = time.perf_counter()
+            bm_o = co.ossl_verify_batch(sub, d["arena"].tobytes(), d["addrs"], cores)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"]["openssl_arm"] = {"value": len(sub) / dt, "unit": "verifies/s", "cores": cores, "kind": "openssl-3 EC_POINT_mul",
+                                                   "matches_golden": bool(np.array_equal(np.unpackbits(bm_o.view(np.uint8), bitorder="little")[: len(sub)],
+                                                                                         np.tile(gold_bits, len(sub) // len(base_items) + 1)[: len(sub)]))}
+        line["quorum_latency_us"]["cpu"] = cpu_latency_legs(d, base_items, cores)
+        line["proposal_hash"] = hash_crossover_leg(eng)
+    if n_gpus == 1:
+        line["ingress"] = ingress_leg(local_rank)
+        line["config4"] = config4_legs(ib, local_rank, stream)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -32,3 +32,110 @@ def all_gather_bitmap(local_words: torch.Tensor, n: int, world: int) -> torch.Te
     full = torch.empty(per * world, dtype=local_words.dtype, device=local_words.device)
     dist.all_gather_into_tensor(full, local_words.contiguous())
     return full[: (n + 31) // 32]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# One round / one backlog split over N ranks (strong scaling): every rank HOLDS ONLY ITS SHARD of the tuples and of the
+# payload bytes; per call: H2D of the shard -> recover kernel over the shard -> shard-local quorum marks -> ONE all-gather of
+# (bitmap words | partial voted sets | valid counts) -> merge + weighted reduce on every rank.  No signature is looked at twice.
+# ---------------------------------------------------------------------------------------------------------------------
+import numpy as np  # noqa: E402
+
+_KINDS_WITH_PAYLOAD = (1, 3, 4, 5)  # IBFT_KIND_PAYLOAD, _WIRE, _WIRE_SEAL, _PAYLOAD2 (include/ibft_verify.h)
+
+
+def rebase_shard(items: np.ndarray, arena: np.ndarray, lo: int, hi: int):
+    """items[lo:hi] as a rank-local batch: a copy of the tuples whose payload offsets point into a PRIVATE arena that holds only
+    the bytes this shard references (second spans of IBFT_KIND_PAYLOAD2 tuples -- shared certificates -- once each)."""
+    local = items[lo:hi].copy()
+    arena = np.ascontiguousarray(arena, dtype=np.uint8).reshape(-1)
+    parts, pos, seen2 = [], 0, {}
+    kinds = local["kind"]
+    for i in np.nonzero(np.isin(kinds, _KINDS_WITH_PAYLOAD))[0]:
+        off, ln = int(local["payload_off"][i]), int(local["payload_len"][i])
+        if off + ln > arena.size:
+            continue  # out-of-range payloads stay out of range (verdict 0 either way)
+        parts.append(arena[off:off + ln])
+        local["payload_off"][i] = pos
+        pos += ln
+        if kinds[i] == 5:
+            off2 = int.from_bytes(bytes(local["digest"][i][:8]), "little")
+            len2 = int.from_bytes(bytes(local["digest"][i][8:12]), "little")
+            if (off2, len2) not in seen2 and off2 + len2 <= arena.size:
+                seen2[(off2, len2)] = pos
+                parts.append(arena[off2:off2 + len2])
+                pos += len2
+            if (off2, len2) in seen2:
+                local["digest"][i][:8] = np.frombuffer(int(seen2[(off2, len2)]).to_bytes(8, "little"), np.uint8)
+    local_arena = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+    return local, local_arena
+
+
+class ShardedVerifier:
+    """Device-side pipeline of one rank.  `engine` must hold the validator tables and have `groups` bound by this object.
+
+        sv = ShardedVerifier(engine, n_global, groups, world, rank, local_items, local_arena)
+        results, bitmap = sv.run()        # host arrays, identical on every rank
+    """
+
+    def __init__(self, engine, n_global: int, groups: np.ndarray, world: int, rank: int, local_items: np.ndarray,
+                 local_arena: np.ndarray, stream=None):
+        from . import engine as _e
+        self.e, self.n, self.world, self.rank = engine, n_global, world, rank
+        self.lo, self.hi = shard_bounds(n_global, world, rank)
+        assert len(local_items) == self.hi - self.lo
+        self.groups = groups
+        engine.bind_groups(groups)
+        self.W = engine.quorum_partial_words()
+        self.per = shard_words(n_global, world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.stream = stream or torch.cuda.current_stream()
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()  # noqa: E731
+        self.h_items = pin(local_items) if len(local_items) else torch.zeros(0, dtype=torch.uint8).pin_memory()
+        self.h_arena = pin(local_arena) if len(local_arena) else torch.zeros(0, dtype=torch.uint8).pin_memory()
+        self.d_items = torch.zeros(max(1, self.h_items.numel()), dtype=torch.uint8, device=dev)
+        self.d_arena = torch.zeros(max(16, self.h_arena.numel()), dtype=torch.uint8, device=dev)
+        self.d_local = torch.zeros(self.per + self.W, dtype=torch.int32, device=dev)
+        self.d_gather = torch.zeros(world * (self.per + self.W), dtype=torch.int32, device=dev)
+        self.d_results = torch.zeros(len(groups) * _e.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        self.h_out = torch.zeros(self.d_results.numel() + 4 * world * self.per, dtype=torch.uint8).pin_memory()
+        self.result_dtype = _e.RESULT_DTYPE
+        # the kernels index tuples and bitmap words by GLOBAL item number: hand them rebased pointers
+        self.items_base = self.d_items.data_ptr() - self.lo * 128
+        self.bitmap_base = self.d_local.data_ptr() - (self.lo // 32) * 4
+
+    def enqueue(self):
+        """H2D of the shard, kernels and the collective on self.stream; returns nothing (call finish() for the host copies)."""
+        st = self.stream.cuda_stream
+        with torch.cuda.stream(self.stream):
+            if self.h_items.numel():
+                self.d_items[: self.h_items.numel()].copy_(self.h_items, non_blocking=True)
+            if self.h_arena.numel():
+                self.d_arena[: self.h_arena.numel()].copy_(self.h_arena, non_blocking=True)
+            self.d_local.zero_()
+            if self.hi > self.lo:
+                self.e.verify_device(self.items_base, self.n, self.d_arena.data_ptr(), self.h_arena.numel(), self.lo, self.hi,
+                                     self.bitmap_base, 0, st)
+            self.e.quorum_mark_device(self.items_base, self.n, self.lo, self.hi, self.bitmap_base,
+                                      self.d_local.data_ptr() + self.per * 4, st)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.d_gather, self.d_local)
+            else:
+                self.d_gather.copy_(self.d_local)
+            self.e.quorum_merge_device(self.d_gather.data_ptr() + self.per * 4, self.world, self.per + self.W,
+                                       self.d_results.data_ptr(), st)
+            nres = self.d_results.numel()
+            self.h_out[:nres].copy_(self.d_results, non_blocking=True)
+            words = self.d_gather.view(self.world, self.per + self.W)[:, : self.per].contiguous().view(torch.uint8).reshape(-1)
+            self.h_out[nres:].copy_(words, non_blocking=True)
+
+    def finish(self):
+        self.stream.synchronize()
+        nres = self.d_results.numel()
+        res = self.h_out[:nres].numpy().view(self.result_dtype).copy()
+        bm = self.h_out[nres:].numpy().view(np.uint32)[: (self.n + 31) // 32].copy()
+        return res, bm
+
+    def run(self):
+        self.enqueue()
+        return self.finish()

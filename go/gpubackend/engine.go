@@ -10,6 +10,7 @@ package gpubackend
 #cgo CFLAGS: -I${SRCDIR}/../../include
 #cgo LDFLAGS: -L${SRCDIR}/../../go-ibft_b200 -libftverify -Wl,-rpath,${SRCDIR}/../../go-ibft_b200
 #include <stdlib.h>
+#include <string.h>
 #include "ibft_verify.h"
 */
 import "C"
@@ -22,11 +23,16 @@ import (
 	"unsafe"
 )
 
-// Engine owns one ibft_engine (one per process per GPU).
+// Engine owns one ibft_engine (one per process per GPU).  The engine itself runs up to two host-buffer calls at a time (a
+// full-capacity lane and a small lane for ingress batches); VerifyBatch may be called from any number of goroutines.
 type Engine struct {
 	h      *C.ibft_engine
 	params C.ibft_engine_params
-	mu     sync.Mutex
+	mu     sync.RWMutex      // guards slotHeight
+	// slotHeight[slot] = height of the validator table resident in that slot.  A message of another height that maps to the same
+	// slot (height % slots) must NOT be checked against it: isAcceptableMessage admits any future height (core/ibft.go:1139-1148),
+	// so H + k*slots would otherwise be answered from H's validator set.  The engine checks ibft_group_desc.height as well.
+	slotHeight map[uint32]uint64
 }
 
 type Params struct {
@@ -40,7 +46,7 @@ func lastError() error { return errors.New(C.GoString(C.ibft_last_error())) }
 
 // NewEngine fails when no CUDA device is usable: there is no CPU fallback (IBFT_ERR_NO_DEVICE).
 func NewEngine(p Params) (*Engine, error) {
-	e := &Engine{}
+	e := &Engine{slotHeight: map[uint32]uint64{}}
 	e.params = C.ibft_engine_params{device: C.int32_t(p.Device), max_items: C.uint32_t(p.MaxItems),
 		max_payload_bytes: C.uint32_t(p.MaxPayloadBytes), max_groups: C.uint32_t(p.MaxGroups),
 		max_table_slots: C.uint32_t(p.MaxTableSlots), max_validators: C.uint32_t(p.MaxValidators)}
@@ -96,9 +102,16 @@ func (e *Engine) SetValidators(height uint64, order [][]byte, powers map[string]
 	if len(addrs) > 0 {
 		ap, pp = (*C.uint8_t)(unsafe.Pointer(&addrs[0])), (*C.uint8_t)(unsafe.Pointer(&pw[0]))
 	}
+	// the slot stops answering for its old height BEFORE the engine swaps the table
+	e.mu.Lock()
+	delete(e.slotHeight, uint32(slot))
+	e.mu.Unlock()
 	if rc := C.ibft_set_validators(e.h, slot, C.uint64_t(height), ap, pp, C.uint32_t(len(addrs)/20)); rc != C.IBFT_OK {
 		return fmt.Errorf("ibft_set_validators: %w", lastError())
 	}
+	e.mu.Lock()
+	e.slotHeight[uint32(slot)] = height
+	e.mu.Unlock()
 	return nil
 }
 
@@ -120,12 +133,12 @@ func (e *Engine) VerifyBatch(items []Item) ([]bool, error) {
 	if n == 0 {
 		return nil, nil
 	}
-	e.mu.Lock()
-	defer e.mu.Unlock()
 	packed := make([]C.ibft_sig_item, n)
 	var arena []byte
 	groups := []C.ibft_group_desc{}
 	groupOf := map[uint64]uint16{}
+	noTable := map[uint16]bool{} // groups whose height has no resident table: verdict forced to false
+	e.mu.RLock()
 	for i, it := range items {
 		p := &packed[i]
 		if len(it.Sig) != 65 || len(it.Signer) != 20 || (it.Kind == C.IBFT_KIND_SEAL && len(it.Hash) != 32) {
@@ -136,7 +149,15 @@ func (e *Engine) VerifyBatch(items []Item) ([]bool, error) {
 		if !ok {
 			g = uint16(len(groups))
 			groupOf[it.Height] = g
-			groups = append(groups, C.ibft_group_desc{table_slot: C.uint16_t(it.Height % uint64(e.params.max_table_slots))})
+			slot := uint32(it.Height % uint64(e.params.max_table_slots))
+			d := C.ibft_group_desc{table_slot: C.IBFT_NO_TABLE, height: C.uint64_t(it.Height)}
+			if h, set := e.slotHeight[slot]; set && h == it.Height {
+				d.table_slot = C.uint16_t(slot)
+			} else {
+				// a height whose validator table is not resident has no members: false, never another height's table
+				noTable[g] = true
+			}
+			groups = append(groups, d)
 		}
 		C.memcpy(unsafe.Pointer(&p.r[0]), unsafe.Pointer(&it.Sig[0]), 32)
 		C.memcpy(unsafe.Pointer(&p.s[0]), unsafe.Pointer(&it.Sig[32]), 32)
@@ -151,6 +172,7 @@ func (e *Engine) VerifyBatch(items []Item) ([]bool, error) {
 			arena = append(arena, it.Payload...)
 		}
 	}
+	e.mu.RUnlock()
 	bitmap := make([]uint32, (n+31)/32)
 	var ap *C.uint8_t
 	if len(arena) > 0 {
@@ -160,14 +182,31 @@ func (e *Engine) VerifyBatch(items []Item) ([]bool, error) {
 	if len(groups) > 0 {
 		gp = &groups[0]
 	}
-	rc := C.ibft_verify_batch(e.h, &packed[0], C.uint32_t(n), ap, C.size_t(len(arena)), gp, C.uint32_t(len(groups)),
-		(*C.uint32_t)(unsafe.Pointer(&bitmap[0])), nil, nil)
+	// _ex: everything comes back with the call itself (a goroutine may change OS threads between two cgo calls, so the
+	// "last call" getters are not usable from Go)
+	rc := C.ibft_verify_batch_ex(e.h, &packed[0], C.uint32_t(n), ap, C.size_t(len(arena)), gp, C.uint32_t(len(groups)),
+		(*C.uint32_t)(unsafe.Pointer(&bitmap[0])), nil, nil, nil, nil, 0)
 	if rc != C.IBFT_OK {
-		return nil, fmt.Errorf("ibft_verify_batch: %w", lastError())
+		return nil, fmt.Errorf("ibft_verify_batch_ex: %w", lastError())
 	}
 	out := make([]bool, n)
 	for i := range out {
-		out[i] = bitmap[i/32]>>(uint(i)%32)&1 == 1
+		out[i] = bitmap[i/32]>>(uint(i)%32)&1 == 1 && !noTable[uint16(packed[i].group)]
+	}
+	return out, nil
+}
+
+// ProposalHash = Keccak-256(Keccak-256(raw) || u64_be(round)), both sponges in one device launch (IsValidProposalHash,
+// core/backend.go:50-51; the synthetic convention of SURVEY.md §8c -- a real embedder substitutes its block hash).
+func (e *Engine) ProposalHash(raw []byte, round uint64) ([32]byte, error) {
+	var out [32]byte
+	off, ln, rd := C.uint32_t(0), C.uint32_t(len(raw)), C.uint64_t(round)
+	var dp *C.uint8_t
+	if len(raw) > 0 {
+		dp = (*C.uint8_t)(unsafe.Pointer(&raw[0]))
+	}
+	if rc := C.ibft_proposal_hash_batch(e.h, dp, C.size_t(len(raw)), &off, &ln, &rd, 1, (*C.uint8_t)(unsafe.Pointer(&out[0]))); rc != C.IBFT_OK {
+		return out, lastError()
 	}
 	return out, nil
 }

@@ -157,3 +157,33 @@ def keccak256_batch(arena: bytes | np.ndarray, offs, lens, n_threads: int = 8) -
     lib().oracle_keccak256_batch(a.ctypes.data_as(ctypes.c_void_p), offs.ctypes.data_as(ctypes.c_void_p), lens.ctypes.data_as(ctypes.c_void_p),
                                  ctypes.c_uint32(len(offs)), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n_threads))
     return out
+
+
+# ---- second CPU arm: OpenSSL 3 point arithmetic (oracle/c/ossl_recover.c); None when libcrypto was not available at build time
+_OSSL = None
+
+
+def ossl_lib():
+    global _OSSL
+    if _OSSL is None:
+        build()
+        so = os.path.join(_HERE, "liboracle_ossl.so")
+        if not os.path.exists(so):
+            subprocess.call(["make", "-C", _HERE, "-s", "liboracle_ossl.so"])
+        _OSSL = ctypes.CDLL(so) if os.path.exists(so) else False
+    return _OSSL or None
+
+
+def ossl_verify_batch(items: np.ndarray, arena: bytes = b"", table=None, n_threads: int = 1):
+    L = ossl_lib()
+    if L is None:
+        return None
+    items = np.ascontiguousarray(items)
+    n = len(items)
+    bitmap = np.zeros((n + 31) // 32, dtype=np.uint32)
+    arena_np = np.frombuffer(arena, dtype=np.uint8) if arena else np.zeros(1, dtype=np.uint8)
+    tab = None if table is None else np.ascontiguousarray(table, dtype=np.uint8).reshape(-1, 20)
+    L.ossl_verify_batch(items.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(n), arena_np.ctypes.data_as(ctypes.c_void_p),
+                        ctypes.c_size_t(len(arena)), None if tab is None else tab.ctypes.data_as(ctypes.c_void_p),
+                        ctypes.c_uint32(0 if tab is None else len(tab)), ctypes.c_int(n_threads), bitmap.ctypes.data_as(ctypes.c_void_p))
+    return bitmap

@@ -88,8 +88,8 @@ def test_commit_round_batched_and_serial_match_oracle():
         assert c.store_senders(height, 0, ip.COMMIT) == sorted(m.from_ for m in o.messages.maps[ip.COMMIT][height][0].values())
         assert c.seal_count() == len(o.state.seals) == n - 5
         calls = c.gpu_device_calls() - calls0
-        # batched: keccak(raw) + keccak(inner||round) + ONE verify launch for all seals; serial: one launch per seal
-        assert calls == (3 if batching else 2 + len([m for m in commits if len(m.payload.committed_seal) == 65 and len(m.payload.proposal_hash) == 32 and m.payload.proposal_hash == ph]))
+        # batched: ONE proposal-hash launch (both sponges) + ONE verify launch for all seals; serial: one launch per seal
+        assert calls == (2 if batching else 1 + len([m for m in commits if len(m.payload.committed_seal) == 65 and len(m.payload.proposal_hash) == 32 and m.payload.proposal_hash == ph]))
         c.close()
 
 

@@ -142,3 +142,15 @@ def test_third_party_recover_and_sign_vectors():
             assert (sg[:32].hex(), sg[32:64].hex(), sg[64]) == (s["r"], s["s"], s["v"])
         priv = cec.derive_private_key(d, cec.SECP256K1())
         priv.public_key().verify(utils.encode_dss_signature(int(s["r"], 16), int(s["s"], 16)), z, cec.ECDSA(utils.Prehashed(hashes.SHA256())))
+
+
+def test_openssl_arm_matches_the_port_on_config2():
+    """bench.py's second CPU arm (oracle/c/ossl_recover.c: OpenSSL 3 point arithmetic) must give the port's verdicts bit for bit."""
+    import os
+    import numpy as np
+    if co.ossl_lib() is None:
+        pytest.skip("libcrypto not available at build time")
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config2.npz"))
+    items = np.ascontiguousarray(d["items"]).view(co.ITEM_DTYPE).reshape(-1)
+    got = co.ossl_verify_batch(items, d["arena"].tobytes(), d["addrs"], 8)
+    assert np.array_equal(got, d["bitmap"])
