@@ -292,8 +292,8 @@ def wire_frames_from_payload_items(items, arena):
     return frames
 
 
-def ingress_leg(local_rank):
-    """64 threads of SINGLE-message IsValidValidator calls through the reference-facing verifier (the call pattern of
+def ingress_leg(local_rank, n_threads=64):
+    """n_threads threads of SINGLE-message IsValidValidator calls through the reference-facing verifier (the call pattern of
     core/ibft.go:1101-1128): the coalescer turns them into a few device batches.  Config 2's 2,000 PREPARE + COMMIT sender messages,
     each asked once per verifier, 8 verifiers (the verdict cache would answer repeats)."""
     import importlib
@@ -320,7 +320,7 @@ def ingress_leg(local_rank):
     for _ in range(8):
         c = host.HostContext("gpu", {}, b"", host.EngineParams(local_rank, 1 << 14, 1 << 22, 32, 8, 4096, 0))
         c.set_validators(int(d2["meta"][2]), addrs, None)
-        v, l, us = c.ingress_storm(frames, 64)
+        v, l, us = c.ingress_storm(frames, n_threads)
         mismatches += int((v != gold).sum())
         lat.extend(float(x) for x in l)
         elapsed += us
@@ -329,7 +329,7 @@ def ingress_leg(local_rank):
         c.close()
     if mismatches:
         raise SystemExit("bench: ingress leg: coalesced single-message answers differ from the bulk path's verdicts")
-    return {"threads": 64, "single_message_calls": asked, "device_calls": calls, "calls_per_device_call": asked / max(1, calls),
+    return {"threads": n_threads, "single_message_calls": asked, "device_calls": calls, "calls_per_device_call": asked / max(1, calls),
             "msgs_per_s": asked / (elapsed * 1e-6), "p50_us": _pct(lat, 0.5), "p95_us": _pct(lat, 0.95),
             "answers_equal_bulk_path": True,
             "note": "IsValidValidator per inbound gossip message from 64 threads (core/ibft.go:1101-1128); a cache miss joins the "
@@ -812,7 +812,11 @@ def main():
         line["quorum_latency_us"]["cpu"] = cpu_latency_legs(d, base_items, cores)
         line["proposal_hash"] = hash_crossover_leg(eng)
     if n_gpus == 1:
-        line["ingress"] = ingress_leg(local_rank)
+        line["ingress"] = ingress_leg(local_rank, 64)
+        line["ingress"]["more_callers"] = ingress_leg(local_rank, 512)
+        if "cpu_baseline" in line:
+            line["ingress"]["cpu_oracle"] = {"single_call_us": 1e6 / line["cpu_baseline"]["single_thread"],
+                                             "all_cores_msgs_per_s": line["cpu_baseline"]["value"], "cores": line["cpu_baseline"]["cores"]}
         line["config4"] = config4_legs(ib, local_rank, stream)
     print(json.dumps(line))
     if world > 1:

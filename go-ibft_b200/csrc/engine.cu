@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/ibft_verify.h"
@@ -1799,6 +1800,24 @@ static int launch_quorum(ibft_engine* e, lane* L, const ibft_sig_item* d_items, 
   return IBFT_OK;
 }
 
+// Staging copy of a chunk of pageable caller memory (a cgo caller's Go heap) into the lane's pinned buffer.  One thread moves
+// ~4 GB/s on the GPU boxes' hosts -- 134 MB of tuples would take longer than the kernels that consume them -- so large chunks are
+// split over a few short-lived helper threads (the copy of chunk k+1 already overlaps the device work on chunk k).
+static void stage_copy(void* dst, const void* src, size_t bytes) {
+  const size_t kMin = 2u << 20;
+  if (bytes < 2 * kMin) { memcpy(dst, src, bytes); return; }
+  const unsigned parts = (unsigned)std::min<size_t>(4, bytes / kMin);
+  const size_t per = (bytes / parts + 63) & ~(size_t)63;
+  std::thread th[3];
+  unsigned started = 0;
+  for (unsigned k = 1; k < parts; k++) {
+    size_t off = k * per, len = k + 1 == parts ? bytes - off : per;
+    th[started++] = std::thread([=]() { memcpy((char*)dst + off, (const char*)src + off, len); });
+  }
+  memcpy(dst, src, std::min(per, bytes));
+  for (unsigned k = 0; k < started; k++) th[k].join();
+}
+
 static int submit_locked(ibft_engine* e, lane* L, const ibft_sig_item* items, uint32_t n, const uint8_t* arena, size_t arena_len,
                          const ibft_group_desc* groups, uint32_t n_groups, uint32_t* bitmap_out,
                          ibft_group_result* results_out, uint8_t* recovered_out) {
@@ -1904,7 +1923,7 @@ static int submit_locked(ibft_engine* e, lane* L, const ibft_sig_item* items, ui
     uint32_t lo = c * CHUNK, hi = std::min(n, lo + CHUNK);
     const ibft_sig_item* src = items + lo;
     if (!caller_pinned) {
-      memcpy(L->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
+      stage_copy(L->h_items + lo, items + lo, (size_t)(hi - lo) * sizeof(ibft_sig_item));
       src = L->h_items + lo;
     }
     cudaStream_t cs = n_chunks > 1 ? L->copy_stream : st;

@@ -65,7 +65,8 @@ IBFT_HD bool item_digest(const ibft_sig_item& it, const uint8_t* arena, size_t a
 // (reference messages/proto/messages.proto:24-44) with a canonical-encoding check.  protobuf-go emits fields in
 // field-number order, omits zero scalars / empty bytes and uses minimal varints; only for such a frame does
 // "frame minus the signature TLV" equal PayloadNoSig (clone, Signature = nil, Marshal: messages/proto/helper.go:13-27).
-// Anything else is handed back to the host (status NEEDS_HOST), never guessed.
+// Anything else is handed back to the host (status NEEDS_HOST), never guessed.  All four message types are accepted: the signed
+// bytes of a ROUND_CHANGE / PREPREPARE frame include its nested certificates, which are validated by the same walk.
 // ------------------------------------------------------------------------------------------------------------
 struct wire_frame {
   uint32_t from_off, from_len;      // value of field 2
@@ -100,76 +101,108 @@ IBFT_HD bool wire_len(const uint8_t* w, uint32_t len, uint32_t& pos, uint32_t& o
   return true;
 }
 
-// true: canonical flat PREPARE/COMMIT-payload frame, `f` filled.  false: hand back to the host.
+// Schema-driven canonical walk of a COMPLETE IbftMessage frame, nested certificates included (messages.proto:24-110):
+//   IbftMessage { View view = 1; bytes from = 2; bytes signature = 3; MessageType type = 4;
+//                 oneof payload { PrePrepareMessage = 5; PrepareMessage = 6; CommitMessage = 7; RoundChangeMessage = 8 } }
+//   PrePrepareMessage { Proposal proposal = 1; bytes proposalHash = 2; RoundChangeCertificate certificate = 3 }
+//   RoundChangeMessage { Proposal lastPreparedProposal = 1; PreparedCertificate latestPreparedCertificate = 2 }
+//   PreparedCertificate { IbftMessage proposalMessage = 1; repeated IbftMessage prepareMessages = 2 }
+//   RoundChangeCertificate { repeated IbftMessage roundChangeMessages = 1 }      Proposal { bytes rawProposal = 1; uint64 round = 2 }
+// "canonical" = what protobuf-go emits for the decoded value (decode + encode reproduces the bytes): fields in field-number
+// order (repeated fields contiguous), minimal varints, zero scalars / empty bytes omitted, sub-messages may be present-but-
+// empty, at most one oneof member.  The walk is iterative (an explicit stack of open sub-messages, depth <= IBFT_WIRE_MAX_DEPTH)
+// because device code cannot recurse; a valid frame nests IbftMessage -> payload -> certificate -> IbftMessage -> payload ->
+// certificate -> IbftMessage -> payload = 8 levels (PREPREPARE carrying ROUND_CHANGE messages carrying prepared certificates).
+#define IBFT_WIRE_MAX_DEPTH 12
+enum wire_msg_type : uint8_t { WT_IBFT = 0, WT_VIEW, WT_PREPREPARE, WT_PREPARE, WT_COMMIT, WT_ROUND_CHANGE, WT_PROPOSAL, WT_RCC, WT_PC };
+// field kinds: 0 unknown, 1 varint (non-zero), 2 bytes (non-empty), 3 + t sub-message of type t; bit 7: repeated
+IBFT_HD uint32_t wire_field_kind(uint32_t msg, uint32_t field) {
+  switch (msg) {
+    case WT_IBFT:
+      switch (field) {
+        case 1: return 3 + WT_VIEW;
+        case 2: case 3: return 2;
+        case 4: return 1;
+        case 5: return 3 + WT_PREPREPARE;
+        case 6: return 3 + WT_PREPARE;
+        case 7: return 3 + WT_COMMIT;
+        case 8: return 3 + WT_ROUND_CHANGE;
+        default: return 0;
+      }
+    case WT_VIEW: return (field == 1 || field == 2) ? 1u : 0u;
+    case WT_PREPREPARE: return field == 1 ? 3u + WT_PROPOSAL : field == 2 ? 2u : field == 3 ? 3u + WT_RCC : 0u;
+    case WT_PREPARE: return field == 1 ? 2u : 0u;
+    case WT_COMMIT: return (field == 1 || field == 2) ? 2u : 0u;
+    case WT_ROUND_CHANGE: return field == 1 ? 3u + WT_PROPOSAL : field == 2 ? 3u + WT_PC : 0u;
+    case WT_PROPOSAL: return field == 1 ? 2u : field == 2 ? 1u : 0u;
+    case WT_RCC: return field == 1 ? (0x80u | (3u + WT_IBFT)) : 0u;
+    case WT_PC: return field == 1 ? 3u + WT_IBFT : field == 2 ? (0x80u | (3u + WT_IBFT)) : 0u;
+    default: return 0;
+  }
+}
+
+// true: canonical frame, `f` describes its TOP-LEVEL message (From, the signature TLV, type, which payload member, and for a
+// flat PREPARE / COMMIT payload the proposalHash / committedSeal spans).  false: hand back to the host.
 IBFT_HD bool parse_wire_frame(const uint8_t* w, uint32_t len, wire_frame& f) {
-  f.from_off = f.from_len = f.sig_tag_off = f.sig_end = f.sig_off = f.sig_len = f.type = f.payload_field = 0;
+  f.from_off = f.from_len = f.sig_off = f.sig_len = f.type = f.payload_field = 0;
   f.hash_off = f.hash_len = f.seal_off = f.seal_len = 0;
   f.has_view = false;
   f.sig_tag_off = f.sig_end = 0xFFFFFFFFu;
-  uint32_t pos = 0, last_field = 0;
-  while (pos < len) {
-    uint32_t tag_off = pos;
+  uint32_t end_stack[IBFT_WIRE_MAX_DEPTH];
+  uint8_t type_stack[IBFT_WIRE_MAX_DEPTH], last_stack[IBFT_WIRE_MAX_DEPTH];
+  int depth = 0;
+  end_stack[0] = len;
+  type_stack[0] = WT_IBFT;
+  last_stack[0] = 0;
+  uint32_t pos = 0;
+  for (;;) {
+    while (depth > 0 && pos == end_stack[depth]) depth--;   // close finished sub-messages
+    if (depth == 0 && pos == len) break;
+    const uint32_t end = end_stack[depth], msg = type_stack[depth];
+    const uint32_t tag_off = pos;
     uint64_t key;
-    if (!wire_varint(w, len, pos, key)) return false;
-    uint32_t field = (uint32_t)(key >> 3), wt = (uint32_t)(key & 7);
-    if (key >> 35) return false;
-    if (field <= last_field) return false;  // strictly increasing field numbers (also rejects duplicates)
-    last_field = field;
-    uint32_t off, n;
-    switch (field) {
-      case 1: {  // View { height = 1, round = 2 } : present-but-empty is canonical ("0a 00")
-        if (wt != 2 || !wire_len(w, len, pos, off, n, true)) return false;
-        f.has_view = true;
-        uint32_t p = off, end = off + n, lastv = 0;
-        while (p < end) {
-          uint64_t k2, v2;
-          if (!wire_varint(w, end, p, k2)) return false;
-          uint32_t f2 = (uint32_t)(k2 >> 3);
-          if ((k2 & 7) != 0 || f2 < 1 || f2 > 2 || f2 <= lastv) return false;
-          lastv = f2;
-          if (!wire_varint(w, end, p, v2) || v2 == 0) return false;  // zero scalars are omitted
-        }
-        break;
-      }
-      case 2:
-        if (wt != 2 || !wire_len(w, len, pos, off, n, false)) return false;
-        f.from_off = off;
-        f.from_len = n;
-        break;
-      case 3:
-        if (wt != 2 || !wire_len(w, len, pos, off, n, false)) return false;
-        f.sig_tag_off = tag_off;
-        f.sig_end = pos;
-        f.sig_off = off;
-        f.sig_len = n;
-        break;
-      case 4: {
-        uint64_t v;
-        if (wt != 0 || !wire_varint(w, len, pos, v) || v == 0 || v > 0xFFFFFFFFull) return false;
+    if (!wire_varint(w, end, pos, key) || (key >> 35)) return false;
+    const uint32_t field = (uint32_t)(key >> 3), wt = (uint32_t)(key & 7);
+    const uint32_t kind = wire_field_kind(msg, field);
+    if (kind == 0) return false;  // unknown field (or field 0)
+    const bool repeated = kind & 0x80u;
+    const uint32_t k = kind & 0x7Fu;
+    uint32_t last = last_stack[depth];
+    if (msg == WT_IBFT && last >= 5 && field >= 5) return false;  // the oneof holds at most one member
+    if (repeated ? field < last : field <= last) return false;   // field-number order; only repeated fields may repeat
+    last_stack[depth] = (uint8_t)field;
+    if (k == 1) {
+      uint64_t v;
+      if (wt != 0 || !wire_varint(w, end, pos, v) || v == 0) return false;  // zero scalars are omitted
+      if (depth == 0 && field == 4) {
+        if (v > 0xFFFFFFFFull) return false;
         f.type = (uint32_t)v;
-        break;
       }
-      case 6:
-      case 7: {  // PrepareMessage { proposalHash = 1 } / CommitMessage { proposalHash = 1, committedSeal = 2 }
-        if (wt != 2 || !wire_len(w, len, pos, off, n, true)) return false;
-        f.payload_field = field;
-        uint32_t p = off, end = off + n, lastv = 0;
-        while (p < end) {
-          uint64_t k2;
-          if (!wire_varint(w, end, p, k2)) return false;
-          uint32_t f2 = (uint32_t)(k2 >> 3), o2, n2;
-          if ((k2 & 7) != 2 || f2 < 1 || f2 > (field == 7 ? 2u : 1u) || f2 <= lastv) return false;
-          lastv = f2;
-          if (!wire_len(w, end, p, o2, n2, false)) return false;
-          if (f2 == 1) { f.hash_off = o2; f.hash_len = n2; }
-          else { f.seal_off = o2; f.seal_len = n2; }
-        }
-        last_field = 8;  // the oneof holds at most one member
-        break;
-      }
-      default:
-        return false;  // preprepareData / roundChangeData (nested messages) and unknown fields: host path
+      continue;
     }
+    uint32_t off, n;
+    if (wt != 2 || !wire_len(w, end, pos, off, n, k != 2)) return false;  // bytes fields are never empty; sub-messages may be
+    if (k == 2) {
+      if (depth == 0) {
+        if (field == 2) { f.from_off = off; f.from_len = n; }
+        else { f.sig_tag_off = tag_off; f.sig_end = pos; f.sig_off = off; f.sig_len = n; }
+      } else if (depth == 1 && (msg == WT_PREPARE || msg == WT_COMMIT)) {
+        if (field == 1) { f.hash_off = off; f.hash_len = n; }
+        else { f.seal_off = off; f.seal_len = n; }
+      }
+      continue;
+    }
+    // sub-message: descend (its bytes are [off, off + n); wire_len already moved pos past them, so step back in)
+    if (depth == 0) {
+      if (field == 1) f.has_view = true;
+      else f.payload_field = field;
+    }
+    if (depth + 1 >= IBFT_WIRE_MAX_DEPTH) return false;
+    depth++;
+    end_stack[depth] = off + n;
+    type_stack[depth] = (uint8_t)(k - 3);
+    last_stack[depth] = 0;
+    pos = off;
   }
   if (f.sig_tag_off == 0xFFFFFFFFu) { f.sig_tag_off = f.sig_end = len; }  // no signature field: nothing to cut out
   return true;

@@ -213,7 +213,7 @@ int ibfthost_store_senders(ibfthost_ctx* c, uint64_t h, uint64_t r, uint32_t typ
 int ibfthost_valid_pc(ibfthost_ctx* c, const uint8_t* pc_wire, size_t len, int has_pc, uint64_t round_limit, uint64_t height) {
   if (!has_pc) return (int)c->ibft->validPC(nullptr, round_limit, height);
   try {
-    auto pc = decode_pc(wire::Reader{pc_wire, pc_wire + len});
+    auto pc = decode_pc(wire::Reader{pc_wire, pc_wire + len, 0, nullptr});
     return (int)c->ibft->validPC(pc.get(), round_limit, height);
   } catch (const DecodeError&) { return 0; }
 }

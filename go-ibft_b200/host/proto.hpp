@@ -59,7 +59,13 @@ struct IbftMessage {  // messages.proto:24-44
   Bytes from, signature;
   uint32_t type = PREPREPARE;
   PayloadKind payload_kind = PAYLOAD_NONE;  // which oneof member is set (independent of `type`, as in Go)
-  Bytes raw_wire;  // the frame this message was decoded from (top-level decode only); lets the GPU verifier submit raw frames
+  // Where this message sits in the gossip frame it was decoded from: [wire_off, wire_off + wire_len) of *root_wire.  Set for the
+  // top-level message AND for every message nested in its certificates (they share the root's bytes), so that the GPU verifier can
+  // submit any of them as a raw-frame span without re-marshalling (IBFT_KIND_WIRE).  nullptr for messages built in memory.
+  std::shared_ptr<const Bytes> root_wire;
+  uint32_t wire_off = 0, wire_len = 0;
+  bool has_wire() const { return root_wire != nullptr && wire_len != 0; }
+  const char* wire_data() const { return root_wire->data() + wire_off; }
   PrePrepareMessage preprepare;
   PrepareMessage prepare;
   CommitMessage commit;
@@ -176,6 +182,7 @@ struct Reader {
   const uint8_t* p;
   const uint8_t* end;
   int depth = 0;
+  const std::shared_ptr<const Bytes>* root = nullptr;  // the frame being decoded (sub-readers inherit it): messages record their span
   bool done() const { return p >= end; }
   uint64_t varint() {
     uint64_t v = 0;
@@ -200,7 +207,7 @@ struct Reader {
       case 2: {
         uint64_t n = varint();
         if (n > (uint64_t)(end - p)) throw DecodeError("truncated bytes");
-        sub = Reader{p, p + n, depth + 1};
+        sub = Reader{p, p + n, depth + 1, root};
         if (sub.depth > kMaxDepth) throw DecodeError("message nesting too deep");
         p += n;
         break;
@@ -227,7 +234,7 @@ inline std::shared_ptr<Proposal> decode_proposal(wire::Reader r) {
   auto p = std::make_shared<Proposal>();
   uint32_t num, wt;
   uint64_t val;
-  wire::Reader sub{nullptr, nullptr, 0};
+  wire::Reader sub{nullptr, nullptr, 0, nullptr};
   while (r.next(num, wt, val, sub)) {
     if (num == 1 && wt == 2) p->raw_proposal = sub.bytes();
     else if (num == 2 && wt == 0) p->round = val;
@@ -238,7 +245,7 @@ inline std::shared_ptr<PreparedCertificate> decode_pc(wire::Reader r) {
   auto pc = std::make_shared<PreparedCertificate>();
   uint32_t num, wt;
   uint64_t val;
-  wire::Reader sub{nullptr, nullptr, 0};
+  wire::Reader sub{nullptr, nullptr, 0, nullptr};
   while (r.next(num, wt, val, sub)) {
     if (num == 1 && wt == 2) pc->proposal_message = decode_message(sub);
     else if (num == 2 && wt == 2) pc->prepare_messages.push_back(decode_message(sub));
@@ -249,7 +256,7 @@ inline std::shared_ptr<RoundChangeCertificate> decode_rcc(wire::Reader r) {
   auto c = std::make_shared<RoundChangeCertificate>();
   uint32_t num, wt;
   uint64_t val;
-  wire::Reader sub{nullptr, nullptr, 0};
+  wire::Reader sub{nullptr, nullptr, 0, nullptr};
   while (r.next(num, wt, val, sub))
     if (num == 1 && wt == 2) c->round_change_messages.push_back(decode_message(sub));
   return c;
@@ -257,15 +264,20 @@ inline std::shared_ptr<RoundChangeCertificate> decode_rcc(wire::Reader r) {
 
 inline MessagePtr decode_message(wire::Reader r) {
   auto m = std::make_shared<IbftMessage>();
+  if (r.root && *r.root) {
+    m->root_wire = *r.root;
+    m->wire_off = (uint32_t)(r.p - (const uint8_t*)(*r.root)->data());
+    m->wire_len = (uint32_t)(r.end - r.p);
+  }
   uint32_t num, wt;
   uint64_t val;
-  wire::Reader sub{nullptr, nullptr, 0};
+  wire::Reader sub{nullptr, nullptr, 0, nullptr};
   while (r.next(num, wt, val, sub)) {
     if (num == 1 && wt == 2) {
       auto v = std::make_shared<View>();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0};
+      wire::Reader s2{nullptr, nullptr, 0, nullptr};
       while (sub.next(n2, w2, v2, s2)) {
         if (n2 == 1 && w2 == 0) v->height = v2;
         else if (n2 == 2 && w2 == 0) v->round = v2;
@@ -282,7 +294,7 @@ inline MessagePtr decode_message(wire::Reader r) {
       m->preprepare = PrePrepareMessage();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0};
+      wire::Reader s2{nullptr, nullptr, 0, nullptr};
       while (sub.next(n2, w2, v2, s2)) {
         if (n2 == 1 && w2 == 2) m->preprepare.proposal = decode_proposal(s2);
         else if (n2 == 2 && w2 == 2) m->preprepare.proposal_hash = s2.bytes();
@@ -293,7 +305,7 @@ inline MessagePtr decode_message(wire::Reader r) {
       m->prepare = PrepareMessage();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0};
+      wire::Reader s2{nullptr, nullptr, 0, nullptr};
       while (sub.next(n2, w2, v2, s2))
         if (n2 == 1 && w2 == 2) m->prepare.proposal_hash = s2.bytes();
     } else if (num == 7 && wt == 2) {
@@ -301,7 +313,7 @@ inline MessagePtr decode_message(wire::Reader r) {
       m->commit = CommitMessage();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0};
+      wire::Reader s2{nullptr, nullptr, 0, nullptr};
       while (sub.next(n2, w2, v2, s2)) {
         if (n2 == 1 && w2 == 2) m->commit.proposal_hash = s2.bytes();
         else if (n2 == 2 && w2 == 2) m->commit.committed_seal = s2.bytes();
@@ -311,7 +323,7 @@ inline MessagePtr decode_message(wire::Reader r) {
       m->round_change = RoundChangeMessage();
       uint32_t n2, w2;
       uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0};
+      wire::Reader s2{nullptr, nullptr, 0, nullptr};
       while (sub.next(n2, w2, v2, s2)) {
         if (n2 == 1 && w2 == 2) m->round_change.last_prepared_proposal = decode_proposal(s2);
         else if (n2 == 2 && w2 == 2) m->round_change.latest_prepared_certificate = decode_pc(s2);
@@ -322,9 +334,9 @@ inline MessagePtr decode_message(wire::Reader r) {
 }
 
 inline MessagePtr decode_message(const uint8_t* data, size_t len) {
-  MessagePtr m = decode_message(wire::Reader{data, data + len, 0});
-  m->raw_wire.assign((const char*)data, len);
-  return m;
+  auto root = std::make_shared<const Bytes>((const char*)data, len);
+  const uint8_t* b = (const uint8_t*)root->data();
+  return decode_message(wire::Reader{b, b + len, 0, &root});
 }
 
 }  // namespace ibft::host

@@ -255,7 +255,9 @@ class GpuVerifier : public Verifier {
   struct Pending {
     Bytes key;  // exact-bytes cache key
     ibft_sig_item item;
-    Bytes payload;
+    Bytes payload;                                 // marshalled items: PayloadNoSig
+    std::shared_ptr<const Bytes> wire_root;        // raw-frame items: the span [wire_off, +wire_len) of the frame they came in
+    uint32_t wire_off = 0, wire_len = 0;
     uint64_t height;
     const IbftMessage* fallback_payload_msg = nullptr;  // raw-frame items: the message to re-marshal if the device hands it back
   };
@@ -279,7 +281,8 @@ class GpuVerifier : public Verifier {
   std::mutex ing_mu_;
   std::condition_variable ing_cv_;
   std::deque<std::shared_ptr<Req>> ing_queue_;
-  bool ing_leader_ = false;
+  int ing_leaders_ = 0;
+  static constexpr int kMaxLeaders = 2;  // two flushes may be on the device at once (the engine has two lanes)
 
   static void put_sig(ibft_sig_item& it, const Bytes& sig, const Bytes& signer) {
     memset(&it, 0, sizeof it);
@@ -293,14 +296,18 @@ class GpuVerifier : public Verifier {
   bool sender_item(const IbftMessage& m, Pending& p, bool allow_wire = true) {
     if (!m.view || m.from.size() != 20 || m.signature.size() != 65) return false;
     p.height = m.view->height;
-    if (allow_wire && use_wire_frames && !m.raw_wire.empty() && (m.payload_kind == PAYLOAD_PREPARE || m.payload_kind == PAYLOAD_COMMIT)) {
+    if (allow_wire && use_wire_frames && m.has_wire()) {
+      // any message type, top-level or nested in a certificate: the device walks the frame (canonical-encoding check included)
+      // and hashes it with the signature TLV cut out -- no clone + marshal on the host
       memset(&p.item, 0, sizeof p.item);
       p.item.kind = IBFT_KIND_WIRE;
-      p.payload = m.raw_wire;
+      p.wire_root = m.root_wire;
+      p.wire_off = m.wire_off;
+      p.wire_len = m.wire_len;
       p.fallback_payload_msg = &m;
       p.key.assign(1, 'W');
       for (int j = 7; j >= 0; j--) p.key.push_back((char)(p.height >> (8 * j)));
-      p.key += m.raw_wire;
+      p.key.append(m.wire_data(), m.wire_len);
       return true;
     }
     p.payload = payload_no_sig(m);
@@ -328,8 +335,10 @@ class GpuVerifier : public Verifier {
 
   // INGRESS COALESCER.  The reference calls IsValidValidator once per inbound gossip message from any number of goroutines
   // (core/ibft.go:1101-1128).  One device call per message would cost a whole kernel launch (~0.4 ms) for one signature and
-  // serialise the callers.  Instead a miss is queued; ONE caller at a time is the leader: it takes everything queued (its own
-  // request included), makes a single device call for the batch, publishes the verdicts and wakes the others.  Requests that
+  // serialise the callers.  Instead a miss is queued; a caller that finds fewer than two flushes in flight becomes a leader: it takes
+  // everything queued (its own request included), makes a single device call for the batch, publishes the verdicts and wakes the
+  // others (two leaders at most: the engine runs two host-buffer calls side by side, so the next batch goes up while the previous
+  // one is still on the device).  Requests that
   // arrive while a flush is on the device pile up and form the next batch -- the batch size adapts to the arrival rate with no
   // timer (group commit); `ingress_linger_us` / `ingress_min_batch` add an optional wait for sparse traffic.  The verdict of
   // every request is exactly what a single-item call would have returned: same item, same table, same kernels.
@@ -346,11 +355,11 @@ class GpuVerifier : public Verifier {
     std::unique_lock<std::mutex> lk(ing_mu_);
     ing_queue_.push_back(req);
     while (!req->done) {
-      if (ing_leader_) {
+      if (ing_leaders_ >= kMaxLeaders || ing_queue_.empty()) {
         ing_cv_.wait(lk);
         continue;
       }
-      ing_leader_ = true;
+      ing_leaders_++;
       if (ingress_linger_us && ing_queue_.size() < ingress_min_batch) {
         lk.unlock();
         std::this_thread::sleep_for(std::chrono::microseconds(ingress_linger_us));
@@ -379,7 +388,7 @@ class GpuVerifier : public Verifier {
         taken[i]->result = verdicts[slot_of[i]] == 1;  // no verdict (launch failure) => false, never true
         taken[i]->done = true;
       }
-      ing_leader_ = false;
+      ing_leaders_--;
       ing_cv_.notify_all();
     }
     return req->result;
@@ -403,6 +412,7 @@ class GpuVerifier : public Verifier {
       std::vector<ibft_sig_item> items(n);
       std::vector<ibft_group_desc> groups;
       std::map<uint64_t, uint16_t> group_of_height;
+      std::unordered_map<const Bytes*, uint32_t> frame_at;  // root frame -> its offset in this call's arena
       Bytes arena;
       for (size_t i = 0; i < n; i++) {
         Pending& p = batch[pos + i];
@@ -421,7 +431,21 @@ class GpuVerifier : public Verifier {
         }
         items[i] = p.item;
         items[i].group = g->second;
-        if (p.item.kind == IBFT_KIND_PAYLOAD || p.item.kind == IBFT_KIND_WIRE) {
+        if (p.item.kind == IBFT_KIND_WIRE) {
+          // a frame goes into the arena ONCE; messages nested in its certificates are spans inside it.  A nested message whose
+          // root frame is not part of this batch contributes only its own bytes.
+          auto placed = frame_at.find(p.wire_root.get());
+          if (placed != frame_at.end()) {
+            items[i].payload_off = placed->second + p.wire_off;
+          } else {
+            const bool whole = p.wire_off == 0 && p.wire_len == p.wire_root->size();
+            if (arena.size() + p.wire_len > params_.max_payload_bytes) { n = i; break; }
+            items[i].payload_off = (uint32_t)arena.size();
+            if (whole) frame_at.emplace(p.wire_root.get(), (uint32_t)arena.size());
+            arena.append(p.wire_root->data() + p.wire_off, p.wire_len);
+          }
+          items[i].payload_len = p.wire_len;
+        } else if (p.item.kind == IBFT_KIND_PAYLOAD) {
           if (arena.size() + p.payload.size() > params_.max_payload_bytes) { n = i; break; }
           items[i].payload_off = (uint32_t)arena.size();
           items[i].payload_len = (uint32_t)p.payload.size();

@@ -154,11 +154,14 @@ def test_config4_full_size_10k_round_change_with_nested_certificates(big_engine)
     assert int(results[0]["n_valid"]) == 20_000 and int(results[0]["n_distinct"]) == 10_000 and bool(results[0]["has_quorum"])
 
 
-def test_config4_n1000_end_to_end_through_wire_codec_and_host_mirror():
+@pytest.mark.parametrize("raw_frames", [False, True])
+def test_config4_n1000_end_to_end_through_wire_codec_and_host_mirror(raw_frames):
     """The same shape at N = 1,000 through the REAL path: wire frames -> C++ decoder -> batching store shim -> GpuVerifier (one
     de-duplicated device batch) -> handleRoundChangeMessage, against oracle/ibft_logic.py with the oracle's ecrecover
     (core/ibft.go:470-512, :1162-1231; messages/messages.go:202-245).  93 MB of ROUND_CHANGE frames, ~667k nested checks,
-    1,002 + 999 unique signatures."""
+    1,002 + 999 unique signatures.
+    raw_frames=True: every message -- the ROUND_CHANGE frames AND the messages nested in their certificates -- goes to the device as
+    a span of the gossip frame it arrived in (IBFT_KIND_WIRE): zero PayloadNoSig re-marshals on the host."""
     n, height = 1000, 1_000_000
     q = 2 * n // 3 + 1
     priv = co.privkeys(3, n)
@@ -231,6 +234,7 @@ def test_config4_n1000_end_to_end_through_wire_codec_and_host_mirror():
     params = host.EngineParams(0, 1 << 14, 1 << 27, 32, 8, 4096, 0)   # the 1,000 sender payloads are 93 MB of signed bytes
     c = host.HostContext("gpu", {"is_proposer": proposer_of}, b"", params)
     assert c.set_validators(height, addrs, None) == 0
+    c.set_wire_frames(raw_frames)
     o.state.view = view1
     c.set_state(height, 1, L.NEW_ROUND, None)
     for m, wbytes in zip(rcs, wires):
@@ -244,4 +248,5 @@ def test_config4_n1000_end_to_end_through_wire_codec_and_host_mirror():
     # unique signatures: n senders + 1 PREPREPARE + the distinct PREPAREs the certificates cover (300 + span) + 1 corrupted variant
     assert c.gpu_items_verified() - items0 == n + 1 + (300 + span) + 1
     assert c.gpu_device_calls() - calls0 <= 3
+    assert c.gpu_frames_handed_back() == 0              # every frame was canonical: nothing was re-marshalled on the host
     c.close()

@@ -101,7 +101,7 @@ def test_verify_batch_ex_returns_status_and_voted_sets_with_the_call(engine):
 def test_two_host_buffer_calls_run_concurrently_and_stay_bit_exact():
     """The engine serialised every call behind one mutex in round 1.  Two lanes now: a bulk handler batch and small ingress
     batches proceed side by side; every call still gets exactly its own verdicts."""
-    d = np.load(os.path.join(HERE, "golden", "config3.npz"))
+    d = dict(np.load(os.path.join(HERE, "golden", "config3.npz")))   # materialised: NpzFile reads lazily and is not thread-safe
     items = np.ascontiguousarray(d["items"]).view(ib.ITEM_DTYPE).reshape(-1)
     e = ib.Engine(device=0, max_items=1 << 17, max_payload_bytes=1 << 24, max_groups=8, max_table_slots=2, max_validators=16384)
     try:
