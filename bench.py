@@ -459,6 +459,7 @@ def main():
     ap.add_argument("--latency-reps", type=int, default=200)
     ap.add_argument("--no-key-cache-leg", action="store_true", help="skip the extra leg that times the key-registry path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="headline + e2e + strong-scaling legs only (development: short multi-GPU runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -628,6 +629,18 @@ def main():
             dist.destroy_process_group()
         return
 
+    if args.skip_extras:
+        print(json.dumps({"metric": "secp256k1_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": n_gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u32 (256-bit modular integer)", "data": "synthetic", "config": workload_config(n_gpus),
+                          "clocks": sampler.summary(), "gpu_launches": int(launches),
+                          "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                          "strong_scaling": strong, "note": "--skip-extras: development run without the latency / CPU / ingress legs"}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     # ---- quorum latency of ONE 10k-validator COMMIT round (10,000 committed seals), host buffers in / bitmap + quorum out
     seal_group = list(d["groups"]).index("COMMIT_SEAL")
     seals = np.ascontiguousarray(base_items[base_items["group"] == seal_group])
@@ -720,8 +733,29 @@ def main():
         for _ in range(e2e_steps):
             bm_k, _, _ = eng_k.verify_batch(host_local, arena_host, groups)
         e2e_k = n_global * e2e_steps / (time.perf_counter() - t0)
+        # the 10,000-seal round on the known-key LATENCY path (k_verify_split + worklist k_recover_qsplit), host buffers in / out
+        lat_known = []
+        for i in range(args.latency_reps + 5):
+            t0 = time.perf_counter()
+            bm_s, _, _ = eng_k.verify_batch(seals, b"", groups)
+            if i >= 5:
+                lat_known.append((time.perf_counter() - t0) * 1e6)
+        bm_plain, _, _ = eng.verify_batch(seals, b"", groups)
+        if not np.array_equal(bm_s, bm_plain):
+            raise SystemExit("bench: known-key latency path: bitmap differs from the recover path")
+        # and an all-valid round (no worklist work at all): the 9,900 valid seals only
+        seals_ok = np.ascontiguousarray(seals[np.unpackbits(bm_plain.view(np.uint8), bitorder="little")[: len(seals)] == 1])
+        lat_known_ok = []
+        for i in range(args.latency_reps + 5):
+            t0 = time.perf_counter()
+            eng_k.verify_batch(seals_ok, b"", groups)
+            if i >= 5:
+                lat_known_ok.append((time.perf_counter() - t0) * 1e6)
         known = {"value": n_global / (ms_k * 1e-3), "unit": "verifies/s", "ms_per_step": ms_k, "e2e": e2e_k, "keys_known": keys_known,
                  "gpu_launches": int(eng_k.launch_count() - lk0),
+                 "round10k_p50_us": _pct(lat_known, 0.5), "round10k_p95_us": _pct(lat_known, 0.95),
+                 "round10k_all_valid_p50_us": _pct(lat_known_ok, 0.5), "round10k_all_valid_items": int(len(seals_ok)),
+                 "round10k_kernel": "k_verify_split (chain + helper warps, verification against the learned keys) + k_recover_qsplit on the worklist",
                  "bitmap_matches_golden": bool(np.array_equal(np.unpackbits(bm_k.view(np.uint8), bitorder="little")[:n_global], np.tile(golden_bits, reps)[:n_global])),
                  "note": "engine flag IBFT_FLAG_KEY_CACHE: k_verify_known (ECDSA verification against the validator's learned key) + k_recover on the "
                          "worklist of everything not accepted; verdicts are the recover path's by construction; the first (cold) pass over "

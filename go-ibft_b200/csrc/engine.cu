@@ -663,6 +663,223 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
 
 #if IBFT_WC > 0
 // ------------------------------------------------------------------------------------------------------------
+// Known-key LATENCY variant (engine flag IBFT_FLAG_KEY_CACHE, mid-size rounds): k_recover_split's chain + helper layout, but
+// the signature is VERIFIED against the validator's learned key instead of recovered (verify_core.cuh "Verification against a
+// KNOWN public key").  The helper warp supplies w = s^-1 (one inversion for the lane's three signatures), the digits of
+// u2 = r w, and later the affine u1*G = (z w) G from the comb tables; the chain warp walks u2*Q over the validator's table of
+// multiples -- 17 rounds of 8 doublings + at most two additions, no per-signature table, no square root, no address hash --
+// adds u1*G and accepts iff the point is exactly R = (r, y) with parity(y) = v.  An accept IS the recover path's verdict 1.
+// Everything else that could still be valid -- key not learned yet, or the verification rejected -- goes to the worklist and is
+// decided by the recover path (k_recover_qsplit in worklist mode, launched right behind this kernel); items that can never be
+// valid (malformed, out of range, unknown group, signer not in the set) are settled here.  A round in which every signature
+// verifies (the normal case of consensus) never runs a second chain.
+// ------------------------------------------------------------------------------------------------------------
+#define IBFT_VSLOT_WORDS 28   // IBFT_SLOT_WORDS + [27] validator index of the signer
+#define IBFT_VSPLIT_SMEM ((IBFT_SPLIT_SIGS * (IBFT_ITEM_ROW_WORDS + IBFT_VSLOT_WORDS)) * 4)
+#define IBFT_VF_VALID 1u      // digits of u2 posted: the chain runs
+#define IBFT_VF_NEG0 2u
+#define IBFT_VF_NEG1 4u
+#define IBFT_VF_GREADY 8u     // u1*G posted
+#define IBFT_VF_GINF 16u
+#define IBFT_VF_RECOVER 32u   // member, but the key is not known yet: worklist
+__global__ void __launch_bounds__(32 * (IBFT_SPLIT_CHAINS + 1), 1)
+k_verify_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
+               uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
+               const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap, uint8_t* __restrict__ status,
+               const uint32_t* __restrict__ ctable, vote_sink sink, uint32_t* __restrict__ worklist) {
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t* s_items = s_dyn;
+  uint32_t* s_slot = s_items + IBFT_SPLIT_SIGS * IBFT_ITEM_ROW_WORDS;  // word w of signature i at [w * 96 + i]
+  const uint32_t S = IBFT_SPLIT_SIGS;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const uint32_t base = shard_lo + blockIdx.x * IBFT_SPLIT_SIGS;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(items + base);
+    uint32_t avail = base < shard_hi ? min((uint32_t)IBFT_SPLIT_SIGS, shard_hi - base) : 0u;
+#pragma unroll
+    for (int k = 0; k < (IBFT_SPLIT_SIGS * 8) / (32 * (IBFT_SPLIT_CHAINS + 1)); k++) {
+      uint32_t u = tid + k * 32 * (IBFT_SPLIT_CHAINS + 1);
+      uint32_t row = u >> 3, col = u & 7;
+      if (row < avail) {
+        uint4 v = __ldg(src + u);
+        uint32_t* d = s_items + row * IBFT_ITEM_ROW_WORDS + col * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+  }
+  __syncthreads();
+  gtab_view G{g_gtable};
+  G.comb = ctable;
+  if (warp == IBFT_SPLIT_CHAINS) {
+    // ------------------------------------------------------------------ helper warp
+    uint32_t okmask = 0;
+    IBFT_ROLLED
+    for (uint32_t p = 0; p < IBFT_SPLIT_CHAINS; p++) {
+      const uint32_t i = 32 * p + lane, idx = base + i;
+      uint32_t flags = 0;
+      if (idx < shard_hi) {
+        ibft_sig_item it;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+        const uint32_t* src = s_items + i * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+        for (int k = 0; k < 32; k++) w[k] = src[k];
+        resolved_item ri;
+        bool have = false;
+        int st = resolve_item(it, arena, arena_len, ri, &have, false);
+        if (status != nullptr) status[idx] = (uint8_t)st;
+        have = have && split_sig_in_range(ri);
+        int v = -1;
+        uint32_t slot = IBFT_NO_TABLE;
+        if (have && group_member(groups, n_groups, slots, n_slots, it.group, ri.signer, &v, &slot)) {
+          const bool ready = v >= 0 && slots[slot].key_state != nullptr && slots[slot].key_state[v] == IBFT_KEY_READY;
+          if (ready) {
+            sc r = sc_from_be(ri.r), sv = sc_from_be(ri.s);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              s_slot[(11 + k) * S + i] = sv.v[k];   // s (inverted below), then r
+              s_slot[(19 + k) * S + i] = r.v[k];
+            }
+            s_slot[27 * S + i] = (uint32_t)v | (slot << 16);
+            okmask |= 1u << p;
+          } else {
+            flags = IBFT_VF_RECOVER;               // member whose key is not known (or no table: v < 0): the recover path decides
+          }
+        }
+      }
+      s_slot[10 * S + i] = flags;
+    }
+    {
+      // w = s^-1 for the lane's signatures with ONE inversion (Montgomery's trick; an absent one contributes 1)
+      sc one;
+#pragma unroll
+      for (int k = 0; k < 8; k++) one.v[k] = k == 0;
+      sc ss[IBFT_SPLIT_CHAINS], pre[IBFT_SPLIT_CHAINS];
+#pragma unroll
+      for (uint32_t p = 0; p < IBFT_SPLIT_CHAINS; p++) {
+        ss[p] = one;
+        if ((okmask >> p) & 1u) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) ss[p].v[k] = s_slot[(11 + k) * S + 32 * p + lane];
+        }
+        pre[p] = p ? sc_mul(pre[p - 1], ss[p]) : ss[p];
+      }
+      sc inv = IBFT_SC_INV(pre[IBFT_SPLIT_CHAINS - 1]);
+#pragma unroll
+      for (int p = IBFT_SPLIT_CHAINS - 1; p >= 0; p--) {
+        sc wi = p ? sc_mul(inv, pre[p - 1]) : inv;
+        if (p) inv = sc_mul(inv, ss[p]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_slot[(11 + k) * S + 32 * p + lane] = wi.v[k];  // w replaces s
+      }
+    }
+    IBFT_ROLLED
+    for (uint32_t p = 0; p < IBFT_SPLIT_CHAINS; p++) {
+      const uint32_t i = 32 * p + lane;
+      if ((okmask >> p) & 1u) {
+        sc w, r;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          w.v[k] = s_slot[(11 + k) * S + i];
+          r.v[k] = s_slot[(19 + k) * S + i];
+        }
+        ecmult_digits dg;
+        ecmult_split_into(sc_mul(r, w), dg, 0);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          s_slot[k * S + i] = dg.ks[0][k];
+          s_slot[(5 + k) * S + i] = dg.ks[1][k];
+        }
+        s_slot[10 * S + i] = IBFT_VF_VALID | (dg.kneg[0] ? IBFT_VF_NEG0 : 0u) | (dg.kneg[1] ? IBFT_VF_NEG1 : 0u);
+      }
+      __threadfence_block();
+      named_bar_arrive(1 + p, 64);
+    }
+    IBFT_ROLLED
+    for (uint32_t p = 0; p < IBFT_SPLIT_CHAINS; p++) {
+      const uint32_t i = 32 * p + lane;
+      if ((okmask >> p) & 1u) {
+        ibft_sig_item it;
+        uint32_t* wd = reinterpret_cast<uint32_t*>(&it);
+        const uint32_t* src = s_items + i * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+        for (int k = 0; k < 32; k++) wd[k] = src[k];
+        resolved_item ri;
+        bool have = false;
+        resolve_item(it, arena, arena_len, ri, &have, true);  // this time with the digest
+        sc w;
+#pragma unroll
+        for (int k = 0; k < 8; k++) w.v[k] = s_slot[(11 + k) * S + i];
+        fe gx = fe_zero(), gy = fe_zero();
+        bool g_inf = false;
+        known_helper_u1g(ri, w, G, g_inf, gx, gy);
+        uint32_t flags = s_slot[10 * S + i] | IBFT_VF_GREADY | (g_inf ? IBFT_VF_GINF : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          s_slot[(11 + k) * S + i] = gx.v[k];
+          s_slot[(19 + k) * S + i] = gy.v[k];
+        }
+        s_slot[10 * S + i] = flags;
+      }
+      __threadfence_block();
+      named_bar_arrive(1 + IBFT_SPLIT_CHAINS + p, 64);
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- chain warp: u2 * Q from the validator's table
+  const uint32_t i = tid, idx = base + i;
+  const bool active = idx < shard_hi;
+  named_bar_sync(1 + warp, 64);  // digits of u2 (and the verdict of the structural checks) are posted
+  jac acc;
+  acc.x = fe_zero(); acc.y = fe_zero(); acc.z = fe_zero();
+  acc.inf = true;
+  uint32_t flags = active ? s_slot[10 * S + i] : 0u;
+  uint32_t vslot = 0;
+  if (flags & IBFT_VF_VALID) {
+    ecmult_digits dg;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      dg.ks[0][k] = s_slot[k * S + i];
+      dg.ks[1][k] = s_slot[(5 + k) * S + i];
+      dg.ks[2][k] = dg.ks[3][k] = 0;
+    }
+    dg.ks[0][5] = dg.ks[1][5] = dg.ks[2][5] = dg.ks[3][5] = 0;
+    dg.kneg[0] = flags & IBFT_VF_NEG0; dg.kneg[1] = flags & IBFT_VF_NEG1;
+    dg.kneg[2] = dg.kneg[3] = false;
+    vslot = s_slot[27 * S + i];
+    const slot_dev& sd = slots[vslot >> 16];
+    gtab_view Qt{sd.key_tab + (size_t)(vslot & 0xFFFFu) * IBFT_KEYTAB_ENTRIES * IBFT_GTAB_ENTRY_WORDS};
+    acc = ecmult_streams_known(dg, G, Qt, false);
+  }
+  named_bar_sync(1 + IBFT_SPLIT_CHAINS + warp, 64);  // u1*G is posted
+  bool ok = false;
+  if (flags & IBFT_VF_VALID) {
+    const uint32_t f2 = s_slot[10 * S + i];
+    fe gx, gy;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      gx.v[k] = s_slot[(11 + k) * S + i];
+      gy.v[k] = s_slot[(19 + k) * S + i];
+    }
+    ibft_sig_item it;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&it);
+    const uint32_t* src = s_items + i * IBFT_ITEM_ROW_WORDS;
+#pragma unroll
+    for (int k = 0; k < 32; k++) w[k] = src[k];
+    resolved_item ri;
+    bool have = false;
+    resolve_item(it, arena, arena_len, ri, &have, false);
+    ok = known_chain_finish(acc, (f2 & IBFT_VF_GINF) != 0, gx, gy, ri);
+    if (ok) record_vote(sink, groups, it.group, (int)(vslot & 0xFFFFu));
+  }
+  // whatever was not accepted but could still be valid goes to the recover pass
+  if (active && !ok && (flags & (IBFT_VF_VALID | IBFT_VF_RECOVER))) worklist[1 + atomicAdd(&worklist[0], 1u)] = idx;
+  uint32_t word = __ballot_sync(0xFFFFFFFFu, ok);
+  if (lane == 0 && active) bitmap[idx >> 5] = word;
+}
+#endif
+
+#if IBFT_WC > 0
+// ------------------------------------------------------------------------------------------------------------
 // K1 + K2, small-round latency variant: the two ideas above combined.  CTA = 3 four-lane CHAIN warps (8 signatures each)
 // + 1 HELPER warp (one lane per signature, a single pass over the CTA's 24), one CTA per SM, one warp per scheduler.
 // The quads walk only u2*phi(R) (XYZZ levels, projective table, no square root, no inversion before the final one);
@@ -677,23 +894,30 @@ __global__ void __launch_bounds__(128, IBFT_QSPLIT_MIN_CTAS)
 k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
                  uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
                  const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
-                 uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink) {
+                 uint8_t* __restrict__ recovered, uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink,
+                 const uint32_t* __restrict__ list) {
+  // list != nullptr: WORKLIST mode (second pass of the known-key latency path): list[0] = count, list[1..] = item indices; the
+  // t-th signature of the grid is item list[1 + t]; CTAs beyond the count leave at once; verdict bits are OR-ed in.
   __shared__ uint32_t s_items[IBFT_QSPLIT_SIGS * IBFT_ITEM_ROW_WORDS];
+  __shared__ uint32_t s_idx[IBFT_QSPLIT_SIGS];
   __shared__ uint32_t s_qtab[IBFT_QSPLIT_SIGS * IBFT_QTAB_WORDS];
   __shared__ uint32_t s_slot[IBFT_QSPLIT_SIGS * IBFT_SLOT_WORDS];
   __shared__ uint32_t s_y[IBFT_QSPLIT_SIGS * 8];
   __shared__ uint4 s_xb[4 * 128];
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-  const uint32_t base = shard_lo + blockIdx.x * IBFT_QSPLIT_SIGS;
+  const uint32_t base = list ? blockIdx.x * IBFT_QSPLIT_SIGS : shard_lo + blockIdx.x * IBFT_QSPLIT_SIGS;
+  const uint32_t limit = list ? list[0] : shard_hi;   // rows [base, limit) of this CTA exist
+  if (base >= limit) return;                            // (uniform over the CTA)
   {
-    const uint4* src = reinterpret_cast<const uint4*>(items + base);
-    uint32_t avail = base < shard_hi ? min((uint32_t)IBFT_QSPLIT_SIGS, shard_hi - base) : 0u;
+    uint32_t avail = min((uint32_t)IBFT_QSPLIT_SIGS, limit - base);
+    if (tid < IBFT_QSPLIT_SIGS) s_idx[tid] = tid < avail ? (list ? list[1 + base + tid] : base + tid) : 0xFFFFFFFFu;
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       uint32_t u = tid + k * 128;
       uint32_t row = u >> 3, col = u & 7;
       if (row < avail) {
-        uint4 v = __ldg(src + u);
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(items + s_idx[row]) + col);
         uint32_t* d = s_items + row * IBFT_ITEM_ROW_WORDS + col * 4;
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
       }
@@ -705,8 +929,8 @@ k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint
   const uint32_t S = IBFT_QSPLIT_SIGS;
   if (warp == 3) {
     // ---------------------------------------------------------------- helper warp: lane l serves signature l (l < 24)
-    const uint32_t i = lane, idx = base + i;
-    const bool mine = lane < S && idx < shard_hi;
+    const uint32_t i = lane, idx = lane < S ? s_idx[lane] : 0xFFFFFFFFu;
+    const bool mine = lane < S && idx != 0xFFFFFFFFu;
     ibft_sig_item it;
     resolved_item ri;
     sc rinv;
@@ -761,8 +985,8 @@ k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint
     return;
   }
   // ------------------------------------------------------------------ chain warps: four lanes per signature
-  const uint32_t q = tid >> 2, idx = base + q;
-  const bool active = idx < shard_hi;
+  const uint32_t q = tid >> 2, idx = s_idx[q];
+  const bool active = idx != 0xFFFFFFFFu;
   exec_quad ex;
   ex.role = (int)(tid & 3u);
   ex.mask = 0xFu << (tid & 28u);
@@ -832,7 +1056,7 @@ k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint
     if (ok) ok = member_and_vote(groups, n_groups, slots, n_slots, it.group, ri.signer, sink, ex.leader(), &vi, &vslot);
     if (ok && ex.leader()) learn_key(slots, vslot, vi, K);
     if (ex.leader()) {
-      if (status != nullptr) status[idx] = (uint8_t)st;
+      if (status != nullptr && list == nullptr) status[idx] = (uint8_t)st;
       if (recovered != nullptr) {
 #pragma unroll
         for (int k = 0; k < 20; k++) recovered[(size_t)idx * 20 + k] = addr[k];
@@ -1294,7 +1518,7 @@ struct lane {
   std::vector<ibft_group_desc> last_groups;
   pending_call pending;
   uint32_t* d_worklist = nullptr;  // key-registry path: [0] = count, [1..] = indices left to the recover pass
-  cudaEvent_t wl_ev[2] = {nullptr, nullptr};  // last use of each worklist (orders launches that arrive on different streams)
+  cudaEvent_t wl_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // last use of each worklist (orders launches that arrive on different streams)
   const uint8_t* dev_arena = nullptr;
   size_t dev_arena_len = 0;
 };
@@ -1380,7 +1604,8 @@ static int lane_alloc(ibft_engine* e, lane* L, uint32_t cap_items, size_t cap_ar
   size_t n = cap_items, words = (n + 31) / 32;
   CU(cudaMalloc(&L->d_items, n * sizeof(ibft_sig_item)));
   if (p.flags & IBFT_FLAG_KEY_CACHE)
-    CU(cudaMalloc(&L->d_worklist, 2 * (n + 1) * 4));  // two lists: consecutive chunks of a large host batch run on two streams
+    CU(cudaMalloc(&L->d_worklist, 4 * (n + 1) * 4));  // four lists: chunks of a large host batch alternate between two streams, the
+                                                      // four pieces of a mid-size round (latency path) run side by side
   CU(cudaMalloc(&L->d_arena, std::max<size_t>(cap_arena, 16)));
   CU(cudaMalloc(&L->d_bitmap, std::max<size_t>(words, 1) * 4));
   CU(cudaMalloc(&L->d_recovered, n * 20));
@@ -1425,6 +1650,7 @@ static int engine_alloc(ibft_engine* e) {
   CU(cudaFuncSetAttribute(k_recover<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * IBFT_RTAB_WORDS * 4));
 #if IBFT_WC > 0
   CU(cudaFuncSetAttribute(k_recover_split, cudaFuncAttributeMaxDynamicSharedMemorySize, IBFT_SPLIT_SMEM));
+  CU(cudaFuncSetAttribute(k_verify_split, cudaFuncAttributeMaxDynamicSharedMemorySize, IBFT_VSPLIT_SMEM));
 #endif
   CU(cudaFuncGetAttributes(&e->recover_attr, k_recover<IBFT_BLOCK>));
   {
@@ -1733,7 +1959,23 @@ static int launch_recover(ibft_engine* e, lane* L, const ibft_sig_item* d_items,
     uint32_t blocks = (cnt + IBFT_QSPLIT_SIGS - 1) / IBFT_QSPLIT_SIGS;
     CU(cudaMemsetAsync(d_bitmap + (lo >> 5), 0, (size_t)((hi + 31) / 32 - (lo >> 5)) * 4, st));  // verdict bits are OR-ed in
     k_recover_qsplit<<<blocks, 128, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                             e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
+                                             e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink, nullptr);
+  } else if (path == IBFT_PATH_SPLIT && (e->p.flags & IBFT_FLAG_KEY_CACHE) && d_recovered == nullptr && d_groups != nullptr &&
+             worklist != nullptr && cnt <= L->cap_items) {
+    // known-key latency path: verify against the learned keys, then recover whatever was not accepted (worklist; the second
+    // launch finds it empty -- and returns at once -- when every signature of the round verified)
+    uint32_t blocks = (cnt + IBFT_SPLIT_SIGS - 1) / IBFT_SPLIT_SIGS;
+    CU(cudaStreamWaitEvent(st, L->wl_ev[worklist_index & 3u], 0));
+    CU(cudaMemsetAsync(worklist, 0, 4, st));
+    k_verify_split<<<blocks, 32 * (IBFT_SPLIT_CHAINS + 1), IBFT_VSPLIT_SMEM, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
+                                                                              e->d_slots, e->p.max_table_slots, d_bitmap, d_status, e->d_ctable,
+                                                                              sink, worklist);
+    e->launches++;
+    CU(cudaGetLastError());
+    uint32_t blocks2 = (cnt + IBFT_QSPLIT_SIGS - 1) / IBFT_QSPLIT_SIGS;
+    k_recover_qsplit<<<blocks2, 128, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots, e->p.max_table_slots,
+                                              d_bitmap, nullptr, nullptr, e->d_ctable, sink, worklist);
+    CU(cudaEventRecord(L->wl_ev[worklist_index & 3u], st));
   } else if (path == IBFT_PATH_SPLIT) {
     uint32_t blocks = (cnt + IBFT_SPLIT_SIGS - 1) / IBFT_SPLIT_SIGS;
     k_recover_split<<<blocks, 32 * (IBFT_SPLIT_CHAINS + 1), IBFT_SPLIT_SMEM, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
@@ -1753,7 +1995,7 @@ static int launch_recover(ibft_engine* e, lane* L, const ibft_sig_item* d_items,
     // the worklist (dense second launch; the threads beyond the worklist's length leave at once)
     uint32_t blocks = (cnt + IBFT_BLOCK - 1) / IBFT_BLOCK;
     // device-resident callers may use different streams: launches sharing a worklist are ordered on the device
-    CU(cudaStreamWaitEvent(st, L->wl_ev[worklist_index & 1u], 0));
+    CU(cudaStreamWaitEvent(st, L->wl_ev[worklist_index & 3u], 0));
     CU(cudaMemsetAsync(worklist, 0, 4, st));
     k_verify_known<<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                                   e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink, worklist);
@@ -1762,7 +2004,7 @@ static int launch_recover(ibft_engine* e, lane* L, const ibft_sig_item* d_items,
     k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
                                                          e->d_slots, e->p.max_table_slots, d_bitmap, nullptr, nullptr, e->d_ctable, sink,
                                                          worklist);
-    CU(cudaEventRecord(L->wl_ev[worklist_index & 1u], st));
+    CU(cudaEventRecord(L->wl_ev[worklist_index & 3u], st));
   } else
 #endif
   if (cnt <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs
@@ -1896,7 +2138,7 @@ static int submit_locked(ibft_engine* e, lane* L, const ibft_sig_item* items, ui
       CU(cudaStreamWaitEvent(ls, L->lat_ev[4], 0));
       CU(cudaMemcpyAsync(L->d_items + lo, src, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, ls));
       rc = launch_recover(e, L, L->d_items, n, L->d_arena, arena_len, lo, hi, n_groups ? L->d_groups : nullptr, n_groups, L->d_bitmap,
-                          recovered_out ? L->d_recovered : nullptr, ls, L->d_status, IBFT_PATH_SPLIT, sink);
+                          recovered_out ? L->d_recovered : nullptr, ls, L->d_status, IBFT_PATH_SPLIT, sink, c);
       if (rc != IBFT_OK) return rc;
       CU(cudaEventRecord(L->lat_ev[c], ls));
       CU(cudaStreamWaitEvent(st, L->lat_ev[c], 0));

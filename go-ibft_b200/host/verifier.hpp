@@ -76,6 +76,7 @@ class GpuVerifier : public Verifier {
   uint32_t ingress_max_batch = 4096;
   uint32_t ingress_min_batch = 1;
   uint32_t ingress_linger_us = 0;
+  uint32_t ingress_second_min = 24;  // queue length from which a SECOND flush goes up while one is still on the device
 
   explicit GpuVerifier(const ibft_engine_params& params) {
     params_ = params;
@@ -355,7 +356,9 @@ class GpuVerifier : public Verifier {
     std::unique_lock<std::mutex> lk(ing_mu_);
     ing_queue_.push_back(req);
     while (!req->done) {
-      if (ing_leaders_ >= kMaxLeaders || ing_queue_.empty()) {
+      // the first leader starts at once; a second one (while a flush is already on the device) only for a queue worth a launch of
+      // its own -- otherwise the newcomers keep piling up behind the flush in flight and go up together when it returns
+      if (ing_queue_.empty() || ing_leaders_ >= kMaxLeaders || (ing_leaders_ == 1 && ing_queue_.size() < ingress_second_min)) {
         ing_cv_.wait(lk);
         continue;
       }

@@ -101,3 +101,53 @@ def test_rejected_verifications_fall_back_to_recovery_exactly():
         assert eng.refresh_key_tables() == 64      # the 16 late validators were learned in round 2
     finally:
         eng.close()
+
+
+def test_known_key_latency_path_on_a_10k_round():
+    """k_verify_split (+ k_recover_qsplit on the worklist): one mid-size round of KNOWN validators on the latency path.  Round 1
+    learns the keys through the recover kernels; round 2 -- same 10,000 seals incl. the 1 % adversarial ones, then fresh seals over
+    another proposal hash -- is verified against the keys.  Bitmap, quorum results and voted sets bit-exact with the recover path."""
+    d, items = load_fixture("config3.npz")
+    seal_group = list(d["groups"]).index("COMMIT_SEAL")
+    seals = np.ascontiguousarray(items[items["group"] == seal_group])
+    gold_bits = np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(items)][items["group"] == seal_group]
+    eng = make_engine(key_cache=True)
+    plain = make_engine()
+    try:
+        for e in (eng, plain):
+            e.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
+        groups = groups_for(eng, len(d["groups"]))
+        bm1, res1, _ = eng.verify_batch(seals, b"", groups)                 # recover path (k_recover_split pieces), keys learned
+        assert np.array_equal(np.unpackbits(bm1.view(np.uint8), bitorder="little")[: len(seals)], gold_bits)
+        assert eng.refresh_key_tables() == int(gold_bits.sum())
+        launches = eng.launch_count()
+        bm2, res2, _ = eng.verify_batch(seals, b"", groups)                 # known-key latency path
+        assert np.array_equal(bm2, bm1) and res1.tobytes() == res2.tobytes()
+        # four pieces x (k_verify_split + worklist k_recover_qsplit) + k_quorum_reduce; no table rebuild
+        assert eng.launch_count() - launches == 9
+        bmp, resp, _ = plain.verify_batch(seals, b"", groups)
+        assert np.array_equal(bm2, bmp) and res2.tobytes() == resp.tobytes()
+        for g in range(len(groups)):
+            assert np.array_equal(eng.voted_bitmap(g, len(d["addrs"])), plain.voted_bitmap(g, len(d["addrs"])))
+        # a fresh round: new proposal hash, every validator signs; one signature corrupted, one misattributed
+        vs_keys = [wl.privkey(2, i) for i in range(0, 10_000, 97)]          # a subset is enough for the oracle-signed fresh items
+        ph = co.keccak256(b"next block")
+        fresh = []
+        for j, k in enumerate(vs_keys):
+            i = 97 * j
+            sig = wl.sign(k, wl.seal_digest(ph))
+            signer = bytes(d["addrs"][i])
+            if j == 5:
+                sig = sig[:40] + bytes([sig[40] ^ 2]) + sig[41:]           # verification rejects -> worklist -> recover says invalid
+            if j == 9:
+                signer = bytes(d["addrs"][i + 1])                           # valid signature of ANOTHER validator's key
+            fresh.append(wl.make_item(sig, signer, 2, ph, seal_group))
+        fresh = np.concatenate(fresh * 80)[:8000]                           # 8,000 tuples: the chain + helper kernel's range
+        a, ra, _ = eng.verify_batch(fresh, b"", groups)
+        b, rb, _ = plain.verify_batch(fresh, b"", groups)
+        assert np.array_equal(a, b) and ra.tobytes() == rb.tobytes()
+        want = co.verify_batch(fresh, b"", tables=[d["addrs"]], group_table=[0] * len(groups), n_threads=8)
+        assert np.array_equal(a, want)
+    finally:
+        eng.close()
+        plain.close()
