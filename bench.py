@@ -163,7 +163,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "verifies/s", "cores": cores, "kind": "port",
                              "sample": f"{sample_n} items of the config-3 batch per step (bounded sample), C oracle, {cores} threads"},
             "e2e": {"value": v, "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def _item_dtype():
@@ -294,11 +294,12 @@ def wire_frames_from_payload_items(items, arena):
 
 def ingress_leg(local_rank, n_threads=64):
     """n_threads threads of SINGLE-message IsValidValidator calls through the reference-facing verifier (the call pattern of
-    core/ibft.go:1101-1128): the coalescer turns them into a few device batches.  Config 2's 2,000 PREPARE + COMMIT sender messages,
-    each asked once per verifier, 8 verifiers (the verdict cache would answer repeats)."""
+    core/ibft.go:1101-1128): the coalescer turns them into a few device batches.  Every message is asked once per verifier (the
+    verdict cache would answer repeats); several verifiers in turn."""
     import importlib
     host = importlib.import_module("go-ibft_b200.host")
-    d2 = np.load(os.path.join(ROOT, "tests", "golden", "config2.npz"))
+    # 64 callers: config 2's 2,000 sender messages; more callers: config 3's 10,000 COMMIT messages (each caller needs a few)
+    d2 = np.load(os.path.join(ROOT, "tests", "golden", "config2.npz" if n_threads <= 64 else "config3.npz"))
     import ibft_b200 as ib
     items = np.ascontiguousarray(d2["items"]).view(ib.ITEM_DTYPE).reshape(-1)
     sel = items["kind"] == ib.KIND_PAYLOAD
@@ -310,15 +311,15 @@ def ingress_leg(local_rank, n_threads=64):
         off = int(it["payload_off"])
         vlen = a[off + 1]
         tuples["signer"][k] = np.frombuffer(a[off + 4 + vlen: off + 24 + vlen], np.uint8)
-    e0 = ib.Engine(device=local_rank, max_items=1 << 12, max_payload_bytes=1 << 22, max_groups=8, max_table_slots=2, max_validators=4096)
+    e0 = ib.Engine(device=local_rank, max_items=1 << 14, max_payload_bytes=1 << 22, max_groups=8, max_table_slots=2, max_validators=16384)
     e0.set_validators(0, int(d2["meta"][2]), d2["addrs"], d2["powers"])
     bulk, _, _ = e0.verify_batch(tuples, d2["arena"], e0.groups(len(d2["groups"])))
     e0.close()
     gold = np.unpackbits(bulk.view(np.uint8), bitorder="little")[: len(tuples)]
     addrs = [bytes(x) for x in d2["addrs"]]
     lat, elapsed, calls, asked, mismatches = [], 0.0, 0, 0, 0
-    for _ in range(8):
-        c = host.HostContext("gpu", {}, b"", host.EngineParams(local_rank, 1 << 14, 1 << 22, 32, 8, 4096, 0))
+    for _ in range(8 if n_threads <= 64 else 3):
+        c = host.HostContext("gpu", {}, b"", host.EngineParams(local_rank, 1 << 14, 1 << 22, 32, 8, 16384, 0))
         c.set_validators(int(d2["meta"][2]), addrs, None)
         v, l, us = c.ingress_storm(frames, n_threads)
         mismatches += int((v != gold).sum())
@@ -450,7 +451,28 @@ def config4_legs(ib, local_rank, stream):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL's version banner when the box sets
+    NCCL_DEBUG=VERSION); NCCL's logging environment is left alone -- instead file descriptor 1 is pointed at stderr for the
+    duration of the run and the JSON line goes to the saved original descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -630,7 +652,7 @@ def main():
         return
 
     if args.skip_extras:
-        print(json.dumps({"metric": "secp256k1_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": n_gpus, "steps": args.steps,
+        emit(({"metric": "secp256k1_verifies_per_sec", "value": value, "unit": "verifies/s", "n_gpus": n_gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "u32 (256-bit modular integer)", "data": "synthetic", "config": workload_config(n_gpus),
                           "clocks": sampler.summary(), "gpu_launches": int(launches),
@@ -802,6 +824,10 @@ def main():
                      "frac": achieved / imad_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per k_recover launch (ncu)",
                      "traffic_source": traffic_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_VERIFY * n_local,
                      "executed_per_ncu": executed,
+                     "issue_active_pct": (executed or {}).get("issue_active_pct"),
+                     "fmaheavy_pipe_pct": (executed or {}).get("fmaheavy_pipe_cycles_active_pct"),
+                     "binding_pipe_note": "from the committed ncu --set full capture of this kernel: the FMA-heavy pipe (IMAD / IMAD.WIDE; an IMAD.WIDE holds it 4 "
+                                          "cycles per warp instruction) is the pipe that binds -- issue-active is low BECAUSE that pipe is busy",
                      "note": "frac uses SURVEY 8d's canonical-algorithm count (5.0e5 IMAD-class instr/verify); the kernel executes fewer "
                              "multiply instructions than that (GLV, combined generator table, safegcd, fused IMAD.WIDE), so frac can "
                              "exceed 1; executed_per_ncu gives the real instruction counts",
@@ -852,7 +878,7 @@ def main():
             line["ingress"]["cpu_oracle"] = {"single_call_us": 1e6 / line["cpu_baseline"]["single_thread"],
                                              "all_cores_msgs_per_s": line["cpu_baseline"]["value"], "cores": line["cpu_baseline"]["cores"]}
         line["config4"] = config4_legs(ib, local_rank, stream)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

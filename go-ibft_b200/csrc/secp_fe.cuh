@@ -579,7 +579,32 @@ IBFT_HD fe fe_mul_i(const fe& a, const fe& b) {
   mul_wide_8x8(R, a.v, b.v);
   return fe_reduce512(R);
 }
+#if defined(IBFT_BLIND_COPY) && defined(__CUDACC__)
+__constant__ uint32_t ibft_c_zero;
+#endif
+#if defined(IBFT_BLIND_COPY) && defined(__CUDA_ARCH__)
+// EXPERIMENT (tools/quick_bench.py variants): the copies that marshal by-value operands into the out-of-line multiplier's
+// argument registers are emitted by ptxas as IMAD.MOV -- on the FMA-heavy pipe, which is the one that binds (80 % busy).  Passing
+// every operand through "x ^ c" with c a __constant__ word that happens to be 0 turns the copy into a LOP3 (ALU pipe, 41 % busy)
+// that ptxas cannot fold away and can place straight into the argument register.
+__device__ __forceinline__ fe fe_blind(const fe& a) {
+  fe r;
+  const uint32_t z = ibft_c_zero;
+#pragma unroll
+  for (int i = 0; i < 8; i++) asm("xor.b32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(z));
+  return r;
+}
+__device__ __noinline__ fe fe_mul_o(fe a, fe b) { return fe_mul_i(a, b); }
+__device__ __forceinline__ fe fe_mul(const fe& a, const fe& b) {
+#if IBFT_BLIND_COPY >= 2
+  return fe_blind(fe_mul_o(fe_blind(a), fe_blind(b)));
+#else
+  return fe_mul_o(fe_blind(a), fe_blind(b));
+#endif
+}
+#else
 IBFT_FN fe fe_mul(fe a, fe b) { return fe_mul_i(a, b); }
+#endif
 
 #if IBFT_PTX
 // shorter carry chains for the squaring triangle
@@ -700,7 +725,18 @@ IBFT_HD fe fe_sqr_i(const fe& a) {
   sqr_wide_8(R, a.v);
   return fe_reduce512(R);
 }
+#if defined(IBFT_BLIND_COPY) && defined(__CUDA_ARCH__)
+__device__ __noinline__ fe fe_sqr_o(fe a) { return fe_sqr_i(a); }
+__device__ __forceinline__ fe fe_sqr(const fe& a) {
+#if IBFT_BLIND_COPY >= 2
+  return fe_blind(fe_sqr_o(fe_blind(a)));
+#else
+  return fe_sqr_o(fe_blind(a));
+#endif
+}
+#else
 IBFT_FN fe fe_sqr(fe a) { return fe_sqr_i(a); }
+#endif
 
 // a^(2^n): out of line, with the squarer inlined in the loop (no per-iteration call marshalling)
 IBFT_FN fe fe_sqrn(fe a, int n) {

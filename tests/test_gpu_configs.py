@@ -250,3 +250,31 @@ def test_config4_n1000_end_to_end_through_wire_codec_and_host_mirror(raw_frames)
     assert c.gpu_device_calls() - calls0 <= 3
     assert c.gpu_frames_handed_back() == 0              # every frame was canonical: nothing was re-marshalled on the host
     c.close()
+
+
+def test_sharded_verifier_pipeline_single_rank(big_engine):
+    """go-ibft_b200/sharding.py ShardedVerifier (the per-rank pipeline bench.py's strong-scaling legs run under torchrun) at
+    world = 1: rebased shard, H2D, kernels, merge, D2H -- bitmap and quorum results equal to the config-5 pin; and the shard
+    rebasing itself for several (world, rank) against the pin's bitmap words."""
+    w, pin = wl.load_full("config5")
+    e = big_engine
+    for k in range(16):
+        e.set_validators(k, w["heights"][k], w["tables"][k], w["powers"])
+    groups = e.groups(w["n_groups"], slot=w["group_table"])
+    items, arena = w["items"], np.frombuffer(w["arena"], np.uint8)
+    n = len(items)
+    li, la = sharding.rebase_shard(items, arena, 0, n)
+    sv = sharding.ShardedVerifier(e, n, groups, 1, 0, li, la, torch.cuda.current_stream())
+    res, bm = sv.run()
+    assert np.array_equal(bm, pin["bitmap"])
+    _results_equal(res, pin["results"])
+    res2, bm2 = sv.run()                                   # the pipeline is re-runnable (buffers are reused)
+    assert np.array_equal(bm2, bm) and res2.tobytes() == res.tobytes()
+    # a rank's rebased shard verifies to exactly its slice of the bitmap
+    for world, rank in ((2, 1), (8, 5), (8, 7)):
+        lo, hi = sharding.shard_bounds(n, world, rank)
+        li, la = sharding.rebase_shard(items, arena, lo, hi)
+        assert la.size < arena.size
+        bitmap, _, _ = e.verify_batch(li, la, groups)
+        assert np.array_equal(bitmap, pin["bitmap"][lo // 32: (hi + 31) // 32])
+    e.bind_groups(None)
