@@ -1947,7 +1947,11 @@ static int launch_recover(ibft_engine* e, lane* L, const ibft_sig_item* d_items,
   int path = forced_path != IBFT_PATH_AUTO ? forced_path : e->recover_path.load();
   if (path == IBFT_PATH_AUTO) {
 #if IBFT_WC > 0
-    if (cnt <= (uint32_t)e->sm_count * 2u * IBFT_QSPLIT_SIGS) path = IBFT_PATH_QSPLIT;
+    // long payloads (ROUND_CHANGE messages with their certificates: up to 909 KB of signed bytes each): the helper warp of the
+    // latency kernels hashes for three (or 24) signatures one after the other, which serialises the sponges that dominate such a
+    // batch -- one thread per signature hashes them all in parallel (config 4, 10,000 x 909 KB: 156 ms -> see DESIGN.md §6)
+    if (arena_len / cnt > 256) path = IBFT_PATH_THREAD;
+    else if (cnt <= (uint32_t)e->sm_count * 2u * IBFT_QSPLIT_SIGS) path = IBFT_PATH_QSPLIT;
     else if (cnt <= (uint32_t)e->sm_count * 2u * IBFT_SPLIT_SIGS) path = IBFT_PATH_SPLIT;
     else path = IBFT_PATH_THREAD;
 #else
@@ -2118,7 +2122,7 @@ static int submit_locked(ibft_engine* e, lane* L, const ibft_sig_item* items, ui
   // pieces, each with its own stream -- stage, copy and launch piece k while piece k+1 is being staged; the four kernels
   // (<= 37 CTAs each) run side by side on different SMs and the main stream joins them before the quorum kernels.
   const bool lat_pieces = e->recover_path.load() == IBFT_PATH_AUTO && n > (uint32_t)e->sm_count * 2u * IBFT_QSPLIT_SIGS &&
-                          n <= (uint32_t)e->sm_count * IBFT_SPLIT_SIGS;
+                          n <= (uint32_t)e->sm_count * IBFT_SPLIT_SIGS && arena_len / n <= 256;
   if (lat_pieces) {
     bool pinned = false;
     cudaPointerAttributes pa;
