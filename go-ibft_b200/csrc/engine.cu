@@ -421,7 +421,9 @@ k_recover_quad(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
 // ------------------------------------------------------------------------------------------------------------
 #define IBFT_SPLIT_CHAINS 3
 #define IBFT_SPLIT_SIGS (32 * IBFT_SPLIT_CHAINS)
-#define IBFT_SLOT_WORDS 27  // [0..4] |k1|, [5..9] |k2| of u2, [10] flags, [11..18] y then gx, [19..26] gy ; see below
+#define IBFT_SLOT_WORDS 28  // [0..4] |k1|, [5..9] |k2| of u2, [10] phase-1 flags, [11..18] y then gx, [19..26] gy, [27] phase-2 flags
+                            // (the two phases have their own flag words: the helper may post phase 2 before a chain warp has
+                            // read phase 1 -- same bits either way, but two words keep the hand-off free of unordered accesses)
 #define IBFT_SPLIT_SMEM ((IBFT_SPLIT_SIGS * (IBFT_ITEM_ROW_WORDS + IBFT_RTAB_WORDS + IBFT_SLOT_WORDS + 8)) * 4)
 #define IBFT_SF_VALID 1u   // phase 1: (r, s, v) in range, digits posted
 #define IBFT_SF_NEG0 2u
@@ -575,7 +577,7 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
             }
           }
         }
-        s_slot[10 * IBFT_SPLIT_SIGS + i] = flags;
+        s_slot[27 * IBFT_SPLIT_SIGS + i] = flags;
       }
       __threadfence_block();
       named_bar_arrive(1 + IBFT_SPLIT_CHAINS + p, 64);
@@ -629,7 +631,7 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
   for (int k = 0; k < 20; k++) addr[k] = 0;
   bool ok = false;
   if (go) {
-    uint32_t flags = s_slot[10 * IBFT_SPLIT_SIGS + i];
+    uint32_t flags = s_slot[27 * IBFT_SPLIT_SIGS + i];
     if (flags & IBFT_SF_ROOT) {
       fe y, gx, gy;
 #pragma unroll
@@ -674,7 +676,7 @@ k_recover_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8
 // valid (malformed, out of range, unknown group, signer not in the set) are settled here.  A round in which every signature
 // verifies (the normal case of consensus) never runs a second chain.
 // ------------------------------------------------------------------------------------------------------------
-#define IBFT_VSLOT_WORDS 28   // IBFT_SLOT_WORDS + [27] validator index of the signer
+#define IBFT_VSLOT_WORDS 29   // [0..26] as IBFT_SLOT_WORDS, [27] validator index | slot << 16 of the signer, [28] phase-2 flags
 #define IBFT_VSPLIT_SMEM ((IBFT_SPLIT_SIGS * (IBFT_ITEM_ROW_WORDS + IBFT_VSLOT_WORDS)) * 4)
 #define IBFT_VF_VALID 1u      // digits of u2 posted: the chain runs
 #define IBFT_VF_NEG0 2u
@@ -812,13 +814,13 @@ k_verify_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
         fe gx = fe_zero(), gy = fe_zero();
         bool g_inf = false;
         known_helper_u1g(ri, w, G, g_inf, gx, gy);
-        uint32_t flags = s_slot[10 * S + i] | IBFT_VF_GREADY | (g_inf ? IBFT_VF_GINF : 0u);
+        uint32_t flags = IBFT_VF_GREADY | (g_inf ? IBFT_VF_GINF : 0u);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           s_slot[(11 + k) * S + i] = gx.v[k];
           s_slot[(19 + k) * S + i] = gy.v[k];
         }
-        s_slot[10 * S + i] = flags;
+        s_slot[28 * S + i] = flags;
       }
       __threadfence_block();
       named_bar_arrive(1 + IBFT_SPLIT_CHAINS + p, 64);
@@ -853,7 +855,7 @@ k_verify_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
   named_bar_sync(1 + IBFT_SPLIT_CHAINS + warp, 64);  // u1*G is posted
   bool ok = false;
   if (flags & IBFT_VF_VALID) {
-    const uint32_t f2 = s_slot[10 * S + i];
+    const uint32_t f2 = s_slot[28 * S + i];
     fe gx, gy;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -978,7 +980,7 @@ k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint
           }
         }
       }
-      s_slot[10 * S + i] = flags;
+      s_slot[27 * S + i] = flags;
     }
     __threadfence_block();
     named_bar_arrive(4, 64); named_bar_arrive(5, 64); named_bar_arrive(6, 64);
@@ -1036,7 +1038,7 @@ k_recover_qsplit(const ibft_sig_item* __restrict__ items, uint32_t n, const uint
   for (int k = 0; k < 20; k++) addr[k] = 0;
   bool ok = false;
   if (go) {
-    uint32_t flags = s_slot[10 * S + q];
+    uint32_t flags = s_slot[27 * S + q];
     if (flags & IBFT_SF_ROOT) {
       fe y, gx, gy;
 #pragma unroll

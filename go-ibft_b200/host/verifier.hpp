@@ -267,6 +267,7 @@ class GpuVerifier : public Verifier {
     Pending p;
     bool done = false;
     bool result = false;
+    std::condition_variable cv;  // per request: a finished flush wakes its own callers only
   };
   mutable std::mutex state_mu_;  // cache_, hash_cache_, slot_height_, current_height_, epoch_, error_  (never held across a device call)
   ibft_engine_params params_{};
@@ -280,7 +281,6 @@ class GpuVerifier : public Verifier {
   std::atomic<uint64_t> device_calls_{0}, items_verified_{0}, frames_handed_back_{0}, ingress_requests_{0}, ingress_flushes_{0};
   // ingress coalescer
   std::mutex ing_mu_;
-  std::condition_variable ing_cv_;
   std::deque<std::shared_ptr<Req>> ing_queue_;
   int ing_leaders_ = 0;
   static constexpr int kMaxLeaders = 2;  // two flushes may be on the device at once (the engine has two lanes)
@@ -359,7 +359,7 @@ class GpuVerifier : public Verifier {
       // the first leader starts at once; a second one (while a flush is already on the device) only for a queue worth a launch of
       // its own -- otherwise the newcomers keep piling up behind the flush in flight and go up together when it returns
       if (ing_queue_.empty() || ing_leaders_ >= kMaxLeaders || (ing_leaders_ == 1 && ing_queue_.size() < ingress_second_min)) {
-        ing_cv_.wait(lk);
+        req->cv.wait(lk);  // woken by the leader that decided this request, or by a finishing leader handing the lead over
         continue;
       }
       ing_leaders_++;
@@ -390,9 +390,10 @@ class GpuVerifier : public Verifier {
       for (size_t i = 0; i < taken.size(); i++) {
         taken[i]->result = verdicts[slot_of[i]] == 1;  // no verdict (launch failure) => false, never true
         taken[i]->done = true;
+        if (taken[i] != req) taken[i]->cv.notify_one();  // only the callers of THIS batch are woken (no thundering herd)
       }
       ing_leaders_--;
-      ing_cv_.notify_all();
+      if (!ing_queue_.empty()) ing_queue_.front()->cv.notify_one();  // somebody is waiting: hand the lead over
     }
     return req->result;
   }

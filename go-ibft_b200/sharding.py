@@ -90,6 +90,10 @@ class ShardedVerifier:
         self.per = shard_words(n_global, world)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.stream = stream or torch.cuda.current_stream()
+        if self.stream.cuda_stream == 0:
+            # the C ABI reads a NULL stream as "the engine's own stream": the legacy default stream cannot be named through it, and
+            # the engine's kernels would then run unordered with torch's copies -- use a real stream
+            self.stream = torch.cuda.Stream()
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()  # noqa: E731
         self.h_items = pin(local_items) if len(local_items) else torch.zeros(0, dtype=torch.uint8).pin_memory()
         self.h_arena = pin(local_arena) if len(local_arena) else torch.zeros(0, dtype=torch.uint8).pin_memory()

@@ -61,3 +61,67 @@ def test_two_rank_gloo_bitmap_allgather_matches_unsharded(tmp_path, n_items):
     for r in range(2):
         got = np.load(os.path.join(str(tmp_path), f"bitmap_{r}.npy"))
         assert np.array_equal(got, want)     # every rank holds the complete, identical bitmap
+
+
+def _worker_config5(rank, world, port, out_dir):
+    """Strong-scaling pipeline of go-ibft_b200/sharding.py on CPU: every rank holds ONLY its rebased shard of the config-5 backlog,
+    verifies it (oracle verdicts stand in for the kernels), marks its votes, and ONE all-gather carries (bitmap words | partial voted
+    sets | valid counts); every rank then merges and reduces -- same layout as ShardedVerifier / ibft_quorum_merge_device."""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import workloads as wl
+    from oracle import coracle as co
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w, pin = wl.load_full("config5")
+    items, arena = w["items"], np.frombuffer(w["arena"], np.uint8)
+    n = len(items)
+    lo, hi = sharding.shard_bounds(n, world, rank)
+    local, local_arena = sharding.rebase_shard(items, arena, lo, hi)
+    assert local_arena.size < arena.size * 0.8                       # the rank holds its own payload bytes only (the seals at the tail carry none)
+    bm = co.verify_batch(local, local_arena.tobytes(), tables=w["tables"], group_table=w["group_table"], n_threads=4)
+    per = sharding.shard_words(n, world)
+    n_val = len(w["tables"][0])
+    vw = (n_val + 31) // 32
+    ng = w["n_groups"]
+    part = np.zeros(per + ng * vw + ng, dtype=np.uint32)            # bitmap words | voted sets | valid counts
+    part[: len(bm)] = bm
+    bits = np.unpackbits(bm.view(np.uint8), bitorder="little")[: hi - lo]
+    index = [{bytes(a): i for i, a in enumerate(t)} for t in w["tables"]]
+    for i in np.nonzero(bits)[0]:
+        g = int(local["group"][i])
+        v = index[w["group_table"][g]][bytes(local["signer"][i])]
+        part[per + g * vw + (v >> 5)] |= np.uint32(1 << (v & 31))
+        part[per + ng * vw + g] += 1
+    gathered = torch.empty(world * len(part), dtype=torch.int32)
+    dist.all_gather_into_tensor(gathered, torch.from_numpy(part.view(np.int32)))
+    parts = gathered.numpy().view(np.uint32).reshape(world, -1)
+    bitmap = parts[:, :per].reshape(-1)[: (n + 31) // 32]
+    voted = np.bitwise_or.reduce(parts[:, per: per + ng * vw], axis=0).reshape(ng, vw)
+    counts = parts[:, per + ng * vw:].sum(axis=0)
+    pw = [int.from_bytes(bytes(p), "big") for p in w["powers"]]
+    quorum = 2 * sum(pw) // 3 + 1
+    res = np.zeros((ng, 3), dtype=np.uint64)
+    for g in range(ng):
+        vs = np.nonzero(np.unpackbits(voted[g].view(np.uint8), bitorder="little")[:n_val])[0]
+        res[g] = (counts[g], len(vs), int(sum(pw[v] for v in vs) >= quorum))
+    np.savez(os.path.join(out_dir, f"c5_{rank}.npz"), bitmap=bitmap, res=res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_config5_strong_scaling_pipeline(tmp_path):
+    import sys
+    sys.path.insert(0, HERE)
+    import workloads as wl
+    w, pin = wl.load_full("config5")          # (also warms the cache the workers read)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker_config5, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        got = np.load(os.path.join(str(tmp_path), f"c5_{r}.npz"))
+        assert np.array_equal(got["bitmap"], pin["bitmap"])
+        assert np.array_equal(got["res"], pin["results"][:, :3])
