@@ -84,6 +84,8 @@ def load_host() -> ctypes.CDLL:
         lib.ibfthost_has_quorum_voted.argtypes = [c_void_p, c_void_p, c_uint32]
         lib.ibfthost_reencode.argtypes = [c_char_p, c_size_t, c_int, c_char_p, c_size_t]
         lib.ibfthost_reencode.restype = c_size_t
+        lib.ibfthost_remarshal.argtypes = [c_char_p, c_size_t, c_int, c_char_p, c_size_t]
+        lib.ibfthost_remarshal.restype = c_size_t
         lib.ibfthost_is_valid_committed_seal.argtypes = [c_void_p, c_char_p, c_size_t, c_char_p, c_size_t, c_char_p, c_size_t]
         lib.ibfthost_is_valid_proposal_hash.argtypes = [c_void_p, c_char_p, c_size_t, c_uint64, c_int, c_char_p, c_size_t]
         _LIB = lib
@@ -100,6 +102,18 @@ def reencode(wire: bytes, with_signature: bool = True):
     n = lib.ibfthost_reencode(wire, len(wire), int(with_signature), buf, len(buf))
     if n == ctypes.c_size_t(-1).value:
         return None
+    return buf.raw[:n]
+
+
+def remarshal(wire: bytes, with_signature: bool = True):
+    """protobuf-go's Marshal(Unmarshal(wire)) restated by the C++ host codec (unknown fields kept, duplicates merged); None on a
+    parse error.  with_signature=False: PayloadNoSig of a message that arrived as `wire`."""
+    lib = load_host()
+    n = lib.ibfthost_remarshal(wire, len(wire), int(with_signature), None, 0)
+    if n == ctypes.c_size_t(-1).value:
+        return None
+    buf = ctypes.create_string_buffer(max(1, n))
+    lib.ibfthost_remarshal(wire, len(wire), int(with_signature), buf, n)
     return buf.raw[:n]
 
 

@@ -241,6 +241,16 @@ size_t ibfthost_reencode(const uint8_t* wire, size_t len, int with_signature, ui
   return e.size();
 }
 
+// PayloadNoSig of a frame as protobuf-go would produce it (Unmarshal, Signature = nil, Marshal): returns the length (or
+// (size_t)-1 on a parse error) and writes the bytes when the buffer is large enough
+size_t ibfthost_remarshal(const uint8_t* wire, size_t len, int with_signature, uint8_t* out, size_t cap) {
+  try {
+    Bytes e = remarshal(wire, len, with_signature != 0);
+    if (out && cap >= e.size()) memcpy(out, e.data(), e.size());
+    return e.size();
+  } catch (const DecodeError&) { return (size_t)-1; }
+}
+
 // InsertProposal-side check (core/backend.go:78-81): n seals = n signers (20 bytes each) + n signatures (65 bytes each) over one
 // proposal hash; returns 1 when the valid seals' distinct signers carry quorum, and the number of valid seals in *n_valid.
 int ibfthost_verify_committed_seals(ibfthost_ctx* c, const uint8_t* hash, size_t hlen, const uint8_t* signers, const uint8_t* sigs,

@@ -8,6 +8,7 @@
 // bytes produced from the reference's own descriptor (tests/golden/proto_wire.json).
 #pragma once
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -201,9 +202,10 @@ struct Reader {
     uint64_t key = varint();
     num = (uint32_t)(key >> 3);
     wt = (uint32_t)(key & 7);
-    if (num == 0) throw DecodeError("field number 0");
+    if (num == 0 || (key >> 3) > 0x1FFFFFFFull) throw DecodeError("invalid field number");
     switch (wt) {
       case 0: val = varint(); break;
+      case 3: skip_group(num, 0); break;  // a (deprecated) group: an unknown field to every message of this schema
       case 2: {
         uint64_t n = varint();
         if (n > (uint64_t)(end - p)) throw DecodeError("truncated bytes");
@@ -224,44 +226,41 @@ struct Reader {
     }
     return true;
   }
+  // moves past the END_GROUP tag that matches `number` (nested groups allowed)
+  void skip_group(uint32_t number, int gdepth) {
+    if (gdepth > kMaxDepth) throw DecodeError("group nesting too deep");
+    for (;;) {
+      uint64_t key = varint();
+      uint32_t num = (uint32_t)(key >> 3), wt = (uint32_t)(key & 7);
+      if (num == 0 || (key >> 3) > 0x1FFFFFFFull) throw DecodeError("invalid field number");
+      if (wt == 4) {
+        if (num != number) throw DecodeError("mismatched end group");
+        return;
+      }
+      switch (wt) {
+        case 0: varint(); break;
+        case 1: if (end - p < 8) throw DecodeError("truncated fixed64"); p += 8; break;
+        case 5: if (end - p < 4) throw DecodeError("truncated fixed32"); p += 4; break;
+        case 2: {
+          uint64_t n = varint();
+          if (n > (uint64_t)(end - p)) throw DecodeError("truncated bytes");
+          p += n;
+          break;
+        }
+        case 3: skip_group(num, gdepth + 1); break;
+        default: throw DecodeError("invalid wire type");
+      }
+    }
+  }
   Bytes bytes() const { return Bytes((const char*)p, (size_t)(end - p)); }
 };
 }  // namespace wire
 
-MessagePtr decode_message(wire::Reader r);
-
-inline std::shared_ptr<Proposal> decode_proposal(wire::Reader r) {
-  auto p = std::make_shared<Proposal>();
-  uint32_t num, wt;
-  uint64_t val;
-  wire::Reader sub{nullptr, nullptr, 0, nullptr};
-  while (r.next(num, wt, val, sub)) {
-    if (num == 1 && wt == 2) p->raw_proposal = sub.bytes();
-    else if (num == 2 && wt == 0) p->round = val;
-  }
-  return p;
-}
-inline std::shared_ptr<PreparedCertificate> decode_pc(wire::Reader r) {
-  auto pc = std::make_shared<PreparedCertificate>();
-  uint32_t num, wt;
-  uint64_t val;
-  wire::Reader sub{nullptr, nullptr, 0, nullptr};
-  while (r.next(num, wt, val, sub)) {
-    if (num == 1 && wt == 2) pc->proposal_message = decode_message(sub);
-    else if (num == 2 && wt == 2) pc->prepare_messages.push_back(decode_message(sub));
-  }
-  return pc;
-}
-inline std::shared_ptr<RoundChangeCertificate> decode_rcc(wire::Reader r) {
-  auto c = std::make_shared<RoundChangeCertificate>();
-  uint32_t num, wt;
-  uint64_t val;
-  wire::Reader sub{nullptr, nullptr, 0, nullptr};
-  while (r.next(num, wt, val, sub))
-    if (num == 1 && wt == 2) c->round_change_messages.push_back(decode_message(sub));
-  return c;
-}
-
+// The typed decoders MERGE the way protobuf-go's Unmarshal does, so that the model a frame decodes to is the one a Go node holds:
+// a singular scalar / bytes field that appears again overwrites, a singular sub-message that appears again is merged field by
+// field, repeated sub-messages accumulate, a different oneof member replaces the one set before (the same member again merges),
+// and a known field with the wrong wire type is an unknown field (ignored by the model; kept by remarshal() below).
+void decode_message_into(IbftMessage& m, wire::Reader r);
 inline MessagePtr decode_message(wire::Reader r) {
   auto m = std::make_shared<IbftMessage>();
   if (r.root && *r.root) {
@@ -269,20 +268,74 @@ inline MessagePtr decode_message(wire::Reader r) {
     m->wire_off = (uint32_t)(r.p - (const uint8_t*)(*r.root)->data());
     m->wire_len = (uint32_t)(r.end - r.p);
   }
+  decode_message_into(*m, r);
+  return m;
+}
+inline void decode_proposal_into(Proposal& p, wire::Reader r) {
   uint32_t num, wt;
   uint64_t val;
   wire::Reader sub{nullptr, nullptr, 0, nullptr};
   while (r.next(num, wt, val, sub)) {
+    if (num == 1 && wt == 2) p.raw_proposal = sub.bytes();
+    else if (num == 2 && wt == 0) p.round = val;
+  }
+}
+inline void merge_message_field(MessagePtr& slot, wire::Reader sub) {
+  if (!slot) {
+    slot = decode_message(sub);
+  } else {
+    decode_message_into(*slot, sub);
+    slot->root_wire = nullptr;  // assembled from two occurrences: there is no single span of the frame that IS this message
+    slot->wire_off = slot->wire_len = 0;
+  }
+}
+inline void decode_pc_into(PreparedCertificate& pc, wire::Reader r) {
+  uint32_t num, wt;
+  uint64_t val;
+  wire::Reader sub{nullptr, nullptr, 0, nullptr};
+  while (r.next(num, wt, val, sub)) {
+    if (num == 1 && wt == 2) merge_message_field(pc.proposal_message, sub);
+    else if (num == 2 && wt == 2) pc.prepare_messages.push_back(decode_message(sub));
+  }
+}
+inline std::shared_ptr<PreparedCertificate> decode_pc(wire::Reader r) {
+  auto pc = std::make_shared<PreparedCertificate>();
+  decode_pc_into(*pc, r);
+  return pc;
+}
+inline void decode_rcc_into(RoundChangeCertificate& c, wire::Reader r) {
+  uint32_t num, wt;
+  uint64_t val;
+  wire::Reader sub{nullptr, nullptr, 0, nullptr};
+  while (r.next(num, wt, val, sub))
+    if (num == 1 && wt == 2) c.round_change_messages.push_back(decode_message(sub));
+}
+
+inline void decode_message_into(IbftMessage& mm, wire::Reader r) {
+  IbftMessage* m = &mm;
+  uint32_t num, wt;
+  uint64_t val;
+  wire::Reader sub{nullptr, nullptr, 0, nullptr};
+  // a oneof member that differs from the one currently set starts from scratch; the same member again merges
+  auto select = [&](PayloadKind k) {
+    if (m->payload_kind != k) {
+      m->preprepare = PrePrepareMessage();
+      m->prepare = PrepareMessage();
+      m->commit = CommitMessage();
+      m->round_change = RoundChangeMessage();
+      m->payload_kind = k;
+    }
+  };
+  while (r.next(num, wt, val, sub)) {
+    uint32_t n2, w2;
+    uint64_t v2;
+    wire::Reader s2{nullptr, nullptr, 0, nullptr};
     if (num == 1 && wt == 2) {
-      auto v = std::make_shared<View>();
-      uint32_t n2, w2;
-      uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0, nullptr};
+      if (!m->view) m->view = std::make_shared<View>();
       while (sub.next(n2, w2, v2, s2)) {
-        if (n2 == 1 && w2 == 0) v->height = v2;
-        else if (n2 == 2 && w2 == 0) v->round = v2;
+        if (n2 == 1 && w2 == 0) m->view->height = v2;
+        else if (n2 == 2 && w2 == 0) m->view->round = v2;
       }
-      m->view = v;
     } else if (num == 2 && wt == 2) {
       m->from = sub.bytes();
     } else if (num == 3 && wt == 2) {
@@ -290,53 +343,163 @@ inline MessagePtr decode_message(wire::Reader r) {
     } else if (num == 4 && wt == 0) {
       m->type = (uint32_t)val;
     } else if (num == 5 && wt == 2) {
-      m->payload_kind = PAYLOAD_PREPREPARE;
-      m->preprepare = PrePrepareMessage();
-      uint32_t n2, w2;
-      uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0, nullptr};
+      select(PAYLOAD_PREPREPARE);
       while (sub.next(n2, w2, v2, s2)) {
-        if (n2 == 1 && w2 == 2) m->preprepare.proposal = decode_proposal(s2);
-        else if (n2 == 2 && w2 == 2) m->preprepare.proposal_hash = s2.bytes();
-        else if (n2 == 3 && w2 == 2) m->preprepare.certificate = decode_rcc(s2);
+        if (n2 == 1 && w2 == 2) {
+          if (!m->preprepare.proposal) m->preprepare.proposal = std::make_shared<Proposal>();
+          decode_proposal_into(*m->preprepare.proposal, s2);
+        } else if (n2 == 2 && w2 == 2) {
+          m->preprepare.proposal_hash = s2.bytes();
+        } else if (n2 == 3 && w2 == 2) {
+          if (!m->preprepare.certificate) m->preprepare.certificate = std::make_shared<RoundChangeCertificate>();
+          decode_rcc_into(*m->preprepare.certificate, s2);
+        }
       }
     } else if (num == 6 && wt == 2) {
-      m->payload_kind = PAYLOAD_PREPARE;
-      m->prepare = PrepareMessage();
-      uint32_t n2, w2;
-      uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0, nullptr};
+      select(PAYLOAD_PREPARE);
       while (sub.next(n2, w2, v2, s2))
         if (n2 == 1 && w2 == 2) m->prepare.proposal_hash = s2.bytes();
     } else if (num == 7 && wt == 2) {
-      m->payload_kind = PAYLOAD_COMMIT;
-      m->commit = CommitMessage();
-      uint32_t n2, w2;
-      uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0, nullptr};
+      select(PAYLOAD_COMMIT);
       while (sub.next(n2, w2, v2, s2)) {
         if (n2 == 1 && w2 == 2) m->commit.proposal_hash = s2.bytes();
         else if (n2 == 2 && w2 == 2) m->commit.committed_seal = s2.bytes();
       }
     } else if (num == 8 && wt == 2) {
-      m->payload_kind = PAYLOAD_ROUND_CHANGE;
-      m->round_change = RoundChangeMessage();
-      uint32_t n2, w2;
-      uint64_t v2;
-      wire::Reader s2{nullptr, nullptr, 0, nullptr};
+      select(PAYLOAD_ROUND_CHANGE);
       while (sub.next(n2, w2, v2, s2)) {
-        if (n2 == 1 && w2 == 2) m->round_change.last_prepared_proposal = decode_proposal(s2);
-        else if (n2 == 2 && w2 == 2) m->round_change.latest_prepared_certificate = decode_pc(s2);
+        if (n2 == 1 && w2 == 2) {
+          if (!m->round_change.last_prepared_proposal) m->round_change.last_prepared_proposal = std::make_shared<Proposal>();
+          decode_proposal_into(*m->round_change.last_prepared_proposal, s2);
+        } else if (n2 == 2 && w2 == 2) {
+          if (!m->round_change.latest_prepared_certificate) m->round_change.latest_prepared_certificate = std::make_shared<PreparedCertificate>();
+          decode_pc_into(*m->round_change.latest_prepared_certificate, s2);
+        }
       }
     }
   }
-  return m;
 }
 
 inline MessagePtr decode_message(const uint8_t* data, size_t len) {
   auto root = std::make_shared<const Bytes>((const char*)data, len);
   const uint8_t* b = (const uint8_t*)root->data();
   return decode_message(wire::Reader{b, b + len, 0, &root});
+}
+
+// ----------------------------------------------------------------------------------------------- byte-exact re-marshal
+// messages/proto/helper.go:13-27 is Clone + Signature = nil + proto.Marshal.  For a canonical frame that is the frame minus its
+// signature TLV (what the device hashes).  For every OTHER parseable frame this restates protobuf-go's parse + marshal on a
+// generic field tree (same rules as the typed decoder above, plus: unknown fields -- unknown numbers, wrong wire types, groups --
+// are kept verbatim and re-emitted after the message's known fields), so that a GPU-backed node and a Go node hash the same
+// bytes whatever a Byzantine validator signed.  Twin of oracle/ibft_proto.py remarshal(); checked against google.protobuf
+// driven by the reference's descriptor (tests/golden/proto_wire.json "noncanonical").
+namespace wire {
+enum TreeType : uint8_t { T_IBFT = 0, T_VIEW, T_PREPREPARE, T_PREPARE, T_COMMIT, T_ROUND_CHANGE, T_PROPOSAL, T_RCC, T_PC };
+// 0 unknown, 1 varint, 2 bytes, 3 sub-message, 4 repeated sub-message, 5 oneof member (sub-message); *sub = its type
+inline int tree_field_kind(TreeType t, uint32_t f, TreeType* sub) {
+  switch (t) {
+    case T_IBFT:
+      switch (f) {
+        case 1: *sub = T_VIEW; return 3;
+        case 2: case 3: return 2;
+        case 4: return 1;
+        case 5: *sub = T_PREPREPARE; return 5;
+        case 6: *sub = T_PREPARE; return 5;
+        case 7: *sub = T_COMMIT; return 5;
+        case 8: *sub = T_ROUND_CHANGE; return 5;
+        default: return 0;
+      }
+    case T_VIEW: return (f == 1 || f == 2) ? 1 : 0;
+    case T_PREPREPARE:
+      if (f == 1) { *sub = T_PROPOSAL; return 3; }
+      if (f == 2) return 2;
+      if (f == 3) { *sub = T_RCC; return 3; }
+      return 0;
+    case T_PREPARE: return f == 1 ? 2 : 0;
+    case T_COMMIT: return (f == 1 || f == 2) ? 2 : 0;
+    case T_ROUND_CHANGE:
+      if (f == 1) { *sub = T_PROPOSAL; return 3; }
+      if (f == 2) { *sub = T_PC; return 3; }
+      return 0;
+    case T_PROPOSAL: return f == 1 ? 2 : f == 2 ? 1 : 0;
+    case T_RCC:
+      if (f == 1) { *sub = T_IBFT; return 4; }
+      return 0;
+    case T_PC:
+      if (f == 1) { *sub = T_IBFT; return 3; }
+      if (f == 2) { *sub = T_IBFT; return 4; }
+      return 0;
+  }
+  return 0;
+}
+struct TreeNode {
+  struct Field {
+    int kind = 0;
+    uint64_t scalar = 0;
+    Bytes bytes;
+    std::vector<std::unique_ptr<TreeNode>> subs;  // one element for a singular sub-message
+  };
+  std::map<uint32_t, Field> fields;
+  Bytes unknown;
+};
+inline void tree_parse_into(TreeNode& node, TreeType type, Reader r) {
+  while (!r.done()) {
+    const uint8_t* start = r.p;
+    uint32_t num, wt;
+    uint64_t val = 0;
+    Reader sub{nullptr, nullptr, 0, nullptr};
+    r.next(num, wt, val, sub);
+    TreeType st = T_IBFT;
+    int kind = tree_field_kind(type, num, &st);
+    const uint32_t want = kind == 1 ? 0u : 2u;
+    if (kind == 0 || wt != want) {
+      node.unknown.append((const char*)start, (size_t)(r.p - start));
+      continue;
+    }
+    if (kind == 5)  // a different oneof member replaces the one set before
+      for (uint32_t other = 5; other <= 8; other++)
+        if (other != num) node.fields.erase(other);
+    TreeNode::Field& f = node.fields[num];
+    f.kind = kind;
+    if (kind == 1) f.scalar = val;
+    else if (kind == 2) f.bytes = sub.bytes();
+    else if (kind == 4) {
+      f.subs.push_back(std::make_unique<TreeNode>());
+      tree_parse_into(*f.subs.back(), st, sub);
+    } else {
+      if (f.subs.empty()) f.subs.push_back(std::make_unique<TreeNode>());
+      tree_parse_into(*f.subs[0], st, sub);  // a second occurrence merges into the first
+    }
+  }
+}
+inline Bytes tree_emit(const TreeNode& node, TreeType type, bool skip_signature) {
+  Bytes o;
+  for (auto& kv : node.fields) {
+    const uint32_t num = kv.first;
+    const TreeNode::Field& f = kv.second;
+    if (skip_signature && type == T_IBFT && num == 3) continue;
+    TreeType st = T_IBFT;
+    tree_field_kind(type, num, &st);
+    if (f.kind == 1) f_varint(o, num, f.scalar);
+    else if (f.kind == 2) f_bytes(o, num, f.bytes);
+    else
+      for (auto& c : f.subs) f_msg(o, num, tree_emit(*c, st, false));
+  }
+  o += node.unknown;
+  return o;
+}
+}  // namespace wire
+
+// proto.Marshal(proto.Unmarshal(frame)), with the (known) signature field cleared first when !with_signature.  Throws DecodeError.
+inline Bytes remarshal(const uint8_t* frame, size_t len, bool with_signature) {
+  wire::TreeNode root;
+  wire::tree_parse_into(root, wire::T_IBFT, wire::Reader{frame, frame + len, 0, nullptr});
+  return wire::tree_emit(root, wire::T_IBFT, !with_signature);
+}
+// PayloadNoSig of a message: for one that was decoded from a frame, the re-marshal of exactly the bytes that arrived
+inline Bytes payload_no_sig_exact(const IbftMessage& m) {
+  if (m.has_wire()) return remarshal((const uint8_t*)m.wire_data(), m.wire_len, false);
+  return payload_no_sig(m);
 }
 
 }  // namespace ibft::host

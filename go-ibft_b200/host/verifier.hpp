@@ -311,7 +311,13 @@ class GpuVerifier : public Verifier {
       p.key.append(m.wire_data(), m.wire_len);
       return true;
     }
-    p.payload = payload_no_sig(m);
+    // marshalled path: for a message that was decoded from a frame, PayloadNoSig is the protobuf-go re-marshal of exactly the
+    // bytes that arrived (unknown fields kept, duplicates merged) -- the model alone would lose them
+    try {
+      p.payload = payload_no_sig_exact(m);
+    } catch (const DecodeError&) {
+      return false;
+    }
     put_sig(p.item, m.signature, m.from);
     p.item.kind = IBFT_KIND_PAYLOAD;
     p.key.assign(1, 'S');

@@ -210,87 +210,217 @@ def _fields(buf: bytes):
         yield num, wt, v
 
 
+# The typed decoders go through the generic field tree below (_parse_into), so that the MODEL a frame decodes to is the one
+# protobuf-go builds: duplicated sub-messages merged, last scalar wins, a later oneof member replaces an earlier one, fields
+# with a wrong wire type ignored (they are unknown fields).
+def _view_from(n) -> View:
+    return View(n.fields.get(1, 0), n.fields.get(2, 0))
+
+
+def _proposal_from(n) -> Proposal:
+    return Proposal(n.fields.get(1, b""), n.fields.get(2, 0))
+
+
+def _pc_from(n) -> PreparedCertificate:
+    pm = n.fields.get(1)
+    reps = n.fields.get(2)
+    return PreparedCertificate(None if pm is None else _message_from(pm), None if reps is None else [_message_from(x) for x in reps])
+
+
+def _rcc_from(n) -> RoundChangeCertificate:
+    return RoundChangeCertificate([_message_from(x) for x in n.fields.get(1, [])])
+
+
+def _message_from(n) -> IbftMessage:
+    m = IbftMessage()
+    f = n.fields
+    if 1 in f:
+        m.view = _view_from(f[1])
+    m.from_ = f.get(2, b"")
+    m.signature = f.get(3, b"")
+    m.type = f.get(4, 0)
+    if 5 in f:
+        g = f[5].fields
+        m.payload = PrePrepareMessage(_proposal_from(g[1]) if 1 in g else None, g.get(2, b""), _rcc_from(g[3]) if 3 in g else None)
+    elif 6 in f:
+        m.payload = PrepareMessage(f[6].fields.get(1, b""))
+    elif 7 in f:
+        m.payload = CommitMessage(f[7].fields.get(1, b""), f[7].fields.get(2, b""))
+    elif 8 in f:
+        g = f[8].fields
+        m.payload = RoundChangeMessage(_proposal_from(g[1]) if 1 in g else None, _pc_from(g[2]) if 2 in g else None)
+    return m
+
+
+def _tree(buf: bytes, type_name: str):
+    n = _Node()
+    _parse_into(n, bytes(buf), type_name)
+    return n
+
+
 def decode_view(buf: bytes) -> View:
-    v = View()
-    for num, wt, val in _fields(buf):
-        if num == 1 and wt == 0:
-            v.height = val
-        elif num == 2 and wt == 0:
-            v.round = val
-    return v
+    return _view_from(_tree(buf, "View"))
 
 
 def decode_proposal(buf: bytes) -> Proposal:
-    p = Proposal()
-    for num, wt, val in _fields(buf):
-        if num == 1 and wt == 2:
-            p.raw_proposal = bytes(val)
-        elif num == 2 and wt == 0:
-            p.round = val
-    return p
+    return _proposal_from(_tree(buf, "Proposal"))
 
 
 def decode_pc(buf: bytes) -> PreparedCertificate:
-    pc = PreparedCertificate()
-    for num, wt, val in _fields(buf):
-        if num == 1 and wt == 2:
-            pc.proposal_message = decode_ibft_message(val)
-        elif num == 2 and wt == 2:
-            if pc.prepare_messages is None:
-                pc.prepare_messages = []
-            pc.prepare_messages.append(decode_ibft_message(val))
-    return pc
+    return _pc_from(_tree(buf, "PreparedCertificate"))
 
 
 def decode_rcc(buf: bytes) -> RoundChangeCertificate:
-    rcc = RoundChangeCertificate()
-    for num, wt, val in _fields(buf):
-        if num == 1 and wt == 2:
-            rcc.round_change_messages.append(decode_ibft_message(val))
-    return rcc
+    return _rcc_from(_tree(buf, "RoundChangeCertificate"))
 
 
 def decode_ibft_message(buf: bytes) -> IbftMessage:
-    m = IbftMessage()
-    for num, wt, val in _fields(bytes(buf)):
-        if num == 1 and wt == 2:
-            m.view = decode_view(val)
-        elif num == 2 and wt == 2:
-            m.from_ = bytes(val)
-        elif num == 3 and wt == 2:
-            m.signature = bytes(val)
-        elif num == 4 and wt == 0:
-            m.type = val
-        elif num == 5 and wt == 2:
-            pp = PrePrepareMessage()
-            for n2, w2, v2 in _fields(val):
-                if n2 == 1 and w2 == 2:
-                    pp.proposal = decode_proposal(v2)
-                elif n2 == 2 and w2 == 2:
-                    pp.proposal_hash = bytes(v2)
-                elif n2 == 3 and w2 == 2:
-                    pp.certificate = decode_rcc(v2)
-            m.payload = pp
-        elif num == 6 and wt == 2:
-            pr = PrepareMessage()
-            for n2, w2, v2 in _fields(val):
-                if n2 == 1 and w2 == 2:
-                    pr.proposal_hash = bytes(v2)
-            m.payload = pr
-        elif num == 7 and wt == 2:
-            cm = CommitMessage()
-            for n2, w2, v2 in _fields(val):
-                if n2 == 1 and w2 == 2:
-                    cm.proposal_hash = bytes(v2)
-                elif n2 == 2 and w2 == 2:
-                    cm.committed_seal = bytes(v2)
-            m.payload = cm
-        elif num == 8 and wt == 2:
-            rc = RoundChangeMessage()
-            for n2, w2, v2 in _fields(val):
-                if n2 == 1 and w2 == 2:
-                    rc.last_prepared_proposal = decode_proposal(v2)
-                elif n2 == 2 and w2 == 2:
-                    rc.latest_prepared_certificate = decode_pc(v2)
-            m.payload = rc
-    return m
+    return _message_from(_tree(buf, "IbftMessage"))
+
+
+# ----------------------------------------------------------------------------- byte-exact re-marshal of ANY parseable frame
+# messages/proto/helper.go:13-27 is proto.Clone + Signature = nil + proto.Marshal.  For a frame protobuf-go itself produced the
+# model encoder above reproduces those bytes.  For every OTHER parseable frame (a Byzantine validator may sign whatever bytes it
+# likes and the honest Go nodes will re-marshal them the protobuf-go way) the result follows protobuf's parsing rules, restated
+# here on a generic field tree:
+#   * a known field with the wrong wire type, and every unknown field (groups included), is kept verbatim in the message's unknown
+#     bytes and re-emitted AFTER its known fields, in arrival order;
+#   * a singular scalar / bytes field that appears several times: the last occurrence wins;
+#   * a singular sub-message that appears several times is MERGED field by field (the same rule, recursively);
+#   * a oneof: a different member replaces the one set before, the same member again is merged;
+#   * repeated sub-messages accumulate;
+#   * on output: fields in field-number order, zero scalars and empty bytes omitted, minimal varints.
+_SCHEMA = {
+    "IbftMessage": {1: ("msg", "View"), 2: ("bytes",), 3: ("bytes",), 4: ("varint",), 5: ("oneof", "PrePrepareMessage"),
+                    6: ("oneof", "PrepareMessage"), 7: ("oneof", "CommitMessage"), 8: ("oneof", "RoundChangeMessage")},
+    "View": {1: ("varint",), 2: ("varint",)},
+    "PrePrepareMessage": {1: ("msg", "Proposal"), 2: ("bytes",), 3: ("msg", "RoundChangeCertificate")},
+    "PrepareMessage": {1: ("bytes",)},
+    "CommitMessage": {1: ("bytes",), 2: ("bytes",)},
+    "RoundChangeMessage": {1: ("msg", "Proposal"), 2: ("msg", "PreparedCertificate")},
+    "Proposal": {1: ("bytes",), 2: ("varint",)},
+    "RoundChangeCertificate": {1: ("rep", "IbftMessage")},
+    "PreparedCertificate": {1: ("msg", "IbftMessage"), 2: ("rep", "IbftMessage")},
+}
+_MAX_DEPTH = 100  # protobuf-go's default recursion limit is 10,000; anything legitimate needs 8
+
+
+class _Node:
+    __slots__ = ("fields", "unknown")
+
+    def __init__(self):
+        self.fields = {}
+        self.unknown = bytearray()
+
+
+def _skip_group(buf: bytes, pos: int, number: int, depth: int) -> int:
+    """position just past the END_GROUP tag matching `number` (nested groups allowed)"""
+    if depth > _MAX_DEPTH:
+        raise DecodeError("nesting too deep")
+    while True:
+        key, pos = _read_varint(buf, pos)
+        num, wt = key >> 3, key & 7
+        if num == 0 or num > 0x1FFFFFFF:
+            raise DecodeError("invalid field number")
+        if wt == 4:
+            if num != number:
+                raise DecodeError("mismatched end group")
+            return pos
+        if wt == 0:
+            _, pos = _read_varint(buf, pos)
+        elif wt == 1:
+            pos += 8
+        elif wt == 5:
+            pos += 4
+        elif wt == 2:
+            ln, pos = _read_varint(buf, pos)
+            pos += ln
+        elif wt == 3:
+            pos = _skip_group(buf, pos, num, depth + 1)
+        else:
+            raise DecodeError("invalid wire type")
+        if pos > len(buf):
+            raise DecodeError("truncated group")
+
+
+def _parse_into(node: _Node, buf: bytes, type_name: str, depth: int = 0) -> None:
+    if depth > _MAX_DEPTH:
+        raise DecodeError("nesting too deep")
+    schema = _SCHEMA[type_name]
+    pos = 0
+    while pos < len(buf):
+        start = pos
+        key, pos = _read_varint(buf, pos)
+        num, wt = key >> 3, key & 7
+        if num == 0 or num > 0x1FFFFFFF:
+            raise DecodeError("invalid field number")
+        val = None
+        if wt == 0:
+            val, pos = _read_varint(buf, pos)
+        elif wt == 1:
+            pos += 8
+        elif wt == 5:
+            pos += 4
+        elif wt == 2:
+            ln, pos = _read_varint(buf, pos)
+            val = buf[pos:pos + ln]
+            pos += ln
+        elif wt == 3:
+            pos = _skip_group(buf, pos, num, depth + 1)
+        else:
+            raise DecodeError("invalid wire type")
+        if pos > len(buf):
+            raise DecodeError("truncated field")
+        spec = schema.get(num)
+        want = None if spec is None else (0 if spec[0] == "varint" else 2)
+        if spec is None or wt != want:
+            node.unknown += buf[start:pos]
+            continue
+        kind = spec[0]
+        if kind == "varint":
+            node.fields[num] = val
+        elif kind == "bytes":
+            node.fields[num] = bytes(val)
+        elif kind == "rep":
+            child = _Node()
+            _parse_into(child, val, spec[1], depth + 1)
+            node.fields.setdefault(num, []).append(child)
+        else:  # singular sub-message ("msg") or oneof member
+            if kind == "oneof":
+                for other in [k for k in node.fields if k != num and schema[k][0] == "oneof"]:
+                    del node.fields[other]
+            child = node.fields.get(num)
+            if child is None:
+                child = node.fields[num] = _Node()
+            _parse_into(child, val, spec[1], depth + 1)  # a second occurrence merges into the first
+
+
+def _emit(node: _Node, type_name: str, skip: tuple = ()) -> bytes:
+    schema = _SCHEMA[type_name]
+    out = bytearray()
+    for num in sorted(node.fields):
+        if num in skip:
+            continue
+        spec, v = schema[num], node.fields[num]
+        if spec[0] == "varint":
+            out += _f_varint(num, v)
+        elif spec[0] == "bytes":
+            out += _f_bytes(num, v)
+        elif spec[0] == "rep":
+            for child in v:
+                out += _f_msg(num, _emit(child, spec[1]))
+        else:
+            out += _f_msg(num, _emit(v, spec[1]))
+    return bytes(out) + bytes(node.unknown)
+
+
+def remarshal(frame: bytes, with_signature: bool = True) -> bytes:
+    """proto.Marshal(proto.Unmarshal(frame)) the protobuf-go way; with_signature=False clears the (known) signature field first:
+    IbftMessage.PayloadNoSig() for a message that arrived as `frame`."""
+    root = _Node()
+    _parse_into(root, bytes(frame), "IbftMessage")
+    return _emit(root, "IbftMessage", skip=() if with_signature else (3,))
+
+
+def payload_no_sig_from_wire(frame: bytes) -> bytes:
+    return remarshal(frame, with_signature=False)

@@ -119,6 +119,90 @@ def cases():
     return out
 
 
+def _tlvs(buf):
+    out, pos = [], 0
+    while pos < len(buf):
+        s = pos
+        key, pos = ip._read_varint(buf, pos)
+        wt = key & 7
+        if wt == 0:
+            _, pos = ip._read_varint(buf, pos)
+        elif wt == 2:
+            ln, pos = ip._read_varint(buf, pos)
+            pos += ln
+        elif wt == 1:
+            pos += 8
+        elif wt == 5:
+            pos += 4
+        else:
+            raise ValueError(wt)
+        out.append(buf[s:pos])
+    return out
+
+
+def noncanonical_cases(cls):
+    """Frames protobuf-go would NOT have produced but parses happily (a Byzantine validator may sign anything): duplicated and
+    re-ordered fields, unknown fields, known numbers with the wrong wire type, groups, non-minimal varints, explicit zeros --
+    with what google.protobuf (same descriptor) re-serialises them to, with and without the signature."""
+    import random
+    M = cls["IbftMessage"]
+    rnd = random.Random(2024)
+    unk = [bytes.fromhex(x) for x in ("4801", "5203616263", "5d01020304", "610102030405060708", "f80101", "1801", "0801", "2a00",
+                                      "1a00", "7b08017c", "7b7c", "7b0a01617c", "2000", "20818000")]
+    base = {n: to_pb(cls, m).SerializeToString(deterministic=True) for n, m in cases().items()}
+    hand = {
+        "view_split_in_two": bytes.fromhex("0a020805") + bytes.fromhex("0a021007") + base["prepare_h1_r0"][4:],
+        "type_twice_last_wins": base["prepare_h1e6_signed"] + bytes.fromhex("2002"),
+        "unknown_in_the_middle": base["commit_h1e6_signed"][:6] + bytes.fromhex("4801") + base["commit_h1e6_signed"][6:],
+        "oneof_replaced": base["prepare_h1e6_signed"] + base["commit_h1e6_signed"][-103:],
+        "signature_as_varint": bytes.fromhex("1801") + base["prepare_h1_r0"],
+        "group_unknown": base["prepare_h1_r0"] + bytes.fromhex("7b0a0161087f7c"),
+    }
+    out = []
+    for name, wire in hand.items():
+        out.append((name, wire))
+    names = sorted(base)
+    for k in range(60):
+        parts = _tlvs(base[names[k % len(names)]])
+        for _ in range(rnd.randrange(1, 4)):
+            op = rnd.randrange(5)
+            if op == 0 and parts:
+                parts.insert(rnd.randrange(len(parts) + 1), rnd.choice(parts))
+            elif op == 1 and len(parts) > 1:
+                i, j = rnd.randrange(len(parts)), rnd.randrange(len(parts))
+                parts[i], parts[j] = parts[j], parts[i]
+            elif op == 2:
+                parts.insert(rnd.randrange(len(parts) + 1), rnd.choice(unk))
+            elif op == 3 and parts:
+                i = rnd.randrange(len(parts))
+                key, pos = ip._read_varint(parts[i], 0)
+                if key & 7 == 2:
+                    ln, pos2 = ip._read_varint(parts[i], pos)
+                    try:
+                        inner = _tlvs(parts[i][pos2:pos2 + ln])
+                    except Exception:
+                        inner = []
+                    if inner:
+                        inner.insert(rnd.randrange(len(inner) + 1), rnd.choice(inner + unk))
+                        body = b"".join(inner)
+                        parts[i] = ip._varint(key) + ip._varint(len(body)) + body
+            elif op == 4 and parts:
+                del parts[rnd.randrange(len(parts))]
+        out.append(("mutant_%02d" % k, b"".join(parts)))
+    recs = []
+    for name, wire in out:
+        try:
+            pb = M.FromString(wire)
+        except Exception:
+            recs.append({"name": name, "wire": wire.hex(), "parses": False})
+            continue
+        full = pb.SerializeToString(deterministic=True)
+        pb.signature = b""
+        recs.append({"name": name, "wire": wire.hex(), "parses": True, "remarshal": full.hex(),
+                     "payload_no_sig": pb.SerializeToString(deterministic=True).hex()})
+    return recs
+
+
 def main():
     cls = load_reference_classes()
     recs = []
@@ -131,7 +215,7 @@ def main():
     path = os.path.join(os.path.dirname(__file__), "proto_wire.json")
     json.dump({"generator": "tests/golden/make_proto_golden.py",
                "source": "descriptor embedded in reference messages/proto/messages.pb.go (protoc-gen-go v1.28.1)",
-               "cases": recs}, open(path, "w"), indent=1)
+               "cases": recs, "noncanonical": noncanonical_cases(cls)}, open(path, "w"), indent=1)
     print("wrote", path, len(recs), "cases")
 
 

@@ -26,6 +26,21 @@ def test_codec_matches_reference_descriptor_golden():
     assert host.reencode(bytes.fromhex("0a05"), True) is None                        # truncated -> decode error, no crash
 
 
+def test_cpp_remarshal_and_merged_model_match_protobuf_on_non_canonical_frames():
+    """C++ twin of oracle remarshal(): protobuf-go's Unmarshal + Marshal restated (unknown fields kept, duplicates merged, a later
+    oneof member replaces an earlier one), against google.protobuf's output for the same frames; and the C++ MODEL of such a frame
+    equals the oracle's merged model."""
+    nc = json.load(open(os.path.join(HERE, "golden", "proto_wire.json")))["noncanonical"]
+    for c in nc:
+        wire = bytes.fromhex(c["wire"])
+        if not c["parses"]:
+            assert host.remarshal(wire) is None
+            continue
+        assert host.remarshal(wire).hex() == c["remarshal"], c["name"]
+        assert host.remarshal(wire, with_signature=False).hex() == c["payload_no_sig"], c["name"]
+        assert host.reencode(wire) == ip.encode_ibft_message(ip.decode_ibft_message(wire)), c["name"]
+
+
 @pytest.mark.parametrize("powers,signers,want", QUORUM_CASES)
 def test_quorum_table_cpp(powers, signers, want):
     """core/validator_manager_test.go:18-187 through the C++ ValidatorManager."""
