@@ -29,6 +29,9 @@ type Verifier struct {
 	Eng            *Engine
 	IsProposerFn   func(id []byte, height, round uint64) bool // embedder policy, not signature work
 	IsValidBlockFn func(raw []byte) bool
+	// ProposalHashFn is the embedder's proposal hash (a real node hashes its block header).  nil: the synthetic convention of
+	// SURVEY.md §8c on the device.  Also the place to hash ONE multi-megabyte proposal on a host core (DESIGN.md §3.3).
+	ProposalHashFn func(raw []byte, round uint64) [32]byte
 
 	// ingress coalescer knobs (see lookupOrCoalesce)
 	IngressMaxBatch int
@@ -226,10 +229,14 @@ func (v *Verifier) IsValidProposalHash(p *proto.Proposal, hash []byte) bool {
 	want, hit := v.hashCache[key]
 	v.mu.Unlock()
 	if !hit {
-		var err error
-		want, err = v.Eng.ProposalHash(p.RawProposal, p.Round)
-		if err != nil {
-			return false
+		if v.ProposalHashFn != nil {
+			want = v.ProposalHashFn(p.RawProposal, p.Round)
+		} else {
+			var err error
+			want, err = v.Eng.ProposalHash(p.RawProposal, p.Round)
+			if err != nil {
+				return false
+			}
 		}
 		v.mu.Lock()
 		if len(v.hashCache) >= maxHashCache { // entries are proposal-sized: bounded against ROUND_CHANGE floods
