@@ -81,7 +81,7 @@ class GpuVerifier : public Verifier {
   uint32_t ingress_max_batch = 4096;
   uint32_t ingress_min_batch = 1;
   uint32_t ingress_linger_us = 0;
-  uint32_t ingress_second_min = 24;  // queue length from which a SECOND flush goes up while one is still on the device
+  uint32_t ingress_second_min = 32;  // queue length from which a SECOND flush goes up while one is still on the device
 
   explicit GpuVerifier(const ibft_engine_params& params) {
     params_ = params;
