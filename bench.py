@@ -245,7 +245,19 @@ def strong_scaling_legs(args, ib, eng_weak, d, base_items, groups3, world, rank,
         raise SystemExit("bench: sharded 10k round: bitmap differs from the golden fixture")
     out["round10k"] = {"workload": "ONE 10k-validator COMMIT round: 10,000 committed seals, weighted quorum", "items": n,
                        "items_per_gpu": int(hi - lo), "p50_us": _pct(ts, 0.5), "p95_us": _pct(ts, 0.95), "reps": len(ts),
+                       "exchange": "nccl all_gather_into_tensor + merge kernel",
                        "has_quorum": bool(res[seal_group]["has_quorum"]), "bitmap_matches_golden": True}
+    # the same round with the exchange done by ONE kernel over NVLink peer memory (no library collective)
+    try:
+        svp = sharding.ShardedVerifier(eng_weak, n, groups3, world, rank, li, la, stream, exchange="p2p")
+        ts, resp, bmp = timed(svp, args.latency_reps)
+        if not np.array_equal(np.unpackbits(bmp.view(np.uint8), bitorder="little")[:n], gold) or resp.tobytes() != res.tobytes():
+            raise SystemExit("bench: sharded 10k round (peer-memory exchange): results differ")
+        out["round10k"]["peer_memory_exchange"] = {"p50_us": _pct(ts, 0.5), "p95_us": _pct(ts, 0.95), "reps": len(ts),
+                                                   "exchange": "k_quorum_exchange: publish flag, wait for peers, merge out of peer memory (CUDA IPC over NVLink); "
+                                                               "all-gather + merge in one launch", "results_equal_nccl_path": True}
+    except (RuntimeError, AttributeError) as ex:
+        out["round10k"]["peer_memory_exchange"] = {"unavailable": str(ex)[:200]}
     # ---- (b) config 5 at its stated size
     w, pin = load_full_cache("config5")
     if w is None:
@@ -262,6 +274,15 @@ def strong_scaling_legs(args, ib, eng_weak, d, base_items, groups3, world, rank,
         li, la = sharding.rebase_shard(items, arena, lo, hi)
         sv5 = sharding.ShardedVerifier(eng5, n, groups5, world, rank, li, la, stream)
         ts, res, bm = timed(sv5, max(20, args.latency_reps // 4))
+        p2p5 = None
+        try:
+            sv5p = sharding.ShardedVerifier(eng5, n, groups5, world, rank, li, la, stream, exchange="p2p")
+            tsp, resp, bmp = timed(sv5p, max(20, args.latency_reps // 4))
+            if not np.array_equal(bmp, pin["bitmap"]) or resp.tobytes() != res.tobytes():
+                raise SystemExit("bench: sharded config 5 (peer-memory exchange): results differ")
+            p2p5 = {"p50_us": _pct(tsp, 0.5), "p95_us": _pct(tsp, 0.95), "results_equal_nccl_path": True}
+        except (RuntimeError, AttributeError) as ex:
+            p2p5 = {"unavailable": str(ex)[:200]}
         if not np.array_equal(bm, pin["bitmap"]):
             raise SystemExit("bench: sharded config 5: bitmap differs from the committed oracle pin")
         want = pin["results"]
@@ -273,7 +294,7 @@ def strong_scaling_legs(args, ib, eng_weak, d, base_items, groups3, world, rank,
                                       "45/45/9/1 PREPARE/COMMIT/ROUND_CHANGE/PREPREPARE, 1% adversarial; sharded by contiguous index range",
                           "items": n, "items_per_gpu": int(hi - lo), "payload_bytes_per_gpu": int(la.size), "groups": int(w["n_groups"]),
                           "p50_us": p50, "p95_us": _pct(ts, 0.95), "reps": len(ts), "verifies_per_s_at_p50": n / (p50 * 1e-6),
-                          "bitmap_and_quorum_match_pin": True}
+                          "bitmap_and_quorum_match_pin": True, "peer_memory_exchange": p2p5}
         eng5.close()
     return out
 

@@ -1108,6 +1108,75 @@ __global__ void k_quorum_merge(const uint32_t* __restrict__ parts, uint32_t n_pa
   else n_valid[i - voted_words] = acc;
 }
 
+// Multi-GPU exchange WITHOUT a library collective: every rank's (bitmap words | partial voted sets | valid counts) sit in a
+// buffer its peers have mapped over NVLink (CUDA IPC); this kernel publishes "my round `epoch` is complete", waits for the
+// peers' flags, then reads their words straight out of peer memory -- OR-ing the voted sets, summing the counts, and assembling
+// the complete bitmap -- so that the all-gather and the merge are ONE launch (the NCCL path costs a collective launch + the
+// merge kernel: ~25-30 us of a 0.5 ms round).  Buffer of rank r: [2 parities][words_per_rank] words, then flags[2].  Rounds
+// alternate parities: a rank can only start writing parity p for round e+2 after it has seen every peer's flag for round e+1,
+// i.e. after every peer has finished reading round e.  The wait is bounded (spin_limit polls): on timeout the kernel reports
+// through *timeout_flag and merges nothing -- it never hangs the device.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+struct peer_bufs {
+  uint32_t* buf[8];  // one node: at most 8 ranks
+};
+__global__ void k_quorum_exchange(peer_bufs peers, uint32_t world, uint32_t rank, uint32_t words_per_rank, uint32_t bitmap_words,
+                                  uint32_t voted_words, uint32_t n_groups, uint32_t epoch, uint32_t spin_limit,
+                                  uint32_t* __restrict__ full_bitmap, uint32_t* __restrict__ voted, uint32_t* __restrict__ n_valid,
+                                  uint32_t* __restrict__ timeout_flag) {
+  __shared__ uint32_t s_ok;
+  const uint32_t par = epoch & 1u;
+  const size_t flags_off = 2 * (size_t)words_per_rank;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();  // the verify / mark kernels' writes to my buffer are visible to the peers before the flag is
+      st_release_sys(peers.buf[rank] + flags_off + par, epoch);
+    }
+    uint32_t ok = 1;
+    for (uint32_t r = 0; r < world && ok; r++) {
+      const uint32_t* f = peers.buf[r] + flags_off + par;
+      uint32_t spins = 0;
+      while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+        if (++spins > spin_limit) { ok = 0; break; }
+        __nanosleep(64);
+      }
+    }
+    if (!ok) atomicExch(timeout_flag, 1u);
+    s_ok = ok;
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const uint32_t per_rank_bitmap = bitmap_words;  // words [0, bitmap_words) of a rank's buffer: its slice of the bitmap
+  const uint32_t total = world * per_rank_bitmap + voted_words + n_groups;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    if (i < world * per_rank_bitmap) {
+      const uint32_t r = i / per_rank_bitmap, w = i % per_rank_bitmap;
+      full_bitmap[i] = ld_relaxed_sys(peers.buf[r] + (size_t)par * words_per_rank + w);
+    } else {
+      const uint32_t j = i - world * per_rank_bitmap;  // index into (voted sets | counts)
+      uint32_t acc = 0;
+      for (uint32_t r = 0; r < world; r++) {
+        uint32_t v = ld_relaxed_sys(peers.buf[r] + (size_t)par * words_per_rank + per_rank_bitmap + j);
+        acc = j < voted_words ? (acc | v) : (acc + v);
+      }
+      if (j < voted_words) voted[j] = acc;
+      else n_valid[j - voted_words] = acc;
+    }
+  }
+}
+
 // one CTA per group: 320-bit sum of the voting power of the voted validators, compared with the threshold
 #define IBFT_REDUCE_THREADS 1024  // one CTA per group; a 10k-validator set is 10 strided passes instead of 40
 __global__ void __launch_bounds__(IBFT_REDUCE_THREADS)
@@ -2447,6 +2516,38 @@ extern "C" int ibft_quorum_merge_device(ibft_engine* e, const void* d_partials, 
   uint32_t total = (uint32_t)(voted_words + n_groups);
   k_quorum_merge<<<(total + 255) / 256, 256, 0, st>>>((const uint32_t*)d_partials, n_parts, part_stride_words, (uint32_t)voted_words,
                                                       n_groups, L->d_voted, L->d_nvalid);
+  e->launches++;
+  CU(cudaGetLastError());
+  k_quorum_reduce<<<n_groups, IBFT_REDUCE_THREADS, 0, st>>>(L->d_groups, L->d_gdev, n_groups, e->d_slots, e->p.max_table_slots, L->d_voted, L->d_nvalid,
+                                            (ibft_group_result*)d_results);
+  e->launches++;
+  CU(cudaGetLastError());
+  return IBFT_OK;
+}
+
+extern "C" int ibft_quorum_exchange_device(ibft_engine* e, const uint64_t* peer_bufs_in, uint32_t world, uint32_t rank,
+                                           uint32_t words_per_rank, uint32_t bitmap_words_per_rank, uint32_t epoch, void* d_bitmap_full,
+                                           void* d_results, void* d_timeout_flag, void* stream) {
+  if (!e || !peer_bufs_in || !d_bitmap_full || !d_results || !d_timeout_flag || world == 0 || world > 8 || rank >= world || epoch == 0) {
+    set_err("bad argument");
+    return IBFT_ERR_INVALID_ARG;
+  }
+  lane* L = &e->lanes[0];
+  std::lock_guard<std::mutex> lk(L->mu);
+  uint32_t n_groups = (uint32_t)L->last_groups.size();
+  if (n_groups == 0) { set_err("call ibft_bind_groups first"); return IBFT_ERR_INVALID_ARG; }
+  size_t voted_words = 0;
+  for (auto& g : L->last_gdev) voted_words += g.n_words;
+  if (words_per_rank < bitmap_words_per_rank + voted_words + n_groups) { set_err("exchange buffer too small"); return IBFT_ERR_INVALID_ARG; }
+  CU(cudaSetDevice(e->p.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : L->stream;
+  peer_bufs pb{};
+  for (uint32_t r = 0; r < world; r++) pb.buf[r] = (uint32_t*)(uintptr_t)peer_bufs_in[r];
+  const uint32_t total = world * bitmap_words_per_rank + (uint32_t)voted_words + n_groups;
+  const uint32_t blocks = std::max(1u, std::min(64u, (total + 255u) / 256u));
+  k_quorum_exchange<<<blocks, 256, 0, st>>>(pb, world, rank, words_per_rank, bitmap_words_per_rank, (uint32_t)voted_words, n_groups, epoch,
+                                            /*spin_limit=*/400000u, (uint32_t*)d_bitmap_full, L->d_voted, L->d_nvalid,
+                                            (uint32_t*)d_timeout_flag);
   e->launches++;
   CU(cudaGetLastError());
   k_quorum_reduce<<<n_groups, IBFT_REDUCE_THREADS, 0, st>>>(L->d_groups, L->d_gdev, n_groups, e->d_slots, e->p.max_table_slots, L->d_voted, L->d_nvalid,

@@ -79,7 +79,10 @@ class ShardedVerifier:
     """
 
     def __init__(self, engine, n_global: int, groups: np.ndarray, world: int, rank: int, local_items: np.ndarray,
-                 local_arena: np.ndarray, stream=None):
+                 local_arena: np.ndarray, stream=None, exchange: str = "nccl"):
+        """exchange = "nccl": one all_gather_into_tensor + merge kernel (any backend / any topology);
+        exchange = "p2p": every rank's words live in a buffer its peers map over NVLink (CUDA IPC, one node, <= 8 ranks) and ONE
+        kernel publishes, waits for the peers and merges straight out of peer memory (ibft_quorum_exchange_device)."""
         from . import engine as _e
         self.e, self.n, self.world, self.rank = engine, n_global, world, rank
         self.lo, self.hi = shard_bounds(n_global, world, rank)
@@ -107,9 +110,50 @@ class ShardedVerifier:
         # the kernels index tuples and bitmap words by GLOBAL item number: hand them rebased pointers
         self.items_base = self.d_items.data_ptr() - self.lo * 128
         self.bitmap_base = self.d_local.data_ptr() - (self.lo // 32) * 4
+        self.exchange = exchange
+        if exchange == "p2p":
+            self.wpr = (self.per + self.W + 63) // 64 * 64                   # words per rank and parity
+            self.xbuf = torch.zeros(2 * self.wpr + 64, dtype=torch.int32, device=dev)   # [2][wpr] words, then the two flags
+            self.epoch = 0
+            self.d_full = torch.zeros(world * self.per, dtype=torch.int32, device=dev)
+            self.d_timeout = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.h_out = torch.zeros(self.d_results.numel() + 4 * world * self.per + 4, dtype=torch.uint8).pin_memory()
+            self._peers = [self.xbuf]
+            if world > 1:
+                from torch.multiprocessing import reductions
+                handles = [None] * world
+                dist.all_gather_object(handles, reductions.reduce_tensor(self.xbuf))   # CUDA IPC handle of my buffer
+                self._peers = [self.xbuf if r == rank else handles[r][0](*handles[r][1]) for r in range(world)]
+                dist.barrier()
+            self.peer_ptrs = [t.data_ptr() for t in self._peers]
+
+    def _enqueue_p2p(self):
+        st = self.stream.cuda_stream
+        self.epoch += 1
+        par = self.epoch & 1
+        with torch.cuda.stream(self.stream):
+            if self.h_items.numel():
+                self.d_items[: self.h_items.numel()].copy_(self.h_items, non_blocking=True)
+            if self.h_arena.numel():
+                self.d_arena[: self.h_arena.numel()].copy_(self.h_arena, non_blocking=True)
+            region = self.xbuf[par * self.wpr: (par + 1) * self.wpr]
+            region.zero_()
+            base = self.xbuf.data_ptr() + par * self.wpr * 4
+            if self.hi > self.lo:
+                self.e.verify_device(self.items_base, self.n, self.d_arena.data_ptr(), self.h_arena.numel(), self.lo, self.hi,
+                                     base - (self.lo // 32) * 4, 0, st)
+            self.e.quorum_mark_device(self.items_base, self.n, self.lo, self.hi, base - (self.lo // 32) * 4, base + self.per * 4, st)
+            self.e.quorum_exchange_device(self.peer_ptrs, self.rank, self.wpr, self.per, self.epoch, self.d_full.data_ptr(),
+                                          self.d_results.data_ptr(), self.d_timeout.data_ptr(), st)
+            nres = self.d_results.numel()
+            self.h_out[:nres].copy_(self.d_results, non_blocking=True)
+            self.h_out[nres: nres + 4 * self.world * self.per].copy_(self.d_full.view(torch.uint8), non_blocking=True)
+            self.h_out[nres + 4 * self.world * self.per:].copy_(self.d_timeout.view(torch.uint8), non_blocking=True)
 
     def enqueue(self):
         """H2D of the shard, kernels and the collective on self.stream; returns nothing (call finish() for the host copies)."""
+        if self.exchange == "p2p":
+            return self._enqueue_p2p()
         st = self.stream.cuda_stream
         with torch.cuda.stream(self.stream):
             if self.h_items.numel():
@@ -137,6 +181,12 @@ class ShardedVerifier:
         self.stream.synchronize()
         nres = self.d_results.numel()
         res = self.h_out[:nres].numpy().view(self.result_dtype).copy()
+        if self.exchange == "p2p":
+            nb = 4 * self.world * self.per
+            if int(self.h_out[nres + nb:].numpy().view(np.uint32)[0]):
+                raise RuntimeError("peer-memory exchange: a peer did not publish its round in time")
+            bm = self.h_out[nres: nres + nb].numpy().view(np.uint32)[: (self.n + 31) // 32].copy()
+            return res, bm
         bm = self.h_out[nres:].numpy().view(np.uint32)[: (self.n + 31) // 32].copy()
         return res, bm
 

@@ -219,6 +219,20 @@ int ibft_quorum_mark_device(ibft_engine* e, const void* d_items, uint32_t n, uin
 int ibft_quorum_merge_device(ibft_engine* e, const void* d_partials, uint32_t n_parts, uint32_t part_stride_words,
                              void* d_results, void* stream);
 
+/* The same exchange WITHOUT a library collective (one node, <= 8 ranks): every rank keeps its (bitmap words | partial) in an
+ * exchange buffer that its peers have mapped over NVLink (CUDA IPC / peer access; the caller exchanges the handles once).
+ *   buffer layout, uint32 words: [2 parities][words_per_rank], then flags[2]; words_per_rank >= bitmap_words_per_rank + W
+ *   (W = ibft_quorum_partial_words).  For round `epoch` (1, 2, 3, ...) a rank verifies its shard with the bitmap pointer rebased
+ *   into parity (epoch & 1) of ITS buffer and marks its votes behind the bitmap words of that parity (ibft_quorum_mark_device),
+ *   then calls this: ONE kernel publishes the rank's flag, waits (bounded) for the peers' flags, reads their words out of peer
+ *   memory -- OR-ing voted sets, summing counts, assembling the complete bitmap in d_bitmap_full (world x bitmap_words_per_rank
+ *   words) -- and the weighted reduce follows.  peer_bufs[r] = device address of rank r's buffer as mapped in THIS process.
+ *   *d_timeout_flag (device uint32, zeroed by the caller) becomes 1 when a peer did not publish in time: results are then
+ *   meaningless and the device is NOT left spinning. */
+int ibft_quorum_exchange_device(ibft_engine* e, const uint64_t* peer_bufs, uint32_t world, uint32_t rank, uint32_t words_per_rank,
+                                uint32_t bitmap_words_per_rank, uint32_t epoch, void* d_bitmap_full, void* d_results,
+                                void* d_timeout_flag, void* stream);
+
 /* Per-group voted set of the most recent reduce: bit i = validator i of the group's table has >= 1 valid item.
  * words_out: caller-allocated, (table_n+31)/32 words.  This is the bitmap core/validator_manager.go's quorum
  * check reads in the Go shim. */

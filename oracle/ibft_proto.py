@@ -74,8 +74,14 @@ class IbftMessage:  # messages.proto:24-44
     type: int = PREPREPARE
     payload: Payload = None
 
+    # set by the decoder for a message that arrived in a NON-canonical encoding (unknown fields, duplicates, ...): the exact bytes,
+    # because PayloadNoSig of such a message on a Go node is the protobuf re-marshal of what arrived, not of this model
+    _wire: Optional[bytes] = field(default=None, repr=False, compare=False)
+
     def payload_no_sig(self) -> bytes:
         """messages/proto/helper.go:13-27."""
+        if self._wire is not None:
+            return payload_no_sig_from_wire(self._wire)
         return encode_ibft_message(self, with_signature=False)
 
 
@@ -249,12 +255,15 @@ def _message_from(n) -> IbftMessage:
     elif 8 in f:
         g = f[8].fields
         m.payload = RoundChangeMessage(_proposal_from(g[1]) if 1 in g else None, _pc_from(g[2]) if 2 in g else None)
+    if n.raw is not None and encode_ibft_message(m) != n.raw:
+        m._wire = n.raw
     return m
 
 
 def _tree(buf: bytes, type_name: str):
     n = _Node()
-    _parse_into(n, bytes(buf), type_name)
+    n.raw = bytes(buf)
+    _parse_into(n, n.raw, type_name)
     return n
 
 
@@ -306,11 +315,12 @@ _MAX_DEPTH = 100  # protobuf-go's default recursion limit is 10,000; anything le
 
 
 class _Node:
-    __slots__ = ("fields", "unknown")
+    __slots__ = ("fields", "unknown", "raw")
 
     def __init__(self):
         self.fields = {}
         self.unknown = bytearray()
+        self.raw = None   # the bytes this node was parsed from; None once a second occurrence has been merged into it
 
 
 def _skip_group(buf: bytes, pos: int, number: int, depth: int) -> int:
@@ -383,6 +393,7 @@ def _parse_into(node: _Node, buf: bytes, type_name: str, depth: int = 0) -> None
             node.fields[num] = bytes(val)
         elif kind == "rep":
             child = _Node()
+            child.raw = bytes(val)
             _parse_into(child, val, spec[1], depth + 1)
             node.fields.setdefault(num, []).append(child)
         else:  # singular sub-message ("msg") or oneof member
@@ -392,6 +403,9 @@ def _parse_into(node: _Node, buf: bytes, type_name: str, depth: int = 0) -> None
             child = node.fields.get(num)
             if child is None:
                 child = node.fields[num] = _Node()
+                child.raw = bytes(val)
+            else:
+                child.raw = None
             _parse_into(child, val, spec[1], depth + 1)  # a second occurrence merges into the first
 
 

@@ -270,6 +270,11 @@ def test_sharded_verifier_pipeline_single_rank(big_engine):
     _results_equal(res, pin["results"])
     res2, bm2 = sv.run()                                   # the pipeline is re-runnable (buffers are reused)
     assert np.array_equal(bm2, bm) and res2.tobytes() == res.tobytes()
+    # the exchange as ONE kernel over (here: its own) peer memory instead of a library collective: same answers, several rounds
+    svp = sharding.ShardedVerifier(e, n, groups, 1, 0, li, la, torch.cuda.current_stream(), exchange="p2p")
+    for _ in range(3):
+        resp, bmp = svp.run()
+        assert np.array_equal(bmp, pin["bitmap"]) and resp.tobytes() == res.tobytes()
     # a rank's rebased shard verifies to exactly its slice of the bitmap
     for world, rank in ((2, 1), (8, 5), (8, 7)):
         lo, hi = sharding.shard_bounds(n, world, rank)

@@ -215,7 +215,10 @@ def test_raw_frame_mode_same_decisions_and_fallback():
     assert c.set_validators(height, vs.addrs, vs.powers) == 0
     c.set_state(height, 0, L.NEW_ROUND, None)
     frames = [enc(m) for m in prepares + commits]
-    frames[3] = frames[3] + b"\x48\x01"                        # unknown field 9 appended: decodes fine, not canonical
+    # unknown field 9 appended: decodes fine, not canonical.  protobuf-go keeps unknown fields through Clone + Marshal, so the bytes
+    # a Go node hashes for this message are NOT the ones its sender signed: invalid on every node (the device hands the frame back
+    # and the host re-marshals it the protobuf-go way; oracle/ibft_proto.py does the same)
+    frames[3] = frames[3] + b"\x48\x01"
     frames[5] = frames[5][:-1] + bytes([frames[5][-1] ^ 1])    # corrupted payload byte: canonical frame, bad signature
     inbound = [ip.decode_ibft_message(f) for f in frames]
     for m in inbound:
@@ -224,7 +227,17 @@ def test_raw_frame_mode_same_decisions_and_fallback():
     assert c.gpu_frames_handed_back() == 1
     for t in (ip.PREPARE, ip.COMMIT):
         assert c.store_senders(height, 0, t) == sorted(m.from_ for m in o.messages.maps[t].get(height, {}).get(0, {}).values())
-    assert c.num_messages(height, 0, ip.PREPARE) == len(prepares) - 1
+    assert c.num_messages(height, 0, ip.PREPARE) == len(prepares) - 2
+    # the same frame with the unknown field INSIDE the signed bytes is valid everywhere: sign the re-marshal of what will arrive
+    m = ip.decode_ibft_message(enc(prepares[7]))
+    m.signature = b""
+    framed = enc(m) + b"\x48\x01"
+    sig = wl.sign(vs.keys[8], co.keccak256(ip.payload_no_sig_from_wire(framed)))
+    cut = len(ip._f_msg(1, ip.encode_view(m.view)) + ip._f_bytes(2, m.from_))
+    framed = framed[:cut] + b"\x1a\x41" + sig + framed[cut:]    # signature TLV right after `from`
+    assert ip.decode_ibft_message(framed).signature == sig and ip.payload_no_sig_from_wire(framed).endswith(b"\x48\x01")
+    assert c.is_valid_validator(framed) is True
+    assert c.gpu_frames_handed_back() == 2
     c.close()
 
 
