@@ -1597,6 +1597,7 @@ struct lane {
 struct ibft_engine {
   ibft_engine_params p;
   lane lanes[IBFT_LANES];
+  uint32_t peer_enabled = 0;  // bit d: peer access to device d has been enabled (ibft_quorum_exchange_device)
   std::atomic<int> last_lane{0};  // lane of the most recently COMPLETED host-buffer call (ibft_last_item_status, ibft_get_voted_bitmap)
   slot_dev* d_slots = nullptr;
   std::vector<slot_host> slots;
@@ -2542,7 +2543,25 @@ extern "C" int ibft_quorum_exchange_device(ibft_engine* e, const uint64_t* peer_
   CU(cudaSetDevice(e->p.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : L->stream;
   peer_bufs pb{};
-  for (uint32_t r = 0; r < world; r++) pb.buf[r] = (uint32_t*)(uintptr_t)peer_bufs_in[r];
+  for (uint32_t r = 0; r < world; r++) {
+    pb.buf[r] = (uint32_t*)(uintptr_t)peer_bufs_in[r];
+    // a peer's buffer lives on another device (mapped into this process through CUDA IPC): this device must be allowed to
+    // dereference it -- peer access over NVLink is enabled once per device pair
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, pb.buf[r]) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != e->p.device) {
+      if (!(e->peer_enabled & (1u << pa.device))) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, e->p.device, pa.device));
+        if (!can) { set_err("device %d cannot access peer device %d", e->p.device, pa.device); return IBFT_ERR_CUDA; }
+        cudaError_t ce = cudaDeviceEnablePeerAccess(pa.device, 0);
+        if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) { set_err("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(ce)); return IBFT_ERR_CUDA; }
+        (void)cudaGetLastError();
+        e->peer_enabled |= 1u << pa.device;
+      }
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
   const uint32_t total = world * bitmap_words_per_rank + (uint32_t)voted_words + n_groups;
   const uint32_t blocks = std::max(1u, std::min(64u, (total + 255u) / 256u));
   k_quorum_exchange<<<blocks, 256, 0, st>>>(pb, world, rank, words_per_rank, bitmap_words_per_rank, (uint32_t)voted_words, n_groups, epoch,
