@@ -251,6 +251,7 @@ def strong_scaling_legs(args, ib, eng_weak, d, base_items, groups3, world, rank,
     try:
         svp = sharding.ShardedVerifier(eng_weak, n, groups3, world, rank, li, la, stream, exchange="p2p")
         ts, resp, bmp = timed(svp, args.latency_reps)
+        svp.close()
         if not np.array_equal(np.unpackbits(bmp.view(np.uint8), bitorder="little")[:n], gold) or resp.tobytes() != res.tobytes():
             raise SystemExit("bench: sharded 10k round (peer-memory exchange): results differ")
         out["round10k"]["peer_memory_exchange"] = {"p50_us": _pct(ts, 0.5), "p95_us": _pct(ts, 0.95), "reps": len(ts),
@@ -278,6 +279,7 @@ def strong_scaling_legs(args, ib, eng_weak, d, base_items, groups3, world, rank,
         try:
             sv5p = sharding.ShardedVerifier(eng5, n, groups5, world, rank, li, la, stream, exchange="p2p")
             tsp, resp, bmp = timed(sv5p, max(20, args.latency_reps // 4))
+            sv5p.close()
             if not np.array_equal(bmp, pin["bitmap"]) or resp.tobytes() != res.tobytes():
                 raise SystemExit("bench: sharded config 5 (peer-memory exchange): results differ")
             p2p5 = {"p50_us": _pct(tsp, 0.5), "p95_us": _pct(tsp, 0.95), "results_equal_nccl_path": True}

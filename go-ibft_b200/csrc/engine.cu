@@ -1597,7 +1597,6 @@ struct lane {
 struct ibft_engine {
   ibft_engine_params p;
   lane lanes[IBFT_LANES];
-  uint32_t peer_enabled = 0;  // bit d: peer access to device d has been enabled (ibft_quorum_exchange_device)
   std::atomic<int> last_lane{0};  // lane of the most recently COMPLETED host-buffer call (ibft_last_item_status, ibft_get_voted_bitmap)
   slot_dev* d_slots = nullptr;
   std::vector<slot_host> slots;
@@ -2526,6 +2525,53 @@ extern "C" int ibft_quorum_merge_device(ibft_engine* e, const void* d_partials, 
   return IBFT_OK;
 }
 
+// Exchange buffers of the peer-memory path: allocated by the engine (a plain cudaMalloc block, so that its IPC handle names
+// exactly this buffer), exported as a 64-byte CUDA IPC handle, and opened by the peers ON THEIR OWN DEVICE with lazy peer access --
+// which is what makes the mapping dereferenceable from the peer's kernels over NVLink.
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+extern "C" int ibft_exchange_alloc(ibft_engine* e, uint32_t words, void** d_buf_out, uint8_t handle_out[64]) {
+  if (!e || !d_buf_out || !handle_out || words == 0) { set_err("bad argument"); return IBFT_ERR_INVALID_ARG; }
+  CU(cudaSetDevice(e->p.device));
+  void* p = nullptr;
+  CU(cudaMalloc(&p, (size_t)words * 4));
+  CU(cudaMemset(p, 0, (size_t)words * 4));
+  cudaIpcMemHandle_t h;
+  cudaError_t ce = cudaIpcGetMemHandle(&h, p);
+  if (ce != cudaSuccess) { cudaFree(p); set_err("cudaIpcGetMemHandle: %s", cudaGetErrorString(ce)); return IBFT_ERR_CUDA; }
+  memcpy(handle_out, &h, 64);
+  *d_buf_out = p;
+  return IBFT_OK;
+}
+extern "C" int ibft_exchange_open(ibft_engine* e, const uint8_t handle[64], void** d_peer_out) {
+  if (!e || !handle || !d_peer_out) { set_err("bad argument"); return IBFT_ERR_INVALID_ARG; }
+  CU(cudaSetDevice(e->p.device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *d_peer_out = p;
+  return IBFT_OK;
+}
+extern "C" int ibft_exchange_close(ibft_engine* e, void* d_peer) {
+  if (!e || !d_peer) { set_err("bad argument"); return IBFT_ERR_INVALID_ARG; }
+  CU(cudaSetDevice(e->p.device));
+  CU(cudaIpcCloseMemHandle(d_peer));
+  return IBFT_OK;
+}
+extern "C" int ibft_exchange_free(ibft_engine* e, void* d_buf) {
+  if (!e || !d_buf) { set_err("bad argument"); return IBFT_ERR_INVALID_ARG; }
+  CU(cudaSetDevice(e->p.device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaFree(d_buf));
+  return IBFT_OK;
+}
+extern "C" int ibft_exchange_clear(ibft_engine* e, void* d_buf, uint32_t word_off, uint32_t words, void* stream) {
+  if (!e || !d_buf) { set_err("bad argument"); return IBFT_ERR_INVALID_ARG; }
+  CU(cudaSetDevice(e->p.device));
+  CU(cudaMemsetAsync((uint32_t*)d_buf + word_off, 0, (size_t)words * 4, stream ? (cudaStream_t)stream : e->lanes[0].stream));
+  return IBFT_OK;
+}
+
 extern "C" int ibft_quorum_exchange_device(ibft_engine* e, const uint64_t* peer_bufs_in, uint32_t world, uint32_t rank,
                                            uint32_t words_per_rank, uint32_t bitmap_words_per_rank, uint32_t epoch, void* d_bitmap_full,
                                            void* d_results, void* d_timeout_flag, void* stream) {
@@ -2545,22 +2591,6 @@ extern "C" int ibft_quorum_exchange_device(ibft_engine* e, const uint64_t* peer_
   peer_bufs pb{};
   for (uint32_t r = 0; r < world; r++) {
     pb.buf[r] = (uint32_t*)(uintptr_t)peer_bufs_in[r];
-    // a peer's buffer lives on another device (mapped into this process through CUDA IPC): this device must be allowed to
-    // dereference it -- peer access over NVLink is enabled once per device pair
-    cudaPointerAttributes pa;
-    if (cudaPointerGetAttributes(&pa, pb.buf[r]) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != e->p.device) {
-      if (!(e->peer_enabled & (1u << pa.device))) {
-        int can = 0;
-        CU(cudaDeviceCanAccessPeer(&can, e->p.device, pa.device));
-        if (!can) { set_err("device %d cannot access peer device %d", e->p.device, pa.device); return IBFT_ERR_CUDA; }
-        cudaError_t ce = cudaDeviceEnablePeerAccess(pa.device, 0);
-        if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) { set_err("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(ce)); return IBFT_ERR_CUDA; }
-        (void)cudaGetLastError();
-        e->peer_enabled |= 1u << pa.device;
-      }
-    } else {
-      (void)cudaGetLastError();
-    }
   }
   const uint32_t total = world * bitmap_words_per_rank + (uint32_t)voted_words + n_groups;
   const uint32_t blocks = std::max(1u, std::min(64u, (total + 255u) / 256u));

@@ -32,6 +32,7 @@ EXPORTS = [
     "ibft_abi_version", "ibft_last_error", "ibft_engine_create", "ibft_engine_destroy", "ibft_engine_device_info",
     "ibft_set_validators", "ibft_get_quorum", "ibft_verify_batch", "ibft_verify_batch_ex", "ibft_last_item_status", "ibft_verify_submit", "ibft_verify_poll",
     "ibft_verify_wait", "ibft_bind_groups", "ibft_verify_batch_device", "ibft_quorum_reduce_device", "ibft_quorum_partial_words", "ibft_quorum_mark_device", "ibft_quorum_merge_device", "ibft_quorum_exchange_device",
+    "ibft_exchange_alloc", "ibft_exchange_open", "ibft_exchange_close", "ibft_exchange_free", "ibft_exchange_clear",
     "ibft_get_voted_bitmap", "ibft_keccak256_batch", "ibft_proposal_hash_batch", "ibft_sign_batch", "ibft_engine_launch_count", "ibft_set_recover_path", "ibft_refresh_key_tables", "ibft_probe_int_peak", "ibft_debug_op", "ibft_debug_ctable",
 ]
 
@@ -90,6 +91,11 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.ibft_quorum_mark_device.argtypes = [c_void_p, c_void_p, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
     lib.ibft_quorum_merge_device.argtypes = [c_void_p, c_void_p, c_uint32, c_uint32, c_void_p, c_void_p]
     lib.ibft_quorum_exchange_device.argtypes = [c_void_p, c_void_p, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ibft_exchange_alloc.argtypes = [c_void_p, c_uint32, POINTER(c_void_p), c_void_p]
+    lib.ibft_exchange_open.argtypes = [c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.ibft_exchange_close.argtypes = [c_void_p, c_void_p]
+    lib.ibft_exchange_free.argtypes = [c_void_p, c_void_p]
+    lib.ibft_exchange_clear.argtypes = [c_void_p, c_void_p, c_uint32, c_uint32, c_void_p]
     lib.ibft_get_voted_bitmap.argtypes = [c_void_p, c_uint32, c_void_p, c_uint32]
     lib.ibft_keccak256_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_uint32, c_void_p]
     lib.ibft_proposal_hash_batch.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]
@@ -281,6 +287,26 @@ class Engine:
         arr = (c_uint64 * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
         self._check(self.lib.ibft_quorum_exchange_device(self.handle, arr, len(peer_ptrs), rank, words_per_rank, bitmap_words_per_rank, epoch,
                                                          d_bitmap_full, d_results, d_timeout_flag, stream or None))
+
+    def exchange_alloc(self, words: int) -> tuple[int, bytes]:
+        """(device address, 64-byte CUDA IPC handle) of a fresh zeroed exchange buffer"""
+        p, h = c_void_p(), (ctypes.c_uint8 * 64)()
+        self._check(self.lib.ibft_exchange_alloc(self.handle, words, ctypes.byref(p), h))
+        return int(p.value), bytes(h)
+
+    def exchange_open(self, handle: bytes) -> int:
+        p, h = c_void_p(), (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+        self._check(self.lib.ibft_exchange_open(self.handle, h, ctypes.byref(p)))
+        return int(p.value)
+
+    def exchange_close(self, d_peer: int):
+        self._check(self.lib.ibft_exchange_close(self.handle, c_void_p(d_peer)))
+
+    def exchange_free(self, d_buf: int):
+        self._check(self.lib.ibft_exchange_free(self.handle, c_void_p(d_buf)))
+
+    def exchange_clear(self, d_buf: int, word_off: int, words: int, stream: int = 0):
+        self._check(self.lib.ibft_exchange_clear(self.handle, c_void_p(d_buf), word_off, words, stream or None))
 
     def voted_bitmap(self, group: int, n_validators: int) -> np.ndarray:
         words = np.zeros((n_validators + 31) // 32, dtype=np.uint32)

@@ -113,19 +113,32 @@ class ShardedVerifier:
         self.exchange = exchange
         if exchange == "p2p":
             self.wpr = (self.per + self.W + 63) // 64 * 64                   # words per rank and parity
-            self.xbuf = torch.zeros(2 * self.wpr + 64, dtype=torch.int32, device=dev)   # [2][wpr] words, then the two flags
+            # [2][wpr] words, then the two flags: an engine-owned cudaMalloc block whose IPC handle the peers open on THEIR device
+            self.xbuf_ptr, handle = engine.exchange_alloc(2 * self.wpr + 64)
             self.epoch = 0
             self.d_full = torch.zeros(world * self.per, dtype=torch.int32, device=dev)
             self.d_timeout = torch.zeros(1, dtype=torch.int32, device=dev)
             self.h_out = torch.zeros(self.d_results.numel() + 4 * world * self.per + 4, dtype=torch.uint8).pin_memory()
-            self._peers = [self.xbuf]
+            self.peer_ptrs = [self.xbuf_ptr]
             if world > 1:
-                from torch.multiprocessing import reductions
                 handles = [None] * world
-                dist.all_gather_object(handles, reductions.reduce_tensor(self.xbuf))   # CUDA IPC handle of my buffer
-                self._peers = [self.xbuf if r == rank else handles[r][0](*handles[r][1]) for r in range(world)]
+                dist.all_gather_object(handles, handle)
+                self.peer_ptrs = [self.xbuf_ptr if r == rank else engine.exchange_open(handles[r]) for r in range(world)]
                 dist.barrier()
-            self.peer_ptrs = [t.data_ptr() for t in self._peers]
+
+    def close(self):
+        """unmap the peers' exchange buffers and free this rank's (p2p only; collective: every rank calls it)"""
+        if self.exchange == "p2p" and getattr(self, "xbuf_ptr", 0):
+            self.stream.synchronize()
+            if self.world > 1:
+                dist.barrier()
+            for r, p in enumerate(self.peer_ptrs):
+                if r != self.rank:
+                    self.e.exchange_close(p)
+            if self.world > 1:
+                dist.barrier()
+            self.e.exchange_free(self.xbuf_ptr)
+            self.xbuf_ptr = 0
 
     def _enqueue_p2p(self):
         st = self.stream.cuda_stream
@@ -136,9 +149,8 @@ class ShardedVerifier:
                 self.d_items[: self.h_items.numel()].copy_(self.h_items, non_blocking=True)
             if self.h_arena.numel():
                 self.d_arena[: self.h_arena.numel()].copy_(self.h_arena, non_blocking=True)
-            region = self.xbuf[par * self.wpr: (par + 1) * self.wpr]
-            region.zero_()
-            base = self.xbuf.data_ptr() + par * self.wpr * 4
+            self.e.exchange_clear(self.xbuf_ptr, par * self.wpr, self.wpr, st)
+            base = self.xbuf_ptr + par * self.wpr * 4
             if self.hi > self.lo:
                 self.e.verify_device(self.items_base, self.n, self.d_arena.data_ptr(), self.h_arena.numel(), self.lo, self.hi,
                                      base - (self.lo // 32) * 4, 0, st)

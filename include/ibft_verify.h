@@ -229,6 +229,16 @@ int ibft_quorum_merge_device(ibft_engine* e, const void* d_partials, uint32_t n_
  *   words) -- and the weighted reduce follows.  peer_bufs[r] = device address of rank r's buffer as mapped in THIS process.
  *   *d_timeout_flag (device uint32, zeroed by the caller) becomes 1 when a peer did not publish in time: results are then
  *   meaningless and the device is NOT left spinning. */
+/* Exchange buffers.  The engine allocates one (zeroed, `words` uint32 words = 2 * words_per_rank + 2 flags, rounded up) and
+ * exports its 64-byte CUDA IPC handle; the caller passes the handle to the other ranks (any side channel), and every rank opens
+ * its peers' handles ON ITS OWN DEVICE with lazy peer access -- the resulting address goes into peer_bufs[].  A rank's own entry
+ * is the address ibft_exchange_alloc returned.  ibft_exchange_clear zeroes a word range on a stream (the parity region, before
+ * the shard is verified into it). */
+int ibft_exchange_alloc(ibft_engine* e, uint32_t words, void** d_buf_out, uint8_t handle_out[64]);
+int ibft_exchange_open(ibft_engine* e, const uint8_t handle[64], void** d_peer_out);
+int ibft_exchange_close(ibft_engine* e, void* d_peer);
+int ibft_exchange_free(ibft_engine* e, void* d_buf);
+int ibft_exchange_clear(ibft_engine* e, void* d_buf, uint32_t word_off, uint32_t words, void* stream);
 int ibft_quorum_exchange_device(ibft_engine* e, const uint64_t* peer_bufs, uint32_t world, uint32_t rank, uint32_t words_per_rank,
                                 uint32_t bitmap_words_per_rank, uint32_t epoch, void* d_bitmap_full, void* d_results,
                                 void* d_timeout_flag, void* stream);

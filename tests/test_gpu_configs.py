@@ -275,6 +275,7 @@ def test_sharded_verifier_pipeline_single_rank(big_engine):
     for _ in range(3):
         resp, bmp = svp.run()
         assert np.array_equal(bmp, pin["bitmap"]) and resp.tobytes() == res.tobytes()
+    svp.close()
     # a rank's rebased shard verifies to exactly its slice of the bitmap
     for world, rank in ((2, 1), (8, 5), (8, 7)):
         lo, hi = sharding.shard_bounds(n, world, rank)
