@@ -14,7 +14,7 @@ pass/fail bitmap words) -> K3 quorum kernels over the complete bitmap.
   cpu_baseline / --impl reference   the C oracle (a port; the Go reference has no crypto and no toolchain here) on the
           box's host cores, on a bounded sample of the same workload.
   strong_scaling  ONE 10,000-seal round and ONE config-5 backlog (100k messages, 16 heights x 10k validators) split over the N
-          ranks, every rank holding only its shard: host-to-host latency p50/p95 per N (go-ibft_b200/sharding.py ShardedVerifier)
+          ranks, every rank holding only its shard: device-timed latency (H2D .. D2H) p50/p95 per N (go-ibft_b200/sharding.py ShardedVerifier)
   ingress   64 threads of single-message IsValidValidator calls through the reference-facing verifier (the coalescer)
 """
 from __future__ import annotations
@@ -213,22 +213,34 @@ def strong_scaling_legs(args, ib, eng_weak, d, base_items, groups3, world, rank,
     import torch
     import torch.distributed as dist
     sharding = importlib.import_module("go-ibft_b200.sharding")
-    out = {"n_gpus": world, "timing": "wall clock around barrier .. results+bitmap on the host, max over ranks per repetition",
+    out = {"n_gpus": world, "timing": "CUDA events on the rank's stream around H2D of the shard .. kernels .. exchange .. D2H of results+bitmap, after a barrier; max over ranks per repetition",
            "collective": "one all_gather_into_tensor of (bitmap words | partial voted sets | valid counts) per round"}
 
     def timed(sv, reps):
-        ts = []
+        """per call: barrier, then H2D of the shard + kernels + exchange + D2H of the results, timed ON THE DEVICE (CUDA events on the
+        stream everything is enqueued on), max over ranks per repetition.  A peer-memory exchange that times out on one rank is recorded
+        and agreed on by all ranks after the loop (the barrier pattern stays intact), then raised everywhere."""
+        ts, failed, res, bm = [], 0, None, None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for i in range(reps + 5):
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            res, bm = sv.run()
-            ts.append((time.perf_counter() - t0) * 1e6)
-        t = torch.tensor(ts[5:], dtype=torch.float64, device="cuda")
+            ev0.record(sv.stream)
+            sv.enqueue()
+            ev1.record(sv.stream)
+            try:
+                res, bm = sv.finish()
+            except RuntimeError:
+                failed = 1
+            ts.append(ev0.elapsed_time(ev1) * 1e3)
+        t = torch.tensor(ts[5:] + [float(failed)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return [float(x) for x in t.cpu()], res, bm
+        t = t.cpu()
+        if float(t[-1]) != 0.0:
+            raise RuntimeError("peer-memory exchange timed out on at least one rank")
+        return [float(x) for x in t[:-1]], res, bm
 
     # ---- (a) one 10,000-seal round (config 3's committed seals)
     seal_group = list(d["groups"]).index("COMMIT_SEAL")

@@ -1,7 +1,9 @@
 #!/bin/bash
+# occupancy variants of k_recover (tables in a global scratch): quick timing + bitmap check
 mkdir -p gpurun_out
-timeout 600 python -m pytest "tests/test_gpu_configs.py::test_sharded_verifier_pipeline_single_rank" -x -q > gpurun_out/dbg_p2p.txt 2>&1
-echo "plain rc=$?" >> gpurun_out/dbg_p2p.txt
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest "tests/test_gpu_configs.py::test_sharded_verifier_pipeline_single_rank" -x -q > gpurun_out/dbg_p2p_memcheck.txt 2>&1
-echo "memcheck rc=$?" >> gpurun_out/dbg_p2p_memcheck.txt
-tail -15 gpurun_out/dbg_p2p.txt; grep -n "Invalid\|at \|by \|=========" gpurun_out/dbg_p2p_memcheck.txt | head -30
+: > gpurun_out/quick_r02_occ.jsonl
+for v in default gtab3 gtab4 gtab5; do
+  if [ $v = default ]; then unset IBFT_LIB; else export IBFT_LIB=$PWD/go-ibft_b200/variants/lib_$v.so; fi
+  timeout 300 python tools/quick_bench.py 20 >> gpurun_out/quick_r02_occ.jsonl 2>> gpurun_out/quick_r02_occ.err
+done
+cat gpurun_out/quick_r02_occ.jsonl
