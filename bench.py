@@ -812,9 +812,9 @@ def main():
                  "gpu_launches": int(eng_k.launch_count() - lk0),
                  "round10k_p50_us": _pct(lat_known, 0.5), "round10k_p95_us": _pct(lat_known, 0.95),
                  "round10k_all_valid_p50_us": _pct(lat_known_ok, 0.5), "round10k_all_valid_items": int(len(seals_ok)),
-                 "round10k_kernel": "k_verify_split (chain + helper warps, verification against the learned keys) + k_recover_qsplit on the worklist",
+                 "round10k_kernel": "k_verify_known<32> (one-warp CTAs, verification against the validator's comb table: 51 additions, no doubling) + k_recover_qsplit on the worklist",
                  "bitmap_matches_golden": bool(np.array_equal(np.unpackbits(bm_k.view(np.uint8), bitorder="little")[:n_global], np.tile(golden_bits, reps)[:n_global])),
-                 "note": "engine flag IBFT_FLAG_KEY_CACHE: k_verify_known (ECDSA verification against the validator's learned key) + k_recover on the "
+                 "note": "engine flag IBFT_FLAG_KEY_CACHE: k_verify_known (ECDSA verification against the learned key through a per-validator comb table, 136 KiB each) + k_recover on the "
                          "worklist of everything not accepted; verdicts are the recover path's by construction; the first (cold) pass over "
                          "a validator set runs at the headline rate"}
         eng_k.close()

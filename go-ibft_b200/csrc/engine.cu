@@ -49,14 +49,15 @@ struct slot_dev {
   uint32_t n;
   uint32_t valid;
   // key registry (engine flag IBFT_FLAG_KEY_CACHE; all nullptr otherwise), validator-index order:
-  uint32_t* key_state;     // 0 = unknown, 1 = key learned from a successful recovery, 2 = table of multiples built
+  uint32_t* key_state;     // 0 = unknown, 1 = key learned from a successful recovery, 3 = table being built, 2 = comb table built
   uint32_t* key_xy;        // n x 16 words: affine public key
-  uint32_t* key_tab;       // n x 128 entries x 16 words: {1..128} * Q, affine (verify_core.cuh build_keytab)
+  uint32_t* key_tab;       // n x IBFT_KEYTAB_WORDS: per validator 17 comb positions x 128 entries x 16 words, affine (build_keytab_pos)
   uint32_t* learn_count;   // number of keys learned so far (the host compares it with the number of tables built)
 };
 #define IBFT_KEY_UNKNOWN 0u
 #define IBFT_KEY_LEARNED 1u
 #define IBFT_KEY_READY 2u
+#define IBFT_KEY_BUILDING 3u  // claimed by a table-build pass (refresh_key_tables_locked)
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
@@ -265,20 +266,21 @@ k_recover(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __
 // path in a second, dense launch of k_recover (so a warp never walks both window loops, and every verdict is the recover
 // path's verdict).  Items that can never be valid (malformed, unknown group, signer not in the set) are settled here.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(IBFT_BLOCK, IBFT_MIN_BLOCKS)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (IBFT_MIN_BLOCKS * IBFT_BLOCK) / BLOCK)
 k_verify_known(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_t* __restrict__ arena, size_t arena_len,
                uint32_t shard_lo, uint32_t shard_hi, const ibft_group_desc* __restrict__ groups, uint32_t n_groups,
                const slot_dev* __restrict__ slots, uint32_t n_slots, uint32_t* __restrict__ bitmap,
                uint8_t* __restrict__ status, const uint32_t* __restrict__ ctable, vote_sink sink, uint32_t* __restrict__ worklist) {
-  __shared__ uint32_t s_items[IBFT_BLOCK * IBFT_ITEM_ROW_WORDS];
+  __shared__ uint32_t s_items[BLOCK * IBFT_ITEM_ROW_WORDS];
   const uint32_t tid = threadIdx.x;
-  const uint32_t base = shard_lo + blockIdx.x * IBFT_BLOCK;
+  const uint32_t base = shard_lo + blockIdx.x * BLOCK;
   {
     const uint4* src = reinterpret_cast<const uint4*>(items + base);
-    uint32_t avail = base < shard_hi ? min((uint32_t)IBFT_BLOCK, shard_hi - base) : 0u;
+    uint32_t avail = base < shard_hi ? min((uint32_t)BLOCK, shard_hi - base) : 0u;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      uint32_t q = tid + k * IBFT_BLOCK;
+      uint32_t q = tid + k * BLOCK;
       uint32_t row = q >> 3, col = q & 7;
       if (row < avail) {
         uint4 v = __ldg(src + q);
@@ -310,7 +312,7 @@ k_verify_known(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
       if (ready) {
         gtab_view G{g_gtable};
         G.comb = ctable;
-        gtab_view Qt{slots[slot].key_tab + (size_t)v * IBFT_KEYTAB_ENTRIES * IBFT_GTAB_ENTRY_WORDS};
+        gtab_view Qt{slots[slot].key_tab + (size_t)v * IBFT_KEYTAB_WORDS};
         ok = ecdsa_verify_known(ri, G, Qt);
       }
       if (ok) record_vote(sink, groups, it.group, v);
@@ -849,7 +851,7 @@ k_verify_split(const ibft_sig_item* __restrict__ items, uint32_t n, const uint8_
     dg.kneg[2] = dg.kneg[3] = false;
     vslot = s_slot[27 * S + i];
     const slot_dev& sd = slots[vslot >> 16];
-    gtab_view Qt{sd.key_tab + (size_t)(vslot & 0xFFFFu) * IBFT_KEYTAB_ENTRIES * IBFT_GTAB_ENTRY_WORDS};
+    gtab_view Qt{sd.key_tab + (size_t)(vslot & 0xFFFFu) * IBFT_KEYTAB_WORDS};
     acc = ecmult_streams_known(dg, G, Qt, false);
   }
   named_bar_sync(1 + IBFT_SPLIT_CHAINS + warp, 64);  // u1*G is posted
@@ -1338,22 +1340,76 @@ k_build_ctable(uint32_t* __restrict__ out) {  // blockIdx.y = comb position: ent
 #endif
 
 #if IBFT_WC > 0
-// key registry: tables of multiples for every validator of `slot` whose key has been learned but whose table is missing.
-// One thread per validator (128 additions + 128 inversions each: ~3 ms for a whole 10k-validator set, once per validator).
+// key registry: comb tables for every validator of `slot` whose key has been learned but whose table is missing.  One thread
+// per (validator, comb position): 8*pos doublings, 128 additions and 128 inversions each -- a whole 10k-validator set
+// (170,000 threads, 21.8 M table entries, 1.39 GB) is built once per validator set; k_keytabs_ready then publishes the tables.
 __global__ void __launch_bounds__(64)
 k_build_keytabs(const slot_dev* __restrict__ slots, uint32_t slot) {
   const slot_dev& s = slots[slot];
-  uint32_t v = blockIdx.x * 64 + threadIdx.x;
-  if (s.key_state == nullptr || v >= s.n || s.key_state[v] != IBFT_KEY_LEARNED) return;
+  const uint32_t t = blockIdx.x * 64 + threadIdx.x;
+  const uint32_t v = t / IBFT_KEYTAB_POSITIONS, pos = t % IBFT_KEYTAB_POSITIONS;
+  if (s.key_state == nullptr || v >= s.n || s.key_state[v] != IBFT_KEY_BUILDING) return;
   aff Q;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     Q.x.v[i] = s.key_xy[16 * (size_t)v + i];
     Q.y.v[i] = s.key_xy[16 * (size_t)v + 8 + i];
   }
-  build_keytab(Q, s.key_tab + (size_t)v * IBFT_KEYTAB_ENTRIES * IBFT_GTAB_ENTRY_WORDS);
+  build_keytab_pos(Q, (int)pos, s.key_tab + (size_t)v * IBFT_KEYTAB_WORDS + (size_t)pos * IBFT_KEYTAB_ENTRIES * IBFT_GTAB_ENTRY_WORDS);
+}
+// state steps around the build, one launch each on the same stream: LEARNED -> BUILDING (claim: the set of validators this pass
+// builds is fixed here -- recover kernels of another lane may keep learning keys meanwhile, those wait for the next pass),
+// BUILDING -> READY (publish)
+__global__ void __launch_bounds__(256)
+k_keytabs_step(const slot_dev* __restrict__ slots, uint32_t slot, uint32_t from, uint32_t to) {
+  const slot_dev& s = slots[slot];
+  const uint32_t v = blockIdx.x * 256 + threadIdx.x;
+  if (s.key_state != nullptr && v < s.n && s.key_state[v] == from) s.key_state[v] = to;
+}
+#endif
+
+#if IBFT_WC > 0
+// key registry carry-over (ibft_set_validators): consensus moves to the next height with (mostly) the same validators, and a
+// key belongs to an ADDRESS, not to a height.  One CTA per validator of the new table (rank r of its sorted address table):
+// look the address up in the donor table; if the donor holds a finished comb table for it, copy key + table (136 KiB, 16-byte
+// loads) and publish.  A 10k-validator set is 1.39 GB of device-to-device copy, once per height.
+__global__ void __launch_bounds__(256)
+k_carry_keys(slot_dev dst, slot_dev src) {
+  __shared__ int s_src;
+  const uint32_t r = blockIdx.x;
+  const uint32_t* k = dst.keys + 6 * (size_t)r;
+  const uint32_t v = __ldg(k + 5);
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = (int)src.n - 1, found = -1;
+    while (lo <= hi && found < 0) {
+      int mid = (lo + hi) >> 1;
+      const uint32_t* q = src.keys + 6 * (size_t)mid;
+      int cmp = 0;
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        uint32_t a = __ldg(q + i), b = __ldg(k + i);
+        if (cmp == 0 && a != b) cmp = a < b ? -1 : 1;
+      }
+      if (cmp == 0) found = (int)__ldg(q + 5);
+      else if (cmp < 0) lo = mid + 1;
+      else hi = mid - 1;
+    }
+    if (found >= 0 && src.key_state[found] != IBFT_KEY_READY) found = -1;
+    s_src = found;
+  }
+  __syncthreads();
+  const int sv = s_src;
+  if (sv < 0) return;
+  const uint4* from = reinterpret_cast<const uint4*>(src.key_tab + (size_t)sv * IBFT_KEYTAB_WORDS);
+  uint4* to = reinterpret_cast<uint4*>(dst.key_tab + (size_t)v * IBFT_KEYTAB_WORDS);
+  for (uint32_t i = threadIdx.x; i < IBFT_KEYTAB_WORDS / 4; i += 256) to[i] = from[i];
+  if (threadIdx.x < 16) dst.key_xy[16 * (size_t)v + threadIdx.x] = src.key_xy[16 * (size_t)sv + threadIdx.x];
   __threadfence();
-  s.key_state[v] = IBFT_KEY_READY;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dst.key_state[v] = IBFT_KEY_READY;
+    atomicAdd(dst.learn_count, 1u);
+  }
 }
 #endif
 
@@ -1878,32 +1934,42 @@ extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t
   CU(cudaSetDevice(e->p.device));
   slot_host& s = e->slots[table_slot];
   CU(cudaDeviceSynchronize());
-  if (s.d_keys) { cudaFree(s.d_keys); s.d_keys = nullptr; }
-  if (s.d_powers) { cudaFree(s.d_powers); s.d_powers = nullptr; }
-  cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab);
-  s.d_key_state = s.d_key_xy = s.d_key_tab = s.d_learn_count = nullptr;
-  s.built_count = 0;
-  s.valid = false;
-  CU(cudaMalloc(&s.d_keys, std::max<size_t>(keys.size(), 6) * 4));
-  CU(cudaMalloc(&s.d_powers, std::max<size_t>(powers.size(), 4) * 8));
-  if (n) {
-    CU(cudaMemcpy(s.d_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s.d_powers, powers.data(), powers.size() * 8, cudaMemcpyHostToDevice));
+  // the slot's previous content stays alive until its key registry has been carried over
+  slot_host old = s;
+  slot_dev old_dev = e->slots_shadow[table_slot];
+  s = slot_host{};
+  int rc_alloc = IBFT_OK;
+  do {
+    cudaError_t ce = cudaMalloc(&s.d_keys, std::max<size_t>(keys.size(), 6) * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc(&s.d_powers, std::max<size_t>(powers.size(), 4) * 8);
+    if (ce == cudaSuccess && n) ce = cudaMemcpy(s.d_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && n) ce = cudaMemcpy(s.d_powers, powers.data(), powers.size() * 8, cudaMemcpyHostToDevice);
+#if IBFT_WC > 0
+    if (ce == cudaSuccess && (e->p.flags & IBFT_FLAG_KEY_CACHE) && n) {
+      ce = cudaMalloc(&s.d_key_state, (size_t)n * 4);
+      if (ce == cudaSuccess) ce = cudaMalloc(&s.d_key_xy, (size_t)n * 64);
+      if (ce == cudaSuccess) ce = cudaMalloc(&s.d_key_tab, (size_t)n * IBFT_KEYTAB_WORDS * 4);  // 136 KiB per validator (comb)
+      if (ce == cudaSuccess) ce = cudaMemset(s.d_key_state, 0, (size_t)n * 4);
+      s.d_learn_count = e->d_learn_counts + table_slot;
+    }
+#endif
+    if (ce != cudaSuccess) {
+      set_err("validator table of %u validators%s: %s", n, (e->p.flags & IBFT_FLAG_KEY_CACHE) ? " with its key registry (136 KiB per validator)" : "",
+              cudaGetErrorString(ce));
+      rc_alloc = ce == cudaErrorMemoryAllocation ? IBFT_ERR_CAPACITY : IBFT_ERR_CUDA;
+      (void)cudaGetLastError();
+    }
+  } while (0);
+  if (rc_alloc != IBFT_OK) {  // the slot keeps its previous table
+    cudaFree(s.d_keys); cudaFree(s.d_powers); cudaFree(s.d_key_state); cudaFree(s.d_key_xy); cudaFree(s.d_key_tab);
+    s = old;
+    return rc_alloc;
   }
+  if (s.d_learn_count) CU(cudaMemset(s.d_learn_count, 0, 4));  // a new validator set starts with an empty registry (then the carry-over)
   s.n = n;
   s.height = height;
   memcpy(s.quorum, q, sizeof s.quorum);
   s.valid = true;
-#if IBFT_WC > 0
-  if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && n) {  // a new validator set starts with an empty key registry
-    CU(cudaMalloc(&s.d_key_state, (size_t)n * 4));
-    CU(cudaMalloc(&s.d_key_xy, (size_t)n * 64));
-    CU(cudaMalloc(&s.d_key_tab, (size_t)n * IBFT_KEYTAB_ENTRIES * 64));
-    s.d_learn_count = e->d_learn_counts + table_slot;
-    CU(cudaMemset(s.d_key_state, 0, (size_t)n * 4));
-    CU(cudaMemset(s.d_learn_count, 0, 4));
-  }
-#endif
   slot_dev sd{};
   sd.keys = s.d_keys;
   sd.powers = s.d_powers;
@@ -1914,6 +1980,30 @@ extern "C" int ibft_set_validators(ibft_engine* e, uint32_t table_slot, uint64_t
   memcpy(sd.quorum, q, sizeof sd.quorum);
   sd.n = n;
   sd.valid = 1;
+#if IBFT_WC > 0
+  if (s.d_key_state) {
+    // carry the keys over from the donor table: the resident table of the greatest height that has a registry (the previous
+    // block, normally) -- this slot's previous content included
+    const slot_dev* donor = nullptr;
+    uint64_t best_h = 0;
+    if (old.valid && old.d_key_state && old.n) { donor = &old_dev; best_h = old.height; }
+    for (uint32_t k = 0; k < e->p.max_table_slots; k++) {
+      const slot_host& o = e->slots[k];
+      if (k == table_slot || !o.valid || !o.d_key_state || !o.n) continue;
+      if (donor == nullptr || o.height > best_h) { donor = &e->slots_shadow[k]; best_h = o.height; }
+    }
+    if (donor != nullptr) {
+      k_carry_keys<<<n, 256>>>(sd, *donor);
+      e->launches++;
+      CU(cudaGetLastError());
+      CU(cudaDeviceSynchronize());
+      CU(cudaMemcpy(&s.built_count, s.d_learn_count, 4, cudaMemcpyDeviceToHost));  // carried keys come with finished tables
+    }
+  }
+#endif
+  if (old.d_keys) cudaFree(old.d_keys);
+  if (old.d_powers) cudaFree(old.d_powers);
+  cudaFree(old.d_key_state); cudaFree(old.d_key_xy); cudaFree(old.d_key_tab);
   e->slots_shadow[table_slot] = sd;
   CU(cudaMemcpy(e->d_slots + table_slot, &sd, sizeof sd, cudaMemcpyHostToDevice));
   return IBFT_OK;
@@ -1936,8 +2026,10 @@ static int refresh_key_tables_locked(ibft_engine* e, lane* L, uint32_t* n_ready_
       if (!s.valid || !s.d_learn_count) continue;
       uint32_t learned = e->h_learn_counts[slot];
       if (learned > s.built_count) {
-        k_build_keytabs<<<(s.n + 63) / 64, 64, 0, L->stream>>>(e->d_slots, slot);
-        e->launches++;
+        k_keytabs_step<<<(s.n + 255) / 256, 256, 0, L->stream>>>(e->d_slots, slot, IBFT_KEY_LEARNED, IBFT_KEY_BUILDING);
+        k_build_keytabs<<<(uint32_t)(((size_t)s.n * IBFT_KEYTAB_POSITIONS + 63) / 64), 64, 0, L->stream>>>(e->d_slots, slot);
+        k_keytabs_step<<<(s.n + 255) / 256, 256, 0, L->stream>>>(e->d_slots, slot, IBFT_KEY_BUILDING, IBFT_KEY_READY);
+        e->launches += 3;
         CU(cudaGetLastError());
         s.built_count = learned;
         built = true;
@@ -2016,8 +2108,19 @@ static int launch_recover(ibft_engine* e, lane* L, const ibft_sig_item* d_items,
   //                            throughput kernel
   const uint32_t cnt = hi - lo;
   int path = forced_path != IBFT_PATH_AUTO ? forced_path : e->recover_path.load();
+  // key-registry path possible: the worklist holds max_items indices (a larger device-resident shard takes the plain recover
+  // path), recovered addresses are not wanted, groups are bound
+  const bool known_ok = (e->p.flags & IBFT_FLAG_KEY_CACHE) && d_recovered == nullptr && d_groups != nullptr && worklist != nullptr &&
+                        cnt <= L->cap_items;
+  // ... and its latency form: one-warp CTAs spread a round over all SMs, and whatever the verification does not accept is
+  // recovered by the four-lane kernel in worklist mode (short payloads only: its helper warp hashes for 24 signatures)
+  const bool small_batch = cnt <= (uint32_t)e->sm_count * 32u * 8u;
   if (path == IBFT_PATH_AUTO) {
 #if IBFT_WC > 0
+    // with learned keys, verifying against the validator's comb table (51 additions, no doubling) beats every recover kernel at
+    // every batch size -- also the four-lane one: the known-key pass goes first, the recover kernels take what it leaves over
+    if (known_ok) path = IBFT_PATH_THREAD;
+    else
     // long payloads (ROUND_CHANGE messages with their certificates: up to 909 KB of signed bytes each): the helper warp of the
     // latency kernels hashes for three (or 24) signatures one after the other, which serialises the sponges that dominate such a
     // batch -- one thread per signature hashes them all in parallel (config 4, 10,000 x 909 KB: 156 ms -> see DESIGN.md §6)
@@ -2035,8 +2138,7 @@ static int launch_recover(ibft_engine* e, lane* L, const ibft_sig_item* d_items,
     CU(cudaMemsetAsync(d_bitmap + (lo >> 5), 0, (size_t)((hi + 31) / 32 - (lo >> 5)) * 4, st));  // verdict bits are OR-ed in
     k_recover_qsplit<<<blocks, 128, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                              e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink, nullptr);
-  } else if (path == IBFT_PATH_SPLIT && (e->p.flags & IBFT_FLAG_KEY_CACHE) && d_recovered == nullptr && d_groups != nullptr &&
-             worklist != nullptr && cnt <= L->cap_items) {
+  } else if (path == IBFT_PATH_SPLIT && known_ok) {
     // known-key latency path: verify against the learned keys, then recover whatever was not accepted (worklist; the second
     // launch finds it empty -- and returns at once -- when every signature of the round verified)
     uint32_t blocks = (cnt + IBFT_SPLIT_SIGS - 1) / IBFT_SPLIT_SIGS;
@@ -2064,25 +2166,35 @@ static int launch_recover(ibft_engine* e, lane* L, const ibft_sig_item* d_items,
                                                          e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink);
   } else
 #if IBFT_WC > 0
-  if ((e->p.flags & IBFT_FLAG_KEY_CACHE) && d_recovered == nullptr && d_groups != nullptr && L->d_worklist != nullptr &&
-      cnt <= L->cap_items) {  // the worklist holds max_items indices: a larger device-resident shard takes the plain recover path
+  if (known_ok) {
     // key-registry path (one thread per signature, any batch size): verify what can be verified, then recover the rest from
     // the worklist (dense second launch; the threads beyond the worklist's length leave at once)
-    uint32_t blocks = (cnt + IBFT_BLOCK - 1) / IBFT_BLOCK;
     // device-resident callers may use different streams: launches sharing a worklist are ordered on the device
     CU(cudaStreamWaitEvent(st, L->wl_ev[worklist_index & 3u], 0));
     CU(cudaMemsetAsync(worklist, 0, 4, st));
-    k_verify_known<<<blocks, IBFT_BLOCK, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
-                                                  e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink, worklist);
+    if (small_batch) {
+      k_verify_known<32><<<(cnt + 31) / 32, 32, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
+                                                        e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink, worklist);
+    } else {
+      k_verify_known<IBFT_BLOCK><<<(cnt + IBFT_BLOCK - 1) / IBFT_BLOCK, IBFT_BLOCK, 0, st>>>(
+          d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots, e->p.max_table_slots, d_bitmap, d_status, e->d_ctable, sink,
+          worklist);
+    }
     e->launches++;
     CU(cudaGetLastError());
-    k_recover<IBFT_BLOCK><<<blocks, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
-                                                         e->d_slots, e->p.max_table_slots, d_bitmap, nullptr, nullptr, e->d_ctable, sink,
-                                                         worklist);
+    if (small_batch && arena_len / cnt <= 256) {
+      k_recover_qsplit<<<(cnt + IBFT_QSPLIT_SIGS - 1) / IBFT_QSPLIT_SIGS, 128, 0, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups,
+                                                                                    e->d_slots, e->p.max_table_slots, d_bitmap, nullptr, nullptr,
+                                                                                    e->d_ctable, sink, worklist);
+    } else {
+      k_recover<IBFT_BLOCK><<<(cnt + IBFT_BLOCK - 1) / IBFT_BLOCK, IBFT_BLOCK, IBFT_BLOCK * IBFT_RTAB_WORDS * 4, st>>>(
+          d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots, e->p.max_table_slots, d_bitmap, nullptr, nullptr, e->d_ctable,
+          sink, worklist);
+    }
     CU(cudaEventRecord(L->wl_ev[worklist_index & 3u], st));
   } else
 #endif
-  if (cnt <= (uint32_t)e->sm_count * 32u * 8u) {  // small batch: one-warp CTAs
+  if (small_batch) {  // one-warp CTAs
     uint32_t blocks = (cnt + 31) / 32;
     k_recover<32><<<blocks, 32, 32 * IBFT_RTAB_WORDS * 4, st>>>(d_items, n, d_arena, arena_len, lo, hi, d_groups, n_groups, e->d_slots,
                                          e->p.max_table_slots, d_bitmap, d_recovered, d_status, e->d_ctable, sink, nullptr);
@@ -2201,6 +2313,8 @@ static int submit_locked(ibft_engine* e, lane* L, const ibft_sig_item* items, ui
     else (void)cudaGetLastError();
     CU(cudaEventRecord(L->lat_ev[4], st));  // arena / groups uploads of this call
     const uint32_t per = ((n + 3) / 4 + IBFT_SPLIT_SIGS - 1) / IBFT_SPLIT_SIGS * IBFT_SPLIT_SIGS;
+    // with a key registry the pieces go through the known-key pass (one-warp CTAs) + worklist; without, chain + helper warps
+    const int piece_path = ((e->p.flags & IBFT_FLAG_KEY_CACHE) && !recovered_out && n_groups && L->d_worklist) ? IBFT_PATH_THREAD : IBFT_PATH_SPLIT;
     for (uint32_t c = 0; c < 4; c++) {
       uint32_t lo = std::min(n, c * per), hi = std::min(n, lo + per);
       if (hi <= lo) break;
@@ -2213,7 +2327,7 @@ static int submit_locked(ibft_engine* e, lane* L, const ibft_sig_item* items, ui
       CU(cudaStreamWaitEvent(ls, L->lat_ev[4], 0));
       CU(cudaMemcpyAsync(L->d_items + lo, src, (size_t)(hi - lo) * sizeof(ibft_sig_item), cudaMemcpyHostToDevice, ls));
       rc = launch_recover(e, L, L->d_items, n, L->d_arena, arena_len, lo, hi, n_groups ? L->d_groups : nullptr, n_groups, L->d_bitmap,
-                          recovered_out ? L->d_recovered : nullptr, ls, L->d_status, IBFT_PATH_SPLIT, sink, c);
+                          recovered_out ? L->d_recovered : nullptr, ls, L->d_status, piece_path, sink, c);
       if (rc != IBFT_OK) return rc;
       CU(cudaEventRecord(L->lat_ev[c], ls));
       CU(cudaStreamWaitEvent(st, L->lat_ev[c], 0));

@@ -534,14 +534,23 @@ IBFT_HD bool known_chain_finish(jac acc, bool g_inf, const fe& gx, const fe& gy,
   return same && ((py.v[0] & 1u) == (uint32_t)ri.v);
 }
 
-// the table {1..128}*Q of one validator (affine, 16 words per entry), by repeated addition; each entry normalised with its own
-// inversion (built once per validator, off the hot path)
-IBFT_HD void build_keytab(const aff& Q, uint32_t* out) {
+// One comb position of a validator's key table: m * 2^(8 pos) * Q for m = 1..128 (affine, 16 words per entry), by 8*pos doublings
+// and repeated addition; each entry normalised with its own inversion (built once per validator, off the hot path).
+IBFT_HD void build_keytab_pos(const aff& Q, int pos, uint32_t* out) {
   jac P;
   P.x = Q.x; P.y = Q.y; P.z = fe_from_u32(1); P.inf = false;
+  aff B = Q;
+  if (pos > 0) {
+    IBFT_ROLLED
+    for (int t = 0; t < IBFT_WQ * pos; t++) P = jac_double(P);
+    fe zi = IBFT_FE_INV(P.z), zi2 = fe_sqr(zi);
+    B.x = fe_normalize(fe_mul(P.x, zi2));
+    B.y = fe_normalize(fe_mul(P.y, fe_mul(zi2, zi)));
+    P.x = B.x; P.y = B.y; P.z = fe_from_u32(1);
+  }
   IBFT_ROLLED
   for (int m = 0; m < IBFT_KEYTAB_ENTRIES; m++) {
-    if (m) P = jac_add_affine(P, Q.x, Q.y);  // the first addition is a doubling (handled by the adder)
+    if (m) P = jac_add_affine(P, B.x, B.y);  // the first addition is a doubling (handled by the adder)
     fe x = fe_zero(), y = fe_zero();
     if (!P.inf && !fe_is_zero(P.z)) {
       fe zi = IBFT_FE_INV(P.z), zi2 = fe_sqr(zi);
@@ -551,6 +560,12 @@ IBFT_HD void build_keytab(const aff& Q, uint32_t* out) {
 #pragma unroll
     for (int i = 0; i < 8; i++) { out[16 * m + i] = x.v[i]; out[16 * m + 8 + i] = y.v[i]; }
   }
+}
+// the whole table of one validator (IBFT_KEYTAB_WORDS words)
+IBFT_HD void build_keytab(const aff& Q, uint32_t* out) {
+  IBFT_ROLLED
+  for (int pos = 0; pos < IBFT_KEYTAB_POSITIONS; pos++)
+    build_keytab_pos(Q, pos, out + (size_t)pos * IBFT_KEYTAB_ENTRIES * IBFT_GTAB_ENTRY_WORDS);
 }
 #endif
 

@@ -228,8 +228,9 @@ int emul_verify_item_known(const ibft_sig_item* it, const uint8_t* arena, size_t
   aff Q;
   Q.x = fe_from_be(key64);
   Q.y = fe_from_be(key64 + 32);
-  std::vector<uint32_t> kt((size_t)IBFT_KEYTAB_ENTRIES * 16);
+  std::vector<uint32_t> kt(IBFT_KEYTAB_WORDS);  // the validator's comb: 17 positions x 128 entries
   build_keytab(Q, kt.data());
+  G.host_pos = emul_pos_entry;  // the generator's per-position comb entries are computed on demand here
   gtab_view Qt{kt.data()};
   uint32_t rtab[IBFT_RTAB_WORDS];
   rtab_view T{rtab, 1};

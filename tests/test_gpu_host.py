@@ -37,8 +37,9 @@ def oracle_backend(vs_by_height, current_height, proposer_of, node_id=b""):
                      is_valid_proposal_hash=is_valid_proposal_hash, is_proposer=proposer_of, id=lambda: node_id)
 
 
-def gpu_ctx(proposer_of, node_id=b""):
-    params = host.EngineParams(0, 1 << 14, 1 << 24, 32, 8, 4096, 0)
+def gpu_ctx(proposer_of, node_id=b"", flags=0):
+    """flags = 1: the verifier's engine keeps a key registry (IBFT_FLAG_KEY_CACHE) -- same decisions, by construction"""
+    params = host.EngineParams(0, 1 << 14, 1 << 24, 32, 8, 4096, flags)
     return host.HostContext("gpu", {"is_proposer": proposer_of}, node_id, params)
 
 
@@ -58,7 +59,8 @@ def make_round(n, height, rnd, seed=21):
     return vs, raw, ph, pp, prepares, commits
 
 
-def test_commit_round_batched_and_serial_match_oracle():
+@pytest.mark.parametrize("flags", [0, 1], ids=["recover", "key_registry"])
+def test_commit_round_batched_and_serial_match_oracle(flags):
     n, height = 40, 1_000_000
     vs, raw, ph, pp, prepares, commits = make_round(n, height, 0)
     outsider = wl.privkey(5000, 1)
@@ -74,7 +76,7 @@ def test_commit_round_batched_and_serial_match_oracle():
     for batching in (True, False):
         o = L.IBFT(oracle_backend({height: set(vs.addrs)}, height, proposer_of), L.ValidatorManager(lambda h: dict(zip(vs.addrs, vs.powers))))
         o.vm.init(height)
-        c = gpu_ctx(proposer_of)
+        c = gpu_ctx(proposer_of, flags=flags)
         c.set_batching(batching)
         assert c.set_validators(height, vs.addrs, vs.powers) == 0
         for x in (o.state,):
@@ -93,13 +95,14 @@ def test_commit_round_batched_and_serial_match_oracle():
         c.close()
 
 
-def test_ingress_prepare_flow_and_single_calls():
+@pytest.mark.parametrize("flags", [0, 1], ids=["recover", "key_registry"])
+def test_ingress_prepare_flow_and_single_calls(flags):
     n, height = 24, 77
     vs, raw, ph, pp, prepares, commits = make_round(n, height, 0, seed=22)
     proposer_of = lambda a, h, r: a == vs.addrs[0]  # noqa: E731
     o = L.IBFT(oracle_backend({height: set(vs.addrs)}, height, proposer_of), L.ValidatorManager(lambda h: dict(zip(vs.addrs, vs.powers))))
     o.vm.init(height)
-    c = gpu_ctx(proposer_of)
+    c = gpu_ctx(proposer_of, flags=flags)
     assert c.set_validators(height, vs.addrs, vs.powers) == 0
     o.state.view = ip.View(height, 0)
     c.set_state(height, 0, L.NEW_ROUND, None)
@@ -121,7 +124,7 @@ def test_ingress_prepare_flow_and_single_calls():
     assert c.num_messages(height, 0, ip.PREPARE) == o.messages.num_messages(ip.View(height, 0), ip.PREPARE) == len(prepares) - 3
     assert c.signal_count() == len(o.messages.signals)
     # fresh context: the same bulk ingress is ONE launch
-    c2 = gpu_ctx(proposer_of)
+    c2 = gpu_ctx(proposer_of, flags=flags)
     assert c2.set_validators(height, vs.addrs, vs.powers) == 0
     c2.set_state(height, 0, L.NEW_ROUND, None)
     c2.add_messages([enc(m) for m in inbound])
@@ -145,7 +148,8 @@ def test_ingress_prepare_flow_and_single_calls():
     c2.close()
 
 
-def test_round_change_with_nested_certificates_dedup():
+@pytest.mark.parametrize("flags", [0, 1], ids=["recover", "key_registry"])
+def test_round_change_with_nested_certificates_dedup(flags):
     """Config-4 shape at small scale: every ROUND_CHANGE embeds the same prepared certificate: the nested
     sender signatures are verified once each (dedup), in the same launch as nothing else."""
     n, height = 16, 9
@@ -165,7 +169,7 @@ def test_round_change_with_nested_certificates_dedup():
     proposer_of = lambda a, h, r: a == vs.addrs[(h + r) % n] if False else (a == vs.addrs[0] and r == 0)  # noqa: E731
     o = L.IBFT(oracle_backend({height: set(vs.addrs)}, height, proposer_of), L.ValidatorManager(lambda h: dict(zip(vs.addrs, vs.powers))))
     o.vm.init(height)
-    c = gpu_ctx(proposer_of)
+    c = gpu_ctx(proposer_of, flags=flags)
     assert c.set_validators(height, vs.addrs, vs.powers) == 0
     o.state.view = view1
     c.set_state(height, 1, L.NEW_ROUND, None)

@@ -44,14 +44,18 @@ def test_learn_then_verify_gives_the_golden_bitmap(name):
         bm4, _, rec4 = plain.verify_batch(items[:500], d["arena"], groups, want_recovered=True)
         plain.close()
         assert np.array_equal(bm3, bm4) and np.array_equal(rec3, rec4)
-        # a new validator set empties the registry
-        eng.set_validators(0, int(d["meta"][2]) + 1, d["addrs"], d["powers"])
+        # a validator set of OTHER addresses starts with an empty registry (keys are carried over by address only)
+        strangers = np.frombuffer(b"".join(wl.address_of(wl.privkey(78, i)) for i in range(8)), np.uint8).reshape(8, 20)
+        eng.set_validators(0, int(d["meta"][2]) + 1, strangers, None)
         assert eng.refresh_key_tables() == 0
         with pytest.raises(ib.EngineError):                                 # the old descriptors name the replaced height
             eng.verify_batch(items, d["arena"], groups)
+        eng.set_validators(0, int(d["meta"][2]) + 2, d["addrs"], d["powers"])
+        assert eng.refresh_key_tables() == 0                                # nothing to carry from the strangers' table
         groups = groups_for(eng, len(d["groups"]))
         bm5, _, _ = eng.verify_batch(items, d["arena"], groups)
         assert np.array_equal(bm5, d["bitmap"])
+        assert eng.refresh_key_tables() == known                            # learned again
     finally:
         eng.close()
 
@@ -104,7 +108,8 @@ def test_rejected_verifications_fall_back_to_recovery_exactly():
 
 
 def test_known_key_latency_path_on_a_10k_round():
-    """k_verify_split (+ k_recover_qsplit on the worklist): one mid-size round of KNOWN validators on the latency path.  Round 1
+    """k_verify_known<32> (+ k_recover_qsplit on the worklist): one mid-size round of KNOWN validators on the latency path (and the
+    same round through the chain + helper form k_verify_split, forced).  Round 1
     learns the keys through the recover kernels; round 2 -- same 10,000 seals incl. the 1 % adversarial ones, then fresh seals over
     another proposal hash -- is verified against the keys.  Bitmap, quorum results and voted sets bit-exact with the recover path."""
     d, items = load_fixture("config3.npz")
@@ -123,8 +128,13 @@ def test_known_key_latency_path_on_a_10k_round():
         launches = eng.launch_count()
         bm2, res2, _ = eng.verify_batch(seals, b"", groups)                 # known-key latency path
         assert np.array_equal(bm2, bm1) and res1.tobytes() == res2.tobytes()
-        # four pieces x (k_verify_split + worklist k_recover_qsplit) + k_quorum_reduce; no table rebuild
+        # four pieces x (k_verify_known + worklist k_recover_qsplit) + k_quorum_reduce; no table rebuild
         assert eng.launch_count() - launches == 9
+        for path in (ib.Engine.PATH_SPLIT, ib.Engine.PATH_THREAD):           # k_verify_split / one chunk of k_verify_known
+            eng.set_recover_path(path)
+            bm3, res3, _ = eng.verify_batch(seals, b"", groups)
+            assert np.array_equal(bm3, bm1) and res1.tobytes() == res3.tobytes()
+        eng.set_recover_path(ib.Engine.PATH_AUTO)
         bmp, resp, _ = plain.verify_batch(seals, b"", groups)
         assert np.array_equal(bm2, bmp) and res2.tobytes() == resp.tobytes()
         for g in range(len(groups)):
@@ -148,6 +158,53 @@ def test_known_key_latency_path_on_a_10k_round():
         assert np.array_equal(a, b) and ra.tobytes() == rb.tobytes()
         want = co.verify_batch(fresh, b"", tables=[d["addrs"]], group_table=[0] * len(groups), n_threads=8)
         assert np.array_equal(a, want)
+    finally:
+        eng.close()
+        plain.close()
+
+
+def test_keys_carry_over_to_the_next_height():
+    """A key belongs to an address, not to a height: ibft_set_validators carries the finished comb tables over from the donor table
+    (the previous height's slot, or the slot's own previous content) for every address that is still a validator.  Verdicts,
+    quorum and voted sets stay those of a plain engine; the carried validators are verified without a single recovery."""
+    d, items = load_fixture("config2.npz")
+    h = int(d["meta"][2])
+    addrs, powers = d["addrs"], d["powers"]
+    eng = make_engine(key_cache=True)
+    plain = make_engine()
+    try:
+        eng.set_validators(0, h, addrs, powers)
+        bm1, _, _ = eng.verify_batch(items, d["arena"], groups_for(eng, len(d["groups"])))
+        assert np.array_equal(bm1, d["bitmap"])
+        known = eng.refresh_key_tables()
+        assert 0 < known <= len(addrs)
+        ok_signers = {bytes(items[i]["signer"]) for i in range(len(items)) if (int(bm1[i >> 5]) >> (i & 31)) & 1}
+        # next height, ANOTHER slot: three validators gone, two new ones (never seen), order reversed, other voting powers
+        newcomers = np.frombuffer(b"".join(wl.address_of(wl.privkey(77, i)) for i in range(2)), np.uint8).reshape(2, 20)
+        addrs2 = np.ascontiguousarray(np.concatenate([addrs[3:][::-1], newcomers]))
+        powers2 = np.ascontiguousarray(np.concatenate([powers[3:][::-1], powers[:2]]))
+        carried = len({bytes(a) for a in addrs2} & ok_signers)
+        for e in (eng, plain):
+            e.set_validators(1, h + 1, addrs2, powers2)
+        assert eng.refresh_key_tables() == known + carried
+        g2 = groups_for(eng, len(d["groups"]), slot=1)
+        launches = eng.launch_count()
+        a, ra, _ = eng.verify_batch(items, d["arena"], g2)
+        assert eng.launch_count() - launches == 3          # known-key pass + worklist pass + quorum: nothing to learn, nothing to build
+        b, rb, _ = plain.verify_batch(items, d["arena"], groups_for(plain, len(d["groups"]), slot=1))
+        assert np.array_equal(a, b) and ra.tobytes() == rb.tobytes()
+        want = co.verify_batch(items, d["arena"].tobytes(), tables=[addrs2], group_table=[0] * len(d["groups"]), n_threads=8)
+        assert np.array_equal(a, want)
+        for g in range(len(g2)):
+            assert np.array_equal(eng.voted_bitmap(g, len(addrs2)), plain.voted_bitmap(g, len(addrs2)))
+        # the same slot re-used for the height after that: the donor is the slot's own previous content
+        eng.set_validators(1, h + 2, addrs2, powers2)
+        assert eng.refresh_key_tables() == known + carried
+        c, rc, _ = eng.verify_batch(items, d["arena"], groups_for(eng, len(d["groups"]), slot=1))
+        assert np.array_equal(c, a) and rc.tobytes() == ra.tobytes()
+        # slot 0 still answers for its own height from its own registry
+        z, _, _ = eng.verify_batch(items, d["arena"], groups_for(eng, len(d["groups"])))
+        assert np.array_equal(z, d["bitmap"])
     finally:
         eng.close()
         plain.close()

@@ -18,17 +18,31 @@ nmax = max(sizes)
 items = np.ascontiguousarray(np.tile(base, (nmax + len(base) - 1) // len(base))[:nmax])
 gold = np.unpackbits(d["bitmap"].view(np.uint8), bitorder="little")[: len(base)]
 gold = np.tile(gold, (nmax + len(base) - 1) // len(base))[:nmax]
-eng = ib.Engine(device=0, max_items=max(nmax, 1024), max_payload_bytes=1 << 22, max_groups=8, max_table_slots=2, max_validators=16384)
+KEY_CACHE = os.environ.get("KEY_CACHE") == "1"   # known-key paths: the keys are learned by a first pass over the whole fixture
+eng = ib.Engine(device=0, max_items=max(nmax, len(base), 1024), max_payload_bytes=1 << 22, max_groups=8, max_table_slots=2, max_validators=16384,
+                key_cache=KEY_CACHE)
 eng.set_validators(0, int(d["meta"][2]), d["addrs"], d["powers"])
 eng.bind_groups(eng.groups(len(d["groups"])))
 t_items = torch.from_numpy(items.view(np.uint8).reshape(-1, 128)).cuda()
 t_arena = torch.from_numpy(np.ascontiguousarray(d["arena"])).cuda()
 st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
+if KEY_CACHE:
+    t_all = torch.from_numpy(base.view(np.uint8).reshape(-1, 128)).cuda()
+    t_bm0 = torch.zeros((len(base) + 31) // 32, dtype=torch.int32, device="cuda")
+    eng.verify_device(t_all.data_ptr(), len(base), t_arena.data_ptr(), t_arena.numel(), 0, len(base), t_bm0.data_ptr(), 0, st.cuda_stream)
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(st)
+    known = eng.refresh_key_tables()
+    t1.record(st)
+    torch.cuda.synchronize()
+    print(json.dumps({"keys_known": known, "table_build_ms_incl_sync": round(t0.elapsed_time(t1), 2)}))
 for n in sizes:
     words = (n + 31) // 32
     row = {"items": n}
-    for name, path in (("thread", ib.Engine.PATH_THREAD), ("quad", ib.Engine.PATH_QUAD), ("split", ib.Engine.PATH_SPLIT), ("qsplit", ib.Engine.PATH_QSPLIT)):
+    for name, path in (("auto", ib.Engine.PATH_AUTO), ("thread", ib.Engine.PATH_THREAD), ("quad", ib.Engine.PATH_QUAD), ("split", ib.Engine.PATH_SPLIT),
+                       ("qsplit", ib.Engine.PATH_QSPLIT)):
         eng.set_recover_path(path)
         t_bm = torch.zeros(words, dtype=torch.int32, device="cuda")
         for _ in range(3):
