@@ -38,7 +38,10 @@ type Engine struct {
 type Params struct {
 	Device, MaxItems, MaxPayloadBytes, MaxGroups, MaxTableSlots, MaxValidators uint32
 	// KeyCache sets IBFT_FLAG_KEY_CACHE: the engine learns every validator's public key from its first valid signature and
-	// verifies (instead of recovering) that validator's later signatures; verdicts are identical.
+	// verifies (instead of recovering) that validator's later signatures against a per-validator comb table in device memory
+	// (136 KiB per validator and resident table: 1.39 GB for 10,000 validators); verdicts are identical.  SetValidators for
+	// the next height carries the tables over by address, so only newcomers are ever recovered again.  ~2.7x the recover
+	// path's throughput, 0.48 ms instead of 0.8 ms for a 10k-validator COMMIT round (DESIGN.md section 3.1c).
 	KeyCache bool
 }
 
