@@ -33,4 +33,11 @@ entries reproduce the published k, r, s bit for bit; OpenSSL agrees on the verif
 High-s is accepted everywhere on the recover path (low-s is a transaction rule, EIP-2), and so it is here.  The two places
 this engine is stricter -- V outside {0,1}, and nonce points with x >= n (probability 2^-128, not targetable) -- can only be
 reached by a Byzantine sender and only make that sender's own message invalid on this node.
+
+CPU ARMS FOR THE BENCH (all test / bench infrastructure, none on the product path).  ``c/ibft_oracle.c`` is the plain port and
+THE checker (4x64-bit limbs, fixed 4-bit windows over 256 doublings, Fermat inversions, no endomorphism -- deliberately unlike
+the CUDA code).  ``c/fast_recover.c`` is a tuned arm (GLV + wNAF, lazily reduced field, binary inversions; ~1.8x the plain port
+per core) and ``c/ossl_recover.c`` an OpenSSL-3 arm (slower than the port on this curve); both are checked bit for bit against
+the plain port in tests/test_oracle_crypto.py and against the golden bitmap in every bench run that times them.  bench.py's
+``cpu_baseline.value`` and ``--impl reference`` use the fastest arm that reproduced the golden verdicts on the host.
 """

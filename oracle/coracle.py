@@ -187,3 +187,41 @@ def ossl_verify_batch(items: np.ndarray, arena: bytes = b"", table=None, n_threa
                         ctypes.c_size_t(len(arena)), None if tab is None else tab.ctypes.data_as(ctypes.c_void_p),
                         ctypes.c_uint32(0 if tab is None else len(tab)), ctypes.c_int(n_threads), bitmap.ctypes.data_as(ctypes.c_void_p))
     return bitmap
+
+
+# ---- tuned CPU arm: GLV + wNAF + binary inversions (oracle/c/fast_recover.c); bench.py's fastest CPU baseline, cross-checked
+# against the plain port in tests/test_oracle_crypto.py
+_FAST = None
+
+
+def fast_lib():
+    global _FAST
+    if _FAST is None:
+        build()
+        so = os.path.join(_HERE, "liboracle_fast.so")
+        src = os.path.join(_HERE, "c", "fast_recover.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle_fast.so"])
+        _FAST = ctypes.CDLL(so)
+        _FAST.fast_ecrecover_address.restype = ctypes.c_int
+    return _FAST
+
+
+def fast_ecrecover_address(digest: bytes, r: bytes, s: bytes, v: int):
+    """address (20 bytes) or None -- same contract as ecrecover_address of the plain port"""
+    out = ctypes.create_string_buffer(20)
+    ok = fast_lib().fast_ecrecover_address(digest, r, s, ctypes.c_uint8(v), out)
+    return out.raw if ok else None
+
+
+def fast_verify_batch(items: np.ndarray, arena: bytes = b"", table=None, n_threads: int = 1) -> np.ndarray:
+    L = fast_lib()
+    items = np.ascontiguousarray(items)
+    n = len(items)
+    bitmap = np.zeros((n + 31) // 32, dtype=np.uint32)
+    arena_np = np.frombuffer(arena, dtype=np.uint8) if arena else np.zeros(1, dtype=np.uint8)
+    tab = None if table is None else np.ascontiguousarray(table, dtype=np.uint8).reshape(-1, 20)
+    L.fast_verify_batch(items.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(n), arena_np.ctypes.data_as(ctypes.c_void_p),
+                        ctypes.c_size_t(len(arena)), None if tab is None else tab.ctypes.data_as(ctypes.c_void_p),
+                        ctypes.c_uint32(0 if tab is None else len(tab)), ctypes.c_int(n_threads), bitmap.ctypes.data_as(ctypes.c_void_p))
+    return bitmap

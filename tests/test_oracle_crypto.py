@@ -154,3 +154,56 @@ def test_openssl_arm_matches_the_port_on_config2():
     items = np.ascontiguousarray(d["items"]).view(co.ITEM_DTYPE).reshape(-1)
     got = co.ossl_verify_batch(items, d["arena"].tobytes(), d["addrs"], 8)
     assert np.array_equal(got, d["bitmap"])
+
+
+def test_tuned_cpu_arm_matches_the_port():
+    """bench.py's tuned CPU arm (oracle/c/fast_recover.c: GLV + wNAF + lazily reduced 4x64-bit field, binary inversions) against the
+    plain port: the third-party vectors, 1,600 random / adversarial signatures (bit flips in r and s, flipped recovery id, foreign
+    digest, random r, out-of-range recovery ids, the high-s twin), range edges, and the config-2 fixture on 8 threads."""
+    import json
+    import os
+    import random
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    # the GLV constants, numerically: lambda^3 = 1 (mod n), beta^3 = 1 (mod p), lambda * G = (beta * Gx, Gy)
+    lam = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+    beta = 0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE
+    assert pow(lam, 3, ec.N) == 1 and pow(beta, 3, ec.P) == 1
+    assert ec.point_mul(lam, ec.G) == (beta * ec.GX % ec.P, ec.GY)
+    doc = json.load(open(os.path.join(here, "golden", "third_party_recover.json")))
+    for v in doc["recover"]:
+        dig, sig = bytes.fromhex(v["digest"]), bytes.fromhex(v["sig"])
+        if len(dig) != 32 or len(sig) != 65:
+            continue
+        got = co.fast_ecrecover_address(dig, sig[:32], sig[32:64], sig[64])
+        assert (got is not None and got.hex() == v["address"]) == v["valid"], v["name"]
+    rng = random.Random(99)
+    for i in range(1600):
+        d = rng.randrange(1, ec.N)
+        z = rng.randbytes(32)
+        sig = bytearray(co.sign_with_k(d, z, rng.randrange(1, ec.N), True))
+        mode = i % 8
+        if mode == 1:
+            sig[rng.randrange(64)] ^= 1 << rng.randrange(8)
+        elif mode == 2:
+            sig[64] ^= 1
+        elif mode == 3:
+            z = rng.randbytes(32)
+        elif mode == 4:
+            sig[:32] = rng.randbytes(32)
+        elif mode == 5:
+            sig[64] = rng.choice([2, 3, 27, 28, 255])
+        elif mode == 6:
+            sig[32:64] = (ec.N - int.from_bytes(sig[32:64], "big")).to_bytes(32, "big")
+            sig[64] ^= 1
+        want = co.ecrecover_address(z, bytes(sig))
+        assert co.fast_ecrecover_address(z, bytes(sig[:32]), bytes(sig[32:64]), sig[64]) == want, (i, mode)
+        if mode in (0, 6):
+            assert want == ec.privkey_to_address(d)
+    for r, s in ((0, 1), (1, 0), (ec.N, 1), (1, ec.N), (ec.N - 1, ec.N - 1), (1, 1), (2, 3), (2**256 - 1, 5), (7, 2**256 - 1)):
+        for v in (0, 1):
+            rb, sb = r.to_bytes(32, "big"), s.to_bytes(32, "big")
+            assert co.fast_ecrecover_address(b"\x11" * 32, rb, sb, v) == co.ecrecover_address(b"\x11" * 32, rb + sb + bytes([v]))
+    d = np.load(os.path.join(here, "golden", "config2.npz"))
+    items = np.ascontiguousarray(d["items"]).view(co.ITEM_DTYPE).reshape(-1)
+    assert np.array_equal(co.fast_verify_batch(items, d["arena"].tobytes(), d["addrs"], 8), d["bitmap"])
