@@ -868,7 +868,7 @@ def main():
         for _ in range(e2e_steps):
             bm_k, _, _ = eng_k.verify_batch(host_local, arena_host, groups)
         e2e_k = n_global * e2e_steps / (time.perf_counter() - t0)
-        # the 10,000-seal round on the known-key LATENCY path (k_verify_split + worklist k_recover_qsplit), host buffers in / out
+        # the 10,000-seal round on the known-key LATENCY path (k_verify_known<32> + worklist k_recover_qsplit), host buffers in / out
         lat_known = []
         for i in range(args.latency_reps + 5):
             t0 = time.perf_counter()
