@@ -365,3 +365,61 @@ def test_verify_known_key_is_equivalent_to_recovering_that_key(emul):
     for r, s, v in [(0, 1, 0), (1, 0, 0), (N, 1, 0), (1, N, 1), (ec.G[0], 1, 2)]:
         sg = r.to_bytes(32, "big") + s.to_bytes(32, "big") + bytes([v])
         assert run(wl.make_item(sg, bytes(20), 0, keccak256(b"x")), ec.G)[0] == 0
+
+
+def test_verify_known_comb_edge_digits_and_colliding_points(emul):
+    """The comb walk of ecdsa_verify_known on CONSTRUCTED scalars: half-scalars whose 8-bit Booth digits sit on the window edges
+    (0, +-1, 127, 128, 129, all-0x80 bytes, 2^127, 2^128 - 1), u1 = 0 (zero digest), and keys that make the generator stream and
+    the key stream meet in the adder (Q = G, -G, lambda*G, -lambda*G, 2G: P + P, P - P and a running sum at infinity).
+    A signature (r, s, z) is built FOR the chosen u1 = z/s, u2 = r/s: R = u1*G + u2*Q, r = R.x, s = r/u2, z = u1*s; it is valid by
+    construction, so the verification must accept and the recover path must yield exactly Q."""
+    import workloads as wl
+    lam = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+    zero = np.zeros(1, np.uint8)
+
+    def run(item, key):
+        rk = ctypes.c_int(0)
+        key64 = key[0].to_bytes(32, "big") + key[1].to_bytes(32, "big")
+        ok = emul.emul_verify_item_known(item.ctypes.data_as(ctypes.c_void_p), zero.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(0), B(key64),
+                                         ctypes.byref(rk))
+        return ok, rk.value
+
+    def craft(u1, u2, Q):
+        R = ec.point_add(ec.point_mul(u1, ec.G) if u1 else ec.INF, ec.point_mul(u2, Q))
+        if R == ec.INF or R[0] >= N or R[0] == 0:
+            return None
+        r = R[0]
+        s = r * pow(u2, -1, N) % N
+        z = u1 * s % N
+        if s == 0:
+            return None
+        return r.to_bytes(32, "big") + s.to_bytes(32, "big") + bytes([R[1] & 1]), z.to_bytes(32, "big")
+
+    all80 = int.from_bytes(b"\x80" * 16, "big")
+    halves = [0, 1, -1, 127, 128, -128, 129, 255, 256, 0x8000, all80, -all80, 2**127, 2**128 - 1, -(2**127) - 5, 0x7F80 << 64]
+    keys = [1, N - 1, lam, N - lam, 2, 0xC0FFEE]
+    built = 0
+    for i, d in enumerate(keys):
+        Q = ec.point_mul(d, ec.G)
+        addr = ec.pubkey_to_address(Q) if hasattr(ec, "pubkey_to_address") else None
+        for j in range(len(halves)):
+            k1, k2 = halves[j], halves[(j * 5 + i) % len(halves)]
+            g1, g2 = halves[(j * 3 + 1) % len(halves)], halves[(j * 7 + i + 2) % len(halves)]
+            u2 = (k1 + k2 * lam) % N
+            u1 = (g1 + g2 * lam) % N
+            if j % 4 == 0:
+                u1 = u2                      # with Q = +-G / +-lambda*G the two streams add the same (or opposite) points
+            if j % 4 == 1:
+                u1 = 0                       # zero digest: no generator term at all
+            if u2 == 0:
+                continue
+            c = craft(u1, u2, Q)
+            if c is None:
+                continue
+            sig, z = c
+            item = wl.make_item(sig, addr if addr else bytes(20), 0, z)
+            assert run(item, Q) == (1, 1), (d, j)
+            # the same signature against ANOTHER key never verifies, and agrees with "does recovery yield that key"
+            assert run(item, ec.point_mul(d + 7, ec.G)) == (0, 0), (d, j)
+            built += 1
+    assert built >= 60
