@@ -71,6 +71,30 @@ def rebase_shard(items: np.ndarray, arena: np.ndarray, lo: int, hi: int):
     return local, local_arena
 
 
+def open_peer_buffers(engine, world: int, rank: int, own_ptr: int, own_handle: bytes) -> list:
+    """Collective: exchange the CUDA IPC handles of the ranks' exchange buffers and map every peer's buffer on this rank's device
+    (engine.exchange_open).  Returns the per-rank device addresses (own_ptr at `rank`).  Either every rank succeeds or every rank
+    raises RuntimeError -- a rank that failed alone would leave the others waiting in their next collective; on failure the
+    mappings made so far are closed and the rank's own buffer is freed."""
+    handles = [None] * world
+    dist.all_gather_object(handles, own_handle)
+    opened, err = [], None
+    try:
+        for r in range(world):
+            opened.append(own_ptr if r == rank else engine.exchange_open(handles[r]))
+    except RuntimeError as ex:      # e.g. no peer access between two devices of this node
+        err = str(ex)
+    errs = [None] * world
+    dist.all_gather_object(errs, err)
+    if any(errs):
+        for r, p in enumerate(opened):
+            if r != rank:
+                engine.exchange_close(p)
+        engine.exchange_free(own_ptr)
+        raise RuntimeError("peer-memory exchange unavailable: " + "; ".join(f"rank {r}: {e}" for r, e in enumerate(errs) if e))
+    return opened
+
+
 class ShardedVerifier:
     """Device-side pipeline of one rank.  `engine` must hold the validator tables and have `groups` bound by this object.
 
@@ -121,10 +145,11 @@ class ShardedVerifier:
             self.h_out = torch.zeros(self.d_results.numel() + 4 * world * self.per + 4, dtype=torch.uint8).pin_memory()
             self.peer_ptrs = [self.xbuf_ptr]
             if world > 1:
-                handles = [None] * world
-                dist.all_gather_object(handles, handle)
-                self.peer_ptrs = [self.xbuf_ptr if r == rank else engine.exchange_open(handles[r]) for r in range(world)]
-                dist.barrier()
+                try:
+                    self.peer_ptrs = open_peer_buffers(engine, world, rank, self.xbuf_ptr, handle)
+                except RuntimeError:
+                    self.xbuf_ptr = 0
+                    raise
 
     def close(self):
         """unmap the peers' exchange buffers and free this rank's (p2p only; collective: every rank calls it)"""

@@ -125,3 +125,59 @@ def test_two_rank_gloo_config5_strong_scaling_pipeline(tmp_path):
         got = np.load(os.path.join(str(tmp_path), f"c5_{r}.npz"))
         assert np.array_equal(got["bitmap"], pin["bitmap"])
         assert np.array_equal(got["res"], pin["results"][:, :3])
+
+
+class _FakeExchangeEngine:
+    """stands in for Engine.exchange_open / _close / _free: 'maps' a handle to an address derived from it, or refuses"""
+
+    def __init__(self, refuse: bool):
+        self.refuse, self.closed, self.freed = refuse, [], []
+
+    def exchange_open(self, handle: bytes) -> int:
+        if self.refuse:
+            raise RuntimeError("cudaIpcOpenMemHandle: peer access is not supported between these two devices")
+        return 0x1000 + handle[0]
+
+    def exchange_close(self, p: int):
+        self.closed.append(p)
+
+    def exchange_free(self, p: int):
+        self.freed.append(p)
+
+
+def _worker_peers(rank, world, port, out_dir, failing_rank):
+    import json
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _FakeExchangeEngine(refuse=(rank == failing_rank))
+    own_ptr, handle = 0xA000 + rank, bytes([rank]) * 64
+    try:
+        ptrs = sharding.open_peer_buffers(eng, world, rank, own_ptr, handle)
+        res = {"ptrs": ptrs}
+    except RuntimeError as ex:
+        res = {"error": str(ex)}
+    res.update(closed=eng.closed, freed=eng.freed)
+    dist.barrier()          # every rank is still in step after the collective setup, whatever its outcome
+    with open(os.path.join(out_dir, f"peers_{rank}.json"), "w") as f:
+        json.dump(res, f)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("failing_rank", [-1, 1])
+def test_peer_buffer_setup_is_all_or_nothing(tmp_path, failing_rank):
+    """open_peer_buffers (the handle exchange of ShardedVerifier's peer-memory exchange): all ranks get the full address list, or --
+    when ONE rank cannot map a peer -- all ranks raise, release what they mapped and stay in step for the next collective."""
+    import json
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker_peers, args=(2, port, str(tmp_path), failing_rank), nprocs=2, join=True)
+    out = [json.load(open(os.path.join(str(tmp_path), f"peers_{r}.json"))) for r in range(2)]
+    if failing_rank < 0:
+        assert out[0]["ptrs"] == [0xA000, 0x1001] and out[1]["ptrs"] == [0x1000, 0xA001]
+        assert not any(o["closed"] or o["freed"] for o in out)
+    else:
+        assert all("rank 1" in o["error"] for o in out)
+        assert out[0]["closed"] == [0x1001] and out[0]["freed"] == [0xA000]      # rank 0 had mapped its peer: unmapped again
+        assert out[1]["closed"] == [] and out[1]["freed"] == [0xA001]
