@@ -263,6 +263,25 @@ int emul_verify_item_known(const ibft_sig_item* it, const uint8_t* arena, size_t
 }
 #endif
 
+#if IBFT_WC > 0
+// one comb position of a validator's key table (build_keytab_pos, the routine k_build_keytabs runs per (validator, position)):
+// out = 128 entries x (X || Y big-endian), entry m-1 = m * 2^(8 pos) * Q
+void emul_keytab_pos(const uint8_t* key64, int pos, uint8_t* out /* 128 * 64 bytes */) {
+  aff Q;
+  Q.x = fe_from_be(key64);
+  Q.y = fe_from_be(key64 + 32);
+  std::vector<uint32_t> kt((size_t)IBFT_KEYTAB_ENTRIES * 16);
+  build_keytab_pos(Q, pos, kt.data());
+  for (int m = 0; m < IBFT_KEYTAB_ENTRIES; m++) {
+    fe x, y;
+    for (int i = 0; i < 8; i++) { x.v[i] = kt[16 * m + i]; y.v[i] = kt[16 * m + 8 + i]; }
+    fe_to_be(x, out + 64 * m);
+    fe_to_be(y, out + 64 * m + 32);
+  }
+}
+int emul_keytab_positions() { return IBFT_KEYTAB_POSITIONS; }
+
+#endif
 void emul_keccak256(const uint8_t* d, uint32_t n, uint8_t* out) { keccak256_bytes(d, n, out); }
 
 // op codes = IBFT_DBG_* of include/ibft_verify.h

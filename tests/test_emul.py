@@ -423,3 +423,21 @@ def test_verify_known_comb_edge_digits_and_colliding_points(emul):
             assert run(item, ec.point_mul(d + 7, ec.G)) == (0, 0), (d, j)
             built += 1
     assert built >= 60
+
+
+def test_key_comb_table_entries_are_the_stated_multiples(emul):
+    """build_keytab_pos (what k_build_keytabs runs per (validator, position)): entry m-1 of position j is m * 2^(8j) * Q, affine and
+    canonical -- checked against the big-int oracle for the first, a middle and the last position."""
+    assert emul.emul_keytab_positions() == 17
+    d = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % N
+    Q = ec.point_mul(d, ec.G)
+    key64 = Q[0].to_bytes(32, "big") + Q[1].to_bytes(32, "big")
+    for pos in (0, 7, 16):
+        out = ctypes.create_string_buffer(128 * 64)
+        emul.emul_keytab_pos(B(key64), pos, out)
+        base = ec.point_mul(pow(2, 8 * pos, N), Q)
+        P = base
+        for m in range(1, 129):
+            e = out.raw[64 * (m - 1): 64 * m]
+            assert (int.from_bytes(e[:32], "big"), int.from_bytes(e[32:], "big")) == P, (pos, m)
+            P = ec.point_add(P, base)
